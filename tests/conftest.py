@@ -1,0 +1,41 @@
+import json
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (HERE, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+class Golden:
+    """The reference's own golden vectors, committed under tests/golden/ (see make_golden.py)."""
+
+    def __init__(self):
+        with open(os.path.join(HERE, "golden", "reference_vectors.json")) as f:
+            self.meta = json.load(f)["vectors"]
+        with open(os.path.join(HERE, "golden", "reference_vectors.bin"), "rb") as f:
+            self.blob = f.read()
+
+    def vectors(self, fmt=None, errors=None):
+        for v in self.meta:
+            if fmt is not None and v["format"] != fmt:
+                continue
+            if errors is not None and (("error" in v) != errors):
+                continue
+            yield v
+
+    def compressed(self, v):
+        return self.blob[v["offset"]: v["offset"] + v["length"]]
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return Golden()

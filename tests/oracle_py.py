@@ -1,0 +1,134 @@
+"""ctypes binding of the CPU oracle (oracle/liblzma_oracle.so) -- TEST INFRASTRUCTURE ONLY.
+
+Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs.  The product package (lzma_rs_b200) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_SO = os.path.join(ORACLE_DIR, "liblzma_oracle.so")
+
+KIND_NAMES = {0: "Ok", 1: "IoError", 2: "HeaderTooShort", 3: "LzmaError", 4: "XzError"}
+
+
+class _Err(C.Structure):
+    _fields_ = [("kind", C.c_int), ("msg", C.c_char * 320)]
+
+
+class _Opt(C.Structure):
+    _fields_ = [("unpacked_mode", C.c_int), ("has_provided", C.c_int), ("provided", C.c_uint64),
+                ("has_memlimit", C.c_int), ("memlimit", C.c_uint64)]
+
+
+class _Res(C.Structure):
+    _fields_ = [("out", C.POINTER(C.c_uint8)), ("out_len", C.c_size_t), ("consumed", C.c_size_t), ("err", _Err)]
+
+
+def build():
+    """Compile the oracle if the .so is missing or stale."""
+    src = os.path.join(ORACLE_DIR, "lzma_oracle.c")
+    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.lzo_lzma_decompress.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Opt), C.POINTER(_Res)]
+        _lib.lzo_lzma2_decompress.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Res)]
+        _lib.lzo_xz_decompress.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Res)]
+        _lib.lzo_result_free.argtypes = [C.POINTER(_Res)]
+        _lib.lzo_error_display.argtypes = [C.POINTER(_Err), C.c_char_p, C.c_size_t]
+        _lib.lzo_decompress_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_int]
+        _lib.lzo_crc32.argtypes = [C.c_char_p, C.c_size_t]
+        _lib.lzo_crc32.restype = C.c_uint32
+        _lib.lzo_crc64.argtypes = [C.c_char_p, C.c_size_t]
+        _lib.lzo_crc64.restype = C.c_uint64
+    return _lib
+
+
+class OracleResult:
+    """(output bytes handed to the sink, consumed input bytes, error kind, Display string)."""
+
+    def __init__(self, out, consumed, kind, msg, display):
+        self.out, self.consumed, self.kind, self.msg, self.display = out, consumed, kind, msg, display
+
+    @property
+    def ok(self):
+        return self.kind == 0
+
+    def __repr__(self):
+        return f"OracleResult(len={len(self.out)}, consumed={self.consumed}, kind={KIND_NAMES[self.kind]}, {self.display!r})"
+
+
+def _finish(res):
+    out = C.string_at(res.out, res.out_len) if res.out_len else b""
+    buf = C.create_string_buffer(400)
+    lib().lzo_error_display(C.byref(res.err), buf, 400)
+    r = OracleResult(out, res.consumed, res.err.kind, res.err.msg.decode(), buf.value.decode())
+    lib().lzo_result_free(C.byref(res))
+    return r
+
+
+def make_options(unpacked_mode=0, provided=None, memlimit=None):
+    """unpacked_mode: 0 ReadFromHeader, 1 ReadHeaderButUseProvided(provided), 2 UseProvided(provided)."""
+    o = _Opt()
+    o.unpacked_mode = unpacked_mode
+    o.has_provided = 0 if provided is None else 1
+    o.provided = 0 if provided is None else provided
+    o.has_memlimit = 0 if memlimit is None else 1
+    o.memlimit = 0 if memlimit is None else memlimit
+    return o
+
+
+def lzma_decompress(data, unpacked_mode=0, provided=None, memlimit=None):
+    res = _Res()
+    opt = make_options(unpacked_mode, provided, memlimit)
+    lib().lzo_lzma_decompress(bytes(data), len(data), C.byref(opt), C.byref(res))
+    return _finish(res)
+
+
+def lzma2_decompress(data):
+    res = _Res()
+    lib().lzo_lzma2_decompress(bytes(data), len(data), C.byref(res))
+    return _finish(res)
+
+
+def xz_decompress(data):
+    res = _Res()
+    lib().lzo_xz_decompress(bytes(data), len(data), C.byref(res))
+    return _finish(res)
+
+
+def crc32(data):
+    return lib().lzo_crc32(bytes(data), len(data))
+
+
+def crc64(data):
+    return lib().lzo_crc64(bytes(data), len(data))
+
+
+def decompress_batch(fmt, blob, in_off, out_off, nthreads):
+    """CPU-baseline batch driver.  blob: np.uint8 array; in_off/out_off: np.uint64 (n+1).
+    Returns (out np.uint8, out_len np.uint64, kinds np.int32, failed)."""
+    n = len(in_off) - 1
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+    out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+    out = np.empty(int(out_off[-1]), dtype=np.uint8)
+    out_len = np.zeros(n, dtype=np.uint64)
+    kinds = np.zeros(n, dtype=np.int32)
+    failed = lib().lzo_decompress_batch(fmt, blob.ctypes.data, in_off.ctypes.data, n, out.ctypes.data,
+                                        out_off.ctypes.data, out_len.ctypes.data, kinds.ctypes.data, nthreads)
+    return out, out_len, kinds, failed
