@@ -1,0 +1,197 @@
+/*
+ * lzma_b200.h -- C ABI of the B200-native many-stream LZMA / LZMA2 / XZ decoder.
+ *
+ * This is the drop-in boundary for the decode path of gendx/lzma-rs (reference @ 1f14478).
+ * The reference has NO FFI/plugin interface of its own: its boundary is three generic Rust
+ * free functions over io::BufRead / io::Write,
+ *
+ *     lzma_rs::lzma_decompress(input, output)                       src/lib.rs:44-49
+ *     lzma_rs::lzma_decompress_with_options(input, output, options) src/lib.rs:52-60
+ *     lzma_rs::lzma2_decompress(input, output)                      src/lib.rs:83-88
+ *     lzma_rs::xz_decompress(input, output)                         src/lib.rs:100-105
+ *
+ * so every entry point below is what a Rust shim for those functions binds (see
+ * INTEGRATION.md and rust/lzma_b200/src/lib.rs): plain pointers and sizes, no C++ or torch
+ * types, never throws, never aborts, no callbacks.  Exported by
+ * lzma_rs_b200/liblzma_b200.so (sm_100a only; there is no CPU fallback -- every stream is
+ * decoded by the CUDA kernels, and every call fails with LZB_RC_NO_DEVICE without a GPU).
+ */
+#ifndef LZMA_B200_H
+#define LZMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZB_ABI_VERSION 1
+
+/* ---- call-level return codes (infrastructure; distinct from per-stream decode status) ---- */
+enum {
+    LZB_RC_OK = 0,
+    LZB_RC_BAD_ARG = -1,
+    LZB_RC_NO_DEVICE = -2, /* no CUDA device / driver: the product has no CPU path */
+    LZB_RC_CUDA = -3,      /* a CUDA call failed; see lzb_last_error() */
+    LZB_RC_OOM = -4
+};
+
+/* ---- stream formats = the three reference entry points ---- */
+typedef enum lzb_format {
+    LZB_FMT_LZMA = 0,  /* .lzma "alone": lzma_decompress[_with_options], lib.rs:44-60 */
+    LZB_FMT_LZMA2 = 1, /* raw LZMA2:     lzma2_decompress,               lib.rs:83-88 */
+    LZB_FMT_XZ = 2     /* .xz:           xz_decompress,                   lib.rs:100-105 */
+} lzb_format;
+
+/* ---- decompress::Options (src/decode/options.rs:3-43), passed by pointer; NULL = default ---- */
+enum { LZB_UNPACKED_READ_FROM_HEADER = 0, LZB_UNPACKED_READ_HEADER_BUT_USE_PROVIDED = 1, LZB_UNPACKED_USE_PROVIDED = 2 };
+typedef struct lzb_options {
+    uint8_t unpacked_mode; /* UnpackedSize variant */
+    uint8_t has_provided;  /* the variant's Option<u64> is Some */
+    uint8_t has_memlimit;  /* memlimit: Option<usize> is Some */
+    uint8_t reserved[5];
+    uint64_t provided;
+    uint64_t memlimit;
+} lzb_options;
+
+/* ---- per-stream status: one code per error site of the reference.
+ * `kind` is the error::Error variant (src/error.rs:7-17); a0..a2 are the values the reference
+ * formats into its message.  lzb_format_error() renders the reference's exact Display string. */
+enum { LZB_KIND_OK = 0, LZB_KIND_IO = 1, LZB_KIND_HEADER_TOO_SHORT = 2, LZB_KIND_LZMA = 3, LZB_KIND_XZ = 4,
+       LZB_KIND_INTERNAL = 5 /* not a reference error: capacity / unsupported on the GPU path */ };
+
+enum {
+    LZB_OK = 0,
+    LZB_E_IO_EOF = 1,               /* IoError(UnexpectedEof): rangecoder.rs:64, xz.rs read_u8/read_u32 `?` sites */
+    LZB_E_HEADER_TOO_SHORT = 2,     /* lzma.rs:101,119-121,133-135,144-146 */
+    LZB_E_LZMA_PROPS = 3,           /* lzma.rs:104-109   a0=props */
+    LZB_E_LZMA_STREAM_TOO_SHORT = 4,/* lzma.rs:643-644 */
+    LZB_E_EOS_MORE_BYTES = 5,       /* lzma.rs:378-380 */
+    LZB_E_UNPACKED_MISMATCH = 6,    /* lzma.rs:513-521   a0=expected a1=got */
+    LZB_E_MATCH_DIST_DICT = 7,      /* lzbuffer.rs:241-246 a0=dist a1=dict_size */
+    LZB_E_MATCH_DIST_OUT = 8,       /* lzbuffer.rs:100-105,247-252 a0=dist a1=len */
+    LZB_E_LZ_DIST_DICT = 9,         /* lzbuffer.rs:274-279 a0=dist a1=dict_size */
+    LZB_E_LZ_DIST_OUT = 10,         /* lzbuffer.rs:128-133,280-285 a0=dist a1=len */
+    LZB_E_MEMLIMIT = 11,            /* lzbuffer.rs:213-217 a0=memlimit */
+    LZB_E_L2_STATUS_EOF = 12,       /* lzma2.rs:60-62 */
+    LZB_E_L2_INVALID_STATUS = 13,   /* lzma2.rs:94-99    a0=status */
+    LZB_E_L2_UNPACKED_EOF = 14,     /* lzma2.rs:128-130, 204-206 */
+    LZB_E_L2_PACKED_EOF = 15,       /* lzma2.rs:133-135 */
+    LZB_E_L2_PROPS_EOF = 16,        /* lzma2.rs:153-155 */
+    LZB_E_L2_PROPS_RANGE = 17,      /* lzma2.rs:158-163  a0=props */
+    LZB_E_L2_PROPS_LCLP = 18,       /* lzma2.rs:170-175  a0=lc a1=lp */
+    LZB_E_L2_STORED_EOF = 19,       /* lzma2.rs:220-225  a0=size */
+    LZB_E_L2_INPUT_TOO_SHORT = 20,  /* lzma2.rs:190-191 */
+    /* XZ container (host-side walk of xz.rs / xz/header.rs / xz/mod.rs) */
+    LZB_E_XZ_MAGIC = 30,            /* header.rs:24-29 */
+    LZB_E_XZ_HEADER_CRC = 31,       /* header.rs:38-44, xz.rs:217-224  a0=read a1=computed */
+    LZB_E_XZ_FLAGS_NULL = 32,       /* xz/mod.rs:27-32   a0=byte */
+    LZB_E_XZ_CHECK_METHOD = 33,     /* xz/mod.rs:65-75   a0=id */
+    LZB_E_XZ_BLOCK_FLAGS = 34,      /* xz.rs:375-380     a0=flags */
+    LZB_E_XZ_FILTER_ID = 35,        /* xz.rs:178-183     a0=id */
+    LZB_E_XZ_PROPS_SIZE = 36,       /* xz.rs:412-417     a0=size a1=header_size */
+    LZB_E_XZ_PROPS_READ = 37,       /* xz.rs:421-426     a0=size */
+    LZB_E_XZ_HEADER_PADDING = 38,   /* xz.rs:435-439 */
+    LZB_E_XZ_FILTER_PROPS = 39,     /* xz.rs:343-348 */
+    LZB_E_XZ_PACKED_SIZE = 40,      /* xz.rs:232-238     a0=expected a1=got */
+    LZB_E_XZ_UNPACKED_SIZE = 41,    /* xz.rs:255-261     a0=expected a1=got */
+    LZB_E_XZ_BLOCK_PADDING = 42,    /* xz.rs:272-278 */
+    LZB_E_XZ_BLOCK_CRC32 = 43,      /* xz.rs:305-312     a0=read a1=computed */
+    LZB_E_XZ_BLOCK_CRC64 = 44,      /* xz.rs:316-323     a0=read a1=computed */
+    LZB_E_XZ_SHA256 = 45,           /* xz.rs:326-330 */
+    LZB_E_XZ_INDEX_COUNT = 46,      /* xz.rs:109-116     a0=index a1=records */
+    LZB_E_XZ_INDEX_UNPADDED = 47,   /* xz.rs:121-127     a0=record a1=actual a2=index */
+    LZB_E_XZ_INDEX_UNPACKED = 48,   /* xz.rs:129-135     a0=record a1=actual a2=index */
+    LZB_E_XZ_INDEX_PADDING = 49,    /* xz.rs:150-155 */
+    LZB_E_XZ_INDEX_CRC = 50,        /* xz.rs:162-168     a0=read a1=computed */
+    LZB_E_XZ_MULTIBYTE = 51,        /* xz.rs:461-463 */
+    LZB_E_XZ_INDEX_SIZE = 52,       /* xz.rs:52-58       a0=expected a1=got */
+    LZB_E_XZ_FLAGS_MISMATCH = 53,   /* xz.rs:65-70       a0=header check a1=footer check */
+    LZB_E_XZ_FOOTER_CRC = 54,       /* xz.rs:73-79       a0=read a1=computed */
+    LZB_E_XZ_FOOTER_MAGIC = 55,     /* xz.rs:81-86 */
+    LZB_E_XZ_TRAILING_DATA = 56,    /* xz.rs:88-92 */
+    /* not reference errors (kind = LZB_KIND_INTERNAL) */
+    LZB_E_CAPACITY = -1,    /* caller's output capacity too small; a0 = bytes needed (lower bound if the size is unknown) */
+    LZB_E_UNSUPPORTED = -2  /* outside the GPU path's limits (stream or output >= 4 GiB - 4 KiB) */
+};
+
+typedef struct lzb_status {
+    int32_t code; /* LZB_OK / LZB_E_* */
+    int32_t kind; /* LZB_KIND_* */
+    uint64_t a0, a1, a2;
+} lzb_status;
+
+typedef struct lzb_ctx lzb_ctx;
+
+/* One context per CUDA device (one process per GPU; multi-GPU = one ctx per rank).
+ * device < 0 -> the current device. */
+int lzb_create(lzb_ctx **ctx, int device);
+void lzb_destroy(lzb_ctx *ctx);
+/* Text of the last infrastructure failure on this ctx (CUDA error string); "" if none. */
+const char *lzb_last_error(const lzb_ctx *ctx);
+int lzb_abi_version(void);
+
+/* Host-side size scan (no GPU work): walks .lzma headers / LZMA2 chunk headers / the XZ container
+ * (lzma.rs:96-161, lzma2.rs:128-136,204-207, xz.rs:356-446) of stream i = in[in_off[i], in_off[i+1])
+ * and writes the output capacity lzb_decode_batch needs for it: exact size for well-formed LZMA2 /
+ * XZ / known-size .lzma, a heuristic bound for end-marker .lzma (decode reports LZB_E_CAPACITY with
+ * the bytes needed if it was too small).  st may be NULL. */
+int lzb_scan(lzb_ctx *ctx, int fmt, const lzb_options *opt, const uint8_t *in, const uint64_t *in_off,
+             uint32_t n, uint64_t *capacity);
+
+/* Decode n independent streams from HOST memory into HOST memory (the reference-facing path):
+ *   stream i input  = in[in_off[i], in_off[i+1])
+ *   stream i output -> out[out_off[i], ...), capacity out_off[i+1]-out_off[i]
+ *   out_len[i]  = bytes the reference would have written to its io::Write sink (also on error:
+ *                 the reference's partial output, e.g. whole validated XZ blocks)
+ *   consumed[i] = bytes the reference would have consumed from its io::BufRead (on success)
+ *   st[i]       = per-stream status
+ * H2D copy, kernels and D2H copy all happen inside the call (pinned buffers copy at full PCIe rate).
+ * Returns LZB_RC_*; per-stream failures do not fail the call. */
+int lzb_decode_batch(lzb_ctx *ctx, int fmt, const lzb_options *opt, const uint8_t *in, const uint64_t *in_off,
+                     uint32_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_len, uint64_t *consumed,
+                     lzb_status *st);
+
+/* Same for DEVICE-resident raw streams (fmt = LZB_FMT_LZMA2, or LZB_FMT_LZMA): d_in / d_out are device
+ * pointers (d_in readable up to the next multiple of 4 bytes); offsets and result arrays are host
+ * arrays.  Runs on `cuda_stream` (a cudaStream_t passed as void*, NULL = the ctx's own stream) and
+ * synchronises it before returning the per-stream results.  This is what bench.py times as the
+ * kernel-only `value`. */
+int lzb_decode_batch_device(lzb_ctx *ctx, int fmt, const lzb_options *opt, const uint8_t *d_in,
+                            const uint64_t *in_off, uint32_t n, uint8_t *d_out, const uint64_t *out_off,
+                            uint64_t *out_len, uint64_t *consumed, lzb_status *st, void *cuda_stream);
+
+/* Two-phase variant of the device path for timing and overlap: prepare uploads the offsets and runs the
+ * per-stream scan kernel (header parse / LZMA2 framing walk) once; launch enqueues ONLY the decode
+ * kernel on `cuda_stream` (no sync); collect synchronises and fetches results.  A prepared batch can
+ * be launched repeatedly.  d_in and d_out must be 16-byte aligned. */
+typedef struct lzb_batch lzb_batch;
+int lzb_batch_prepare(lzb_ctx *ctx, int fmt, const lzb_options *opt, const uint8_t *d_in, const uint64_t *in_off,
+                      uint32_t n, uint8_t *d_out, const uint64_t *out_off, lzb_batch **batch);
+int lzb_batch_launch(lzb_batch *batch, void *cuda_stream);
+int lzb_batch_collect(lzb_batch *batch, void *cuda_stream, uint64_t *out_len, uint64_t *consumed, lzb_status *st);
+void lzb_batch_destroy(lzb_batch *batch);
+/* Number of kernels one lzb_batch_launch enqueues (for bench.py's gpu_launches claim). */
+int lzb_batch_kernels_per_launch(const lzb_batch *batch);
+
+/* Single-stream convenience for the Rust/C++ shim: scan + decode + (for end-marker .lzma) capacity
+ * retry.  *out is malloc'ed by the library (free with lzb_free) and holds *out_len bytes -- on error
+ * the reference's partial output.  Returns LZB_RC_*; *st has the decode status. */
+int lzb_decompress_alloc(lzb_ctx *ctx, int fmt, const lzb_options *opt, const uint8_t *in, size_t in_len,
+                         uint8_t **out, size_t *out_len, size_t *consumed, lzb_status *st);
+void lzb_free(void *p);
+
+/* Device CRC of byte ranges (XZ block check, xz.rs:295-333): crc32[i] / crc64[i] of
+ * d_data[off[i], off[i]+len[i]).  Host arrays for off/len/results. */
+int lzb_crc_device(lzb_ctx *ctx, const uint8_t *d_data, const uint64_t *off, const uint64_t *len, uint32_t n,
+                   uint32_t *crc32, uint64_t *crc64, void *cuda_stream);
+
+/* Renders the reference's Display string for a status ("lzma error: ...", src/error.rs:28-37) into
+ * buf (NUL-terminated, truncated to buf_len).  Returns the untruncated length. */
+size_t lzb_format_error(const lzb_status *st, char *buf, size_t buf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LZMA_B200_H */

@@ -1,0 +1,252 @@
+"""lzma_rs_b200 -- B200-native many-stream LZMA / LZMA2 / XZ decompressor (host-side mirror of the lzma-rs API).
+
+Mirrors the decode entry points of gendx/lzma-rs (src/lib.rs:44-60, 83-88, 100-105) over the C ABI in
+include/lzma_b200.h:
+
+    lzma_decompress(input, output)                        -> lzma_rs::lzma_decompress
+    lzma_decompress_with_options(input, output, options)  -> lzma_rs::lzma_decompress_with_options
+    lzma2_decompress(input, output)                       -> lzma_rs::lzma2_decompress
+    xz_decompress(input, output)                          -> lzma_rs::xz_decompress
+
+`input` is a bytes-like object or a binary reader (`.read()`), `output` a binary writer (`.write()`), the same
+roles io::BufRead / io::Write play in the reference.  Errors are raised as `error.Error` subclasses whose `str()`
+is the reference's Display string.  On error the reference's partial output has already been written to `output`.
+
+The `*_batch` functions are the many-stream form the GPU is built for.  Every byte is decoded by the CUDA kernels
+in liblzma_b200.so -- there is no CPU fallback; without the library or a GPU the calls raise.
+"""
+import ctypes as _C
+import enum as _enum
+
+import numpy as _np
+
+from . import _native
+
+__all__ = ["lzma_decompress", "lzma_decompress_with_options", "lzma2_decompress", "xz_decompress",
+           "lzma_decompress_batch", "lzma2_decompress_batch", "xz_decompress_batch", "decompress", "error", "Context"]
+
+
+class error:  # namespace mirroring lzma_rs::error (src/error.rs:7-37)
+    class Error(Exception):
+        """lzma_rs::error::Error"""
+        prefix = ""
+
+        def __init__(self, display, status=None, partial_output=b""):
+            super().__init__(display)
+            self.status = status
+            self.partial_output = partial_output
+
+    class IoError(Error):
+        pass
+
+    class HeaderTooShort(Error):
+        pass
+
+    class LzmaError(Error):
+        pass
+
+    class XzError(Error):
+        pass
+
+    class InternalError(Error):
+        """Not a reference error: capacity/limits of the GPU path or a CUDA failure."""
+
+
+_KIND_TO_EXC = {_native.KIND_IO: error.IoError, _native.KIND_HEADER_TOO_SHORT: error.HeaderTooShort,
+                _native.KIND_LZMA: error.LzmaError, _native.KIND_XZ: error.XzError,
+                _native.KIND_INTERNAL: error.InternalError}
+
+
+class decompress:  # namespace mirroring lzma_rs::decompress (src/decode/options.rs:3-43)
+    class UnpackedSizeMode(_enum.IntEnum):
+        ReadFromHeader = 0
+        ReadHeaderButUseProvided = 1
+        UseProvided = 2
+
+    class UnpackedSize:
+        """UnpackedSize::{ReadFromHeader, ReadHeaderButUseProvided(Option<u64>), UseProvided(Option<u64>)}"""
+
+        def __init__(self, mode=0, value=None):
+            self.mode, self.value = int(mode), value
+
+        @classmethod
+        def ReadFromHeader(cls):
+            return cls(0)
+
+        @classmethod
+        def ReadHeaderButUseProvided(cls, x):
+            return cls(1, x)
+
+        @classmethod
+        def UseProvided(cls, x):
+            return cls(2, x)
+
+    class Options:
+        """decompress::Options { unpacked_size, memlimit, allow_incomplete (stream API only) }"""
+
+        def __init__(self, unpacked_size=None, memlimit=None, allow_incomplete=False):
+            self.unpacked_size = unpacked_size or decompress.UnpackedSize.ReadFromHeader()
+            self.memlimit = memlimit
+            self.allow_incomplete = allow_incomplete
+
+        def _native(self):
+            return _native.make_options(self.unpacked_size.mode, self.unpacked_size.value, self.memlimit)
+
+
+class StreamResult:
+    """Outcome of one stream of a batch call."""
+    __slots__ = ("data", "consumed", "status", "display")
+
+    def __init__(self, data, consumed, status, display):
+        self.data, self.consumed, self.status, self.display = data, consumed, status, display
+
+    @property
+    def ok(self):
+        return int(self.status["code"]) == 0
+
+    def raise_for_status(self):
+        if not self.ok:
+            raise _KIND_TO_EXC.get(int(self.status["kind"]), error.InternalError)(self.display, self.status, self.data)
+
+
+class Context:
+    """One decoder context per CUDA device (lzb_create / lzb_destroy)."""
+
+    def __init__(self, device=-1):
+        self._lib = _native.load()
+        h = _C.c_void_p()
+        rc = self._lib.lzb_create(_C.byref(h), device)
+        if rc != _native.RC_OK:
+            raise RuntimeError(f"lzb_create failed (rc={rc}): no usable CUDA device -- lzma_rs_b200 has no CPU fallback")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lzb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def last_error(self):
+        return self._lib.lzb_last_error(self._h).decode()
+
+    def scan(self, fmt, blob, in_off, options=None):
+        n = len(in_off) - 1
+        cap = _np.zeros(n, dtype=_np.uint64)
+        opt = (options or decompress.Options())._native()
+        rc = self._lib.lzb_scan(self._h, fmt, _C.byref(opt), blob.ctypes.data, in_off.ctypes.data, n, cap.ctypes.data)
+        if rc != _native.RC_OK:
+            raise RuntimeError(f"lzb_scan failed rc={rc}: {self.last_error()}")
+        return cap
+
+    def decode_batch(self, fmt, streams, options=None, capacities=None):
+        """streams: list of bytes-like.  Returns a list of StreamResult (same order)."""
+        blob, in_off = _native.pack_streams(streams)
+        n = len(streams)
+        opt = (options or decompress.Options())._native()
+        if capacities is None:
+            capacities = self.scan(fmt, blob, in_off, options)
+        capacities = _np.asarray(capacities, dtype=_np.uint64)
+        out_off = _np.zeros(n + 1, dtype=_np.uint64)
+        _np.cumsum((capacities + _np.uint64(15)) // _np.uint64(16) * _np.uint64(16), out=out_off[1:])
+        out = _np.empty(int(out_off[-1]) + 16, dtype=_np.uint8)
+        out_len = _np.zeros(n, dtype=_np.uint64)
+        consumed = _np.zeros(n, dtype=_np.uint64)
+        st = _np.zeros(n, dtype=_native.STATUS_DTYPE)
+        rc = self._lib.lzb_decode_batch(self._h, fmt, _C.byref(opt), blob.ctypes.data, in_off.ctypes.data, n,
+                                        out.ctypes.data, out_off.ctypes.data, out_len.ctypes.data,
+                                        consumed.ctypes.data, st.ctypes.data)
+        if rc != _native.RC_OK:
+            raise RuntimeError(f"lzb_decode_batch failed rc={rc}: {self.last_error()}")
+        res = []
+        for i in range(n):
+            o = int(out_off[i])
+            data = out[o:o + int(out_len[i])].tobytes()
+            disp = "" if st[i]["code"] == 0 else _native.format_status(self._lib, st[i])
+            res.append(StreamResult(data, int(consumed[i]), st[i].copy(), disp))
+        return res
+
+    def decompress_one(self, fmt, data, options=None):
+        """lzb_decompress_alloc: scan + decode (+ capacity retry for end-marker .lzma)."""
+        opt = (options or decompress.Options())._native()
+        buf = bytes(data)
+        out = _C.c_void_p()
+        out_len, consumed = _C.c_size_t(), _C.c_size_t()
+        st = _native.Status()
+        rc = self._lib.lzb_decompress_alloc(self._h, fmt, _C.byref(opt), buf, len(buf), _C.byref(out),
+                                            _C.byref(out_len), _C.byref(consumed), _C.byref(st))
+        if rc != _native.RC_OK:
+            raise RuntimeError(f"lzb_decompress_alloc failed rc={rc}: {self.last_error()}")
+        payload = _C.string_at(out, out_len.value) if out_len.value else b""
+        self._lib.lzb_free(out)
+        row = _np.zeros((), dtype=_native.STATUS_DTYPE)
+        row["code"], row["kind"], row["a0"], row["a1"], row["a2"] = st.code, st.kind, st.a0, st.a1, st.a2
+        disp = "" if st.code == 0 else _native.format_status(self._lib, st)
+        return StreamResult(payload, consumed.value, row, disp)
+
+
+_default_ctx = None
+
+
+def _ctx():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+def _read_all(inp):
+    if isinstance(inp, (bytes, bytearray, memoryview)):
+        return bytes(inp), None
+    return inp.read(), inp
+
+
+def _one(fmt, inp, output, options):
+    data, reader = _read_all(inp)
+    r = _ctx().decompress_one(fmt, data, options)
+    if output is not None and r.data:
+        output.write(r.data)  # on error this is the reference's partial output
+    if reader is not None and r.ok and hasattr(reader, "seek") and r.consumed != len(data):
+        reader.seek(r.consumed - len(data), 1)  # leave unread trailing bytes in the reader, like BufRead::consume
+    r.raise_for_status()
+    return r.data
+
+
+def lzma_decompress(input, output=None):
+    """lzma_rs::lzma_decompress (src/lib.rs:44-49)."""
+    return _one(_native.FMT_LZMA, input, output, None)
+
+
+def lzma_decompress_with_options(input, output=None, options=None):
+    """lzma_rs::lzma_decompress_with_options (src/lib.rs:52-60)."""
+    return _one(_native.FMT_LZMA, input, output, options)
+
+
+def lzma2_decompress(input, output=None):
+    """lzma_rs::lzma2_decompress (src/lib.rs:83-88)."""
+    return _one(_native.FMT_LZMA2, input, output, None)
+
+
+def xz_decompress(input, output=None):
+    """lzma_rs::xz_decompress (src/lib.rs:100-105)."""
+    return _one(_native.FMT_XZ, input, output, None)
+
+
+def lzma_decompress_batch(streams, options=None):
+    return _ctx().decode_batch(_native.FMT_LZMA, streams, options)
+
+
+def lzma2_decompress_batch(streams):
+    return _ctx().decode_batch(_native.FMT_LZMA2, streams)
+
+
+def xz_decompress_batch(streams):
+    return _ctx().decode_batch(_native.FMT_XZ, streams)

@@ -1,0 +1,442 @@
+// lzb_decode_core.h -- K1's per-stream decode (one warp = one stream), written so that the SAME source also
+// compiles as plain C++ with LZB_LANES == 1 (tests/host_emulation: CPU-side check of the decode logic against
+// the oracle; test infrastructure only -- the shipped library always runs this code on the GPU).
+//
+// Behavioural contract: SURVEY.md 3.5 (bit-exact with the reference including its leniencies and its error
+// precedence).  Every lane of a warp runs the same scalar decode (uniform control flow, shared-memory reads
+// are broadcasts); lanes only differ inside the window / stored-chunk copies.
+#pragma once
+#include <stdint.h>
+
+#include "lzb_types.h"
+
+#ifdef __CUDACC__
+#define LZB_LANES 32
+#define LZB_DEV __device__ __forceinline__
+#define LZB_DEV_NOINLINE __device__ __noinline__
+#define LZB_SYNCWARP() __syncwarp()
+#define LZB_LDG(p) __ldg(p)
+#define LZB_MIN(a, b) min(a, b)
+#else  // host emulation of a 1-lane "warp"
+#define LZB_LANES 1
+#define LZB_DEV static inline
+#define LZB_DEV_NOINLINE static
+#define LZB_SYNCWARP() ((void)0)
+#define LZB_LDG(p) (*(p))
+#define LZB_MIN(a, b) ((a) < (b) ? (a) : (b))
+#define __restrict__
+static inline uint32_t __byte_perm(uint32_t x, uint32_t, uint32_t) { return __builtin_bswap32(x); }  // only 0x0123 is used
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { return (hi << s) | (lo >> (32 - s)); }
+#endif
+
+#define RC_TOP (1u << 24)
+
+// ------------------------------------------------------------------------------------------------
+// range decoder + input window
+// ------------------------------------------------------------------------------------------------
+struct Dec {
+    uint32_t range, code;
+    const uint32_t* __restrict__ words;  // 4-byte aligned base of this stream's input
+    uint32_t p;      // next byte to consume (relative to words)
+    uint32_t lim;    // end of the current io::Take (lzma2.rs:189) or of the stream
+    uint32_t lastw;  // last word index that may be loaded
+    uint32_t cur;    // upcoming bytes, most significant first
+    uint32_t nxt;    // prefetched following word (memory order)
+};
+
+LZB_DEV uint32_t ld_word(const Dec& d, uint32_t w) { return LZB_LDG(d.words + LZB_MIN(w, d.lastw)); }
+
+LZB_DEV void rd_seek(Dec& d, uint32_t p) {
+    uint32_t w = p >> 2;
+    d.p = p;
+    d.cur = __byte_perm(ld_word(d, w), 0, 0x0123) << ((p & 3u) * 8u);
+    d.nxt = ld_word(d, w + 1);
+}
+
+// normalize, rangecoder.rs:60-69: ONE conditional 8-bit shift after every decision.  Reads past
+// `lim` are detected by the caller as p > lim at the symbol boundary (UnexpectedEof, rangecoder.rs:64).
+LZB_DEV void rc_normalize(Dec& d) {
+    if (d.range < RC_TOP) {
+        d.range <<= 8;
+        d.code = __funnelshift_l(d.cur, d.code, 8);  // (code << 8) | next byte
+        d.cur <<= 8;
+        d.p += 1;
+        if ((d.p & 3u) == 0) {
+            d.cur = __byte_perm(d.nxt, 0, 0x0123);
+            d.nxt = ld_word(d, (d.p >> 2) + 1);
+        }
+    }
+}
+
+// decode_bit, rangecoder.rs:93-120 (update == true off the stream API).
+LZB_DEV uint32_t rc_bit(Dec& d, uint16_t* prob) {
+    uint32_t pv = *prob;
+    uint32_t bound = (d.range >> 11) * pv;
+    bool one = d.code >= bound;
+    d.range = one ? d.range - bound : bound;
+    d.code = one ? d.code - bound : d.code;
+    // one: p -= p >> 5 ; zero: p += (2048 - p) >> 5  ==  p -= (p + off) >> 5 (arithmetic), off = one ? 0 : 31-2048
+    int off = one ? 0 : (31 - 2048);
+    pv = pv - (uint32_t)(((int)pv + off) >> 5);
+    *prob = (uint16_t)pv;
+    rc_normalize(d);
+    return one ? 1u : 0u;
+}
+
+// get(count), rangecoder.rs:72-90
+LZB_DEV uint32_t rc_direct(Dec& d, uint32_t count) {
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        d.range >>= 1;
+        uint32_t b = d.code >= d.range;
+        if (b) d.code -= d.range;
+        rc_normalize(d);
+        r = (r << 1) | b;
+    }
+    return r;
+}
+
+// parse_bit_tree, rangecoder.rs:122-134
+template <int NB>
+LZB_DEV uint32_t rc_tree(Dec& d, uint16_t* probs) {
+    uint32_t m = 1;
+#pragma unroll
+    for (int i = 0; i < NB; i++) m = (m << 1) | rc_bit(d, probs + m);
+    return m - (1u << NB);
+}
+
+// parse_reverse_bit_tree, rangecoder.rs:136-151
+LZB_DEV uint32_t rc_rtree(Dec& d, uint16_t* probs, uint32_t nb) {
+    uint32_t m = 1, r = 0;
+    for (uint32_t i = 0; i < nb; i++) {
+        uint32_t b = rc_bit(d, probs + m);
+        m = (m << 1) | b;
+        r |= b << i;
+    }
+    return r;
+}
+
+// LenDecoder::decode, rangecoder.rs:256-269
+LZB_DEV uint32_t rc_len(Dec& d, uint16_t* L, uint32_t pos_state) {
+    if (!rc_bit(d, L + 0)) return rc_tree<3>(d, L + T_LEN_LOW + pos_state * 8);
+    if (!rc_bit(d, L + 1)) return 8 + rc_tree<3>(d, L + T_LEN_MID + pos_state * 8);
+    return 16 + rc_tree<8>(d, L + T_LEN_HIGH);
+}
+
+LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
+    uint32_t* T32 = reinterpret_cast<uint32_t*>(T);
+    for (uint32_t i = lane; i < n_u16 / 2; i += LZB_LANES) T32[i] = 0x04000400u;  // every prob = 0x400 (lzma.rs:188-214)
+    LZB_SYNCWARP();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: decode one stream with one warp
+// ------------------------------------------------------------------------------------------------
+#define FAIL(c, x, y)        \
+    do {                     \
+        err = (c);           \
+        ea0 = (uint64_t)(x); \
+        ea1 = (uint64_t)(y); \
+        goto finish;         \
+    } while (0)
+
+LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t* __restrict__ in_blob,
+                                         uint8_t* out_blob, uint16_t* T, uint32_t tab_lclp, LzbResult* res,
+                                         int lane) {
+    Dec d;
+    const bool is_lzma1 = itp->kind == LZB_ITEM_LZMA;
+    const uint32_t p0 = (uint32_t)(itp->in_off & 3ull);
+    const uint8_t* __restrict__ inb = in_blob + (itp->in_off - p0);
+    const uint32_t stream_lim = p0 + (uint32_t)itp->in_len;
+    uint8_t* out = out_blob + itp->out_off;
+    const uint32_t cap = (uint32_t)LZB_MIN(itp->out_cap, (uint64_t)0xFFFFF000u);
+    const uint32_t tab_u16 = T_LIT + (0x300u << tab_lclp);
+    uint32_t opos = 0, dict_base = 0;
+    uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
+    uint32_t lc = 0, lp = 0, pb = 0;
+    uint32_t prev_byte = 0, match_byte = 0;
+    bool mb_valid = false, tables_fresh = true;
+    uint32_t dict_size = 0xFFFFFFFFu, mem_stop = 0xFFFFFFFFu;
+    uint32_t target = 0;
+    bool has_target = false;
+    int err = LZB_OK;
+    uint64_t ea0 = 0, ea1 = 0;
+    uint32_t chunks = 0;
+
+    if (itp->kind == LZB_ITEM_PRESET) {  // status decided by the header parse (K2 / host)
+        if (lane == 0) {
+            res->code = itp->preset_code;
+            res->chunks = 0;
+            res->a0 = itp->preset_a0;
+            res->a1 = 0;
+            res->out_len = 0;
+            res->sink_len = 0;
+            res->consumed = 0;
+        }
+        return;
+    }
+
+    d.words = reinterpret_cast<const uint32_t*>(inb);
+    d.lastw = itp->in_len ? (stream_lim - 1) >> 2 : 0;
+    d.p = p0;
+    d.lim = stream_lim;
+    d.range = 0xFFFFFFFFu;
+    d.code = 0;
+    d.cur = d.nxt = 0;
+
+    if (is_lzma1) {
+        lc = itp->lc;
+        lp = itp->lp;
+        pb = itp->pb;
+        dict_size = itp->dict_size;
+        if (itp->memlimit < (uint64_t)dict_size) mem_stop = (uint32_t)itp->memlimit;  // lzbuffer.rs:209-217
+        has_target = itp->unpacked != LZB_UNKNOWN_SIZE;
+        target = (uint32_t)LZB_MIN(itp->unpacked, (uint64_t)0xFFFFFFFFu);  // sizes beyond the cap are never reached
+        if (lc + lp > tab_lclp) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
+    }
+    fill_tables(T, tab_u16, lane);
+
+    for (;;) {  // LZMA2 chunk loop (lzma2.rs:59-78); a .lzma stream is a single pass
+        if (is_lzma1) {
+            if (stream_lim - d.p < 5) FAIL(LZB_E_LZMA_STREAM_TOO_SHORT, 0, 0);  // lzma.rs:643-644
+        } else {
+            if (d.p >= stream_lim) FAIL(LZB_E_L2_STATUS_EOF, 0, 0);
+            uint32_t status = inb[d.p];
+            d.p += 1;
+            chunks++;
+            if (status == 0) break;
+            if (status == 1 || status == 2) {  // parse_uncompressed, lzma2.rs:195-229
+                if (stream_lim - d.p < 2) FAIL(LZB_E_L2_UNPACKED_EOF, 0, 0);
+                uint32_t n = (((uint32_t)inb[d.p] << 8) | inb[d.p + 1]) + 1;
+                d.p += 2;
+                if (status == 1) {  // accum.reset(): everything so far goes to the sink, window restarts
+                    dict_base = opos;
+                    prev_byte = 0;
+                }
+                if (stream_lim - d.p < n) FAIL(LZB_E_L2_STORED_EOF, n, 0);
+                if (cap - opos < n) FAIL(LZB_E_CAPACITY, (uint64_t)opos + n, 0);
+                {
+                    const uint8_t* s = inb + d.p;
+                    uint8_t* t = out + opos;
+                    uint32_t i = lane;
+                    for (; i + 3 * LZB_LANES < n; i += 4 * LZB_LANES) {
+                        uint8_t v0 = LZB_LDG(s + i), v1 = LZB_LDG(s + i + LZB_LANES), v2 = LZB_LDG(s + i + 2 * LZB_LANES),
+                                v3 = LZB_LDG(s + i + 3 * LZB_LANES);
+                        t[i] = v0;
+                        t[i + LZB_LANES] = v1;
+                        t[i + 2 * LZB_LANES] = v2;
+                        t[i + 3 * LZB_LANES] = v3;
+                    }
+                    for (; i < n; i += LZB_LANES) t[i] = LZB_LDG(s + i);
+                }
+                opos += n;
+                d.p += n;
+                prev_byte = inb[d.p - 1];
+                mb_valid = false;
+                continue;
+            }
+            if (status < 0x80) FAIL(LZB_E_L2_INVALID_STATUS, status, 0);  // lzma2.rs:94-99
+            const uint32_t mode = (status >> 5) & 3u;
+            if (stream_lim - d.p < 2) FAIL(LZB_E_L2_UNPACKED_EOF, 0, 0);
+            const uint32_t unpacked = ((((status & 0x1Fu) << 16) | ((uint32_t)inb[d.p] << 8) | inb[d.p + 1])) + 1;
+            d.p += 2;
+            if (stream_lim - d.p < 2) FAIL(LZB_E_L2_PACKED_EOF, 0, 0);
+            const uint32_t packed = (((uint32_t)inb[d.p] << 8) | inb[d.p + 1]) + 1;
+            d.p += 2;
+            if (mode == 3) {  // reset_dict
+                dict_base = opos;
+                prev_byte = 0;
+            }
+            if (mode >= 1) {      // reset_state
+                if (mode >= 2) {  // reset_props
+                    if (d.p >= stream_lim) FAIL(LZB_E_L2_PROPS_EOF, 0, 0);
+                    uint32_t props = inb[d.p];
+                    d.p += 1;
+                    if (props >= 225) FAIL(LZB_E_L2_PROPS_RANGE, props, 0);
+                    lc = props % 9;
+                    props /= 9;
+                    lp = props % 5;
+                    pb = props / 5;
+                    if (lc + lp > 4) FAIL(LZB_E_L2_PROPS_LCLP, lc, lp);
+                }
+                if (lc + lp > tab_lclp) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
+                if (!tables_fresh) fill_tables(T, tab_u16, lane);  // reset_state, lzma.rs:216-249
+                state = 0;
+                rep0 = rep1 = rep2 = rep3 = 0;
+            }
+            has_target = true;
+            target = (opos - dict_base) + unpacked;  // set_unpacked_size(unpacked + accum.len()), lzma2.rs:186-187
+            d.lim = LZB_MIN(d.p + packed, stream_lim);   // input.take(packed_size), lzma2.rs:189
+            if (d.lim - d.p < 5) FAIL(LZB_E_L2_INPUT_TOO_SHORT, 0, 0);
+            mb_valid = false;
+        }
+        tables_fresh = false;
+
+        // RangeDecoder::new, rangecoder.rs:20-30: one byte skipped (value ignored), then a BE u32
+        d.range = 0xFFFFFFFFu;
+        d.code = ((uint32_t)inb[d.p + 1] << 24) | ((uint32_t)inb[d.p + 2] << 16) | ((uint32_t)inb[d.p + 3] << 8) |
+                 (uint32_t)inb[d.p + 4];
+        rd_seek(d, d.p + 5);
+
+        const uint32_t pb_mask = (1u << pb) - 1, lp_mask = (1u << lp) - 1;
+
+        // process_mode(Finish), lzma.rs:435-455, 496-511
+        for (;;) {
+            const uint32_t len = opos - dict_base;
+            if (has_target) {
+                if (len >= target) break;
+            } else if (d.code == 0 && d.p == d.lim) {  // is_finished_ok, rangecoder.rs:50-52
+                break;
+            }
+            const uint32_t pos_state = len & pb_mask;
+
+            if (!rc_bit(d, T + T_IS_MATCH + (state << 4) + pos_state)) {
+                // ---- literal, lzma.rs:287-307 + decode_literal 526-561
+                uint16_t* probs = T + T_LIT + (((len & lp_mask) << lc) + (prev_byte >> (8 - lc))) * 0x300u;
+                uint32_t sym = 1;
+                if (state >= 7) {
+                    if (!mb_valid) {  // last_n(rep[0] + 1), lzbuffer.rs:98-108 / 240-256
+                        if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
+                        if (rep0 >= dict_size) FAIL(LZB_E_MATCH_DIST_DICT, (uint64_t)rep0 + 1, dict_size);
+                        if (rep0 >= len) FAIL(LZB_E_MATCH_DIST_OUT, (uint64_t)rep0 + 1, len);
+                        LZB_SYNCWARP();
+                        match_byte = out[opos - rep0 - 1];
+                    }
+                    uint32_t mb = match_byte;
+                    do {
+                        uint32_t match_bit = (mb >> 7) & 1u;
+                        mb <<= 1;
+                        uint32_t bit = rc_bit(d, probs + ((1u + match_bit) << 8) + sym);
+                        sym = (sym << 1) | bit;
+                        if (match_bit != bit) break;
+                    } while (sym < 0x100);
+                }
+                while (sym < 0x100) sym = (sym << 1) | rc_bit(d, probs + sym);
+                if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
+                if (opos >= mem_stop) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
+                if (opos >= cap) FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);
+                prev_byte = sym & 0xFFu;
+                if (lane == 0) out[opos] = (uint8_t)prev_byte;
+                opos += 1;
+                state = state < 4 ? 0 : (state < 10 ? state - 3 : state - 6);
+                mb_valid = false;
+                continue;
+            }
+
+            // ---- LZ, lzma.rs:309-390
+            uint32_t mlen;
+            if (rc_bit(d, T + T_IS_REP + state)) {
+                bool short_rep = false;
+                if (!rc_bit(d, T + T_IS_REP_G0 + state)) {
+                    if (!rc_bit(d, T + T_IS_REP0LONG + (state << 4) + pos_state)) short_rep = true;
+                } else {
+                    uint32_t dist;
+                    if (!rc_bit(d, T + T_IS_REP_G1 + state)) {
+                        dist = rep1;
+                    } else {
+                        if (!rc_bit(d, T + T_IS_REP_G2 + state)) {
+                            dist = rep2;
+                        } else {
+                            dist = rep3;
+                            rep3 = rep2;
+                        }
+                        rep2 = rep1;
+                    }
+                    rep1 = rep0;
+                    rep0 = dist;
+                }
+                if (short_rep) {
+                    state = state < 7 ? 9 : 11;
+                    mlen = 1;
+                } else {
+                    mlen = rc_len(d, T + T_REP_LEN, pos_state) + 2;
+                    state = state < 7 ? 8 : 11;
+                }
+                if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
+            } else {
+                rep3 = rep2;
+                rep2 = rep1;
+                rep1 = rep0;
+                const uint32_t l = rc_len(d, T + T_LEN, pos_state);
+                state = state < 7 ? 7 : 10;
+                // decode_distance, lzma.rs:563-592
+                const uint32_t pos_slot = rc_tree<6>(d, T + T_POS_SLOT + (l < 3 ? l : 3) * 64);
+                if (pos_slot < 4) {
+                    rep0 = pos_slot;
+                } else {
+                    const uint32_t nd = (pos_slot >> 1) - 1;
+                    uint32_t r = (2u | (pos_slot & 1u)) << nd;
+                    if (pos_slot < 14) {
+                        r += rc_rtree(d, T + T_POS_DEC + r - pos_slot, nd);
+                    } else {
+                        r += rc_direct(d, nd - 4) << 4;
+                        r += rc_rtree(d, T + T_ALIGN, 4);
+                    }
+                    rep0 = r;
+                }
+                if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
+                if (rep0 == 0xFFFFFFFFu) {  // end-of-stream marker, lzma.rs:373-381
+                    if (d.code == 0 && d.p == d.lim) {
+                        has_target = has_target;  // Finished: fall to the size check below
+                        goto chunk_done;
+                    }
+                    FAIL(LZB_E_EOS_MORE_BYTES, 0, 0);
+                }
+                mlen = l + 2;
+            }
+
+            // ---- append_lz(mlen, rep0 + 1), lzbuffer.rs:125-143 / 272-297
+            {
+                if (rep0 >= dict_size) FAIL(LZB_E_LZ_DIST_DICT, (uint64_t)rep0 + 1, dict_size);
+                if (rep0 >= len) FAIL(LZB_E_LZ_DIST_OUT, (uint64_t)rep0 + 1, len);
+                if (mem_stop - opos < mlen && mem_stop != 0xFFFFFFFFu) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
+                if (!is_lzma1 && len + mlen > target)  // the window is never flushed past this point
+                    FAIL(LZB_E_UNPACKED_MISMATCH, target, (uint64_t)len + mlen);
+                if (cap - opos < mlen) FAIL(LZB_E_CAPACITY, (uint64_t)opos + mlen, 0);
+                const uint32_t dist = rep0 + 1;
+                const uint8_t* src = out + opos - dist;
+                uint8_t* dst = out + opos;
+                LZB_SYNCWARP();  // earlier stores of other lanes are visible to these loads
+                uint32_t i_last = mlen - 1, i_next = mlen;
+                if (dist >= mlen) {
+                    for (uint32_t i = lane; i < mlen; i += LZB_LANES) dst[i] = src[i];
+                    if (dist == mlen) i_next = 0;
+                } else {  // overlapping: the window replicates with period dist
+                    for (uint32_t i = lane; i < mlen; i += LZB_LANES) dst[i] = src[i % dist];
+                    i_last %= dist;
+                    i_next %= dist;
+                }
+                prev_byte = src[i_last];   // last byte written      (uniform load)
+                match_byte = src[i_next];  // out[new_opos - dist]: the match byte of a following literal
+                mb_valid = true;
+                opos += mlen;
+            }
+        }
+    chunk_done:
+        {
+            const uint32_t len = opos - dict_base;
+            if (has_target && len != target)  // lzma.rs:513-521
+                FAIL(LZB_E_UNPACKED_MISMATCH, is_lzma1 ? itp->unpacked : (uint64_t)target, len);
+        }
+        if (is_lzma1) break;
+    }
+
+finish:
+    LZB_SYNCWARP();
+    if (lane == 0) {
+        uint64_t sink = opos;
+        if (err != LZB_OK) {
+            // what had reached the caller's sink when the reference returned the error:
+            // LZMA2: everything before the last dict reset (lzbuffer.rs:73-78); LZMA: whole ring slabs (264-267)
+            sink = is_lzma1 ? (uint64_t)(opos / dict_size) * dict_size : dict_base;
+        }
+        res->code = err;
+        res->chunks = chunks;
+        res->a0 = ea0;
+        res->a1 = ea1;
+        res->out_len = opos;
+        res->sink_len = sink;
+        res->consumed = d.p - p0;
+    }
+}
+

@@ -1,0 +1,496 @@
+// lzb_host.cu -- the C ABI (include/lzma_b200.h): contexts, device memory, kernel launches.
+// All decoding happens in lzb_kernels.cu on the GPU; the host only plans (lzb_plan.cpp) and moves bytes.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <numeric>
+#include <vector>
+
+#include "lzb_plan.h"
+#include "lzb_types.h"
+
+struct LzbCrcRange {
+    uint64_t off, len, first_seg;
+};
+#define CRC_SEG 4096u
+
+extern "C" __global__ void lzb_decode_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
+                                             LzbResult*, unsigned int*, uint32_t, uint32_t);
+extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, const uint64_t*, const uint64_t*, uint32_t,
+                                           LzbItem*, LzbScan*);
+extern "C" __global__ void lzb_crc_partial_kernel(const uint8_t*, const LzbCrcRange*, const uint32_t*, uint64_t,
+                                                  uint32_t*, uint64_t*);
+extern "C" __global__ void lzb_crc_fold_kernel(const LzbCrcRange*, uint32_t, const uint32_t*, const uint64_t*,
+                                               uint32_t*, uint64_t*);
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(n + n / 8, 4096);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+}  // namespace
+
+struct lzb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int smem_optin = 0;
+    int smem_configured = -1;
+    char err[320] = {0};
+    std::mutex mu;
+    DevBuf d_in, d_out, d_items, d_results, d_order, d_counter, d_scan, d_off, d_crc_ranges, d_crc_segmap, d_crc_part32,
+        d_crc_part64, d_crc_out32, d_crc_out64;
+};
+
+#define CUDA_TRY(ctx, call)                                                                         \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                     __LINE__);                                                                     \
+            return e_ == cudaErrorMemoryAllocation ? LZB_RC_OOM : LZB_RC_CUDA;                       \
+        }                                                                                           \
+    } while (0)
+
+namespace {
+
+struct LaunchCfg {
+    uint32_t lclp, warp_bytes, warps, grid;
+};
+
+LaunchCfg decode_config(const lzb_ctx* ctx, uint32_t n, uint32_t lclp) {
+    LaunchCfg c;
+    c.lclp = lclp;
+    c.warp_bytes = (lzb_table_u16(lclp) * 2 + 15u) & ~15u;
+    uint32_t max_warps = std::min<uint32_t>(16, (uint32_t)ctx->smem_optin / c.warp_bytes);
+    if (max_warps < 1) max_warps = 1;
+    uint32_t per_sm = (n + ctx->sm_count - 1) / ctx->sm_count;
+    c.warps = std::min(std::max<uint32_t>(per_sm, 1), max_warps);
+    uint32_t blocks_per_sm = std::max<uint32_t>(1, max_warps / c.warps);
+    uint32_t want = (n + c.warps - 1) / c.warps;
+    c.grid = std::max<uint32_t>(1, std::min<uint32_t>(want, (uint32_t)ctx->sm_count * blocks_per_sm));
+    return c;
+}
+
+// Enqueues counter reset + K1 on `s`.  items/order/results/counter are device pointers.
+int launch_decode(lzb_ctx* ctx, cudaStream_t s, const LzbItem* d_items, const uint32_t* d_order, uint32_t n,
+                  const uint8_t* d_in_base, uint8_t* d_out_base, LzbResult* d_results, unsigned int* d_counter,
+                  const LaunchCfg& c) {
+    const int smem = (int)(c.warps * c.warp_bytes);
+    if (smem > ctx->smem_configured) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(lzb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+        ctx->smem_configured = ctx->smem_optin;
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), s));
+    lzb_decode_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, n, d_in_base, d_out_base, d_results, d_counter,
+                                                         c.lclp, c.warp_bytes);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return LZB_RC_OK;
+}
+
+void order_by_length(const LzbItem* items, uint32_t n, std::vector<uint32_t>& order) {
+    order.resize(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return items[a].in_len > items[b].in_len; });
+}
+
+// The one shipped Executor: work items run on the GPU.
+class CudaExecutor : public lzb::Executor {
+   public:
+    CudaExecutor(lzb_ctx* ctx, cudaStream_t s, const uint8_t* d_in_base, uint8_t* d_out_base)
+        : ctx_(ctx), s_(s), in_(d_in_base), out_(d_out_base) {}
+
+    int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, LzbResult* results) override {
+        if (max_lclp > 4) return decode_without_big_tables(items, n, results);
+        int rc = run(items, n, max_lclp, results);
+        if (rc != LZB_RC_OK) return rc;
+        // the framing scan can under-estimate lc+lp on malformed streams: rerun just those with the LZMA2 maximum
+        std::vector<uint32_t> redo;
+        for (uint32_t i = 0; i < n; i++)
+            if (results[i].code == LZB_E_UNSUPPORTED && results[i].a1 == max_lclp && results[i].a0 <= 4 && max_lclp < 4)
+                redo.push_back(i);
+        if (!redo.empty()) {
+            std::vector<LzbItem> sub(redo.size());
+            std::vector<LzbResult> subres(redo.size());
+            for (size_t k = 0; k < redo.size(); k++) sub[k] = items[redo[k]];
+            rc = run(sub.data(), (uint32_t)sub.size(), 4, subres.data());
+            if (rc != LZB_RC_OK) return rc;
+            for (size_t k = 0; k < redo.size(); k++) results[redo[k]] = subres[k];
+        }
+        return LZB_RC_OK;
+    }
+
+    int crc(const lzb::CrcRange* ranges, uint32_t n, uint32_t* crc32, uint64_t* crc64) override {
+        std::vector<LzbCrcRange> rg(n);
+        std::vector<uint32_t> segmap;
+        uint64_t nseg = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            rg[i].off = ranges[i].off;
+            rg[i].len = ranges[i].len;
+            rg[i].first_seg = nseg;
+            uint64_t k = (ranges[i].len + CRC_SEG - 1) / CRC_SEG;
+            segmap.insert(segmap.end(), (size_t)k, i);
+            nseg += k;
+        }
+        lzb_ctx* ctx = ctx_;
+        CUDA_TRY(ctx, ctx->d_crc_ranges.ensure(n * sizeof(LzbCrcRange)));
+        CUDA_TRY(ctx, ctx->d_crc_segmap.ensure(std::max<uint64_t>(nseg, 1) * 4));
+        CUDA_TRY(ctx, ctx->d_crc_part32.ensure(std::max<uint64_t>(nseg, 1) * 4));
+        CUDA_TRY(ctx, ctx->d_crc_part64.ensure(std::max<uint64_t>(nseg, 1) * 8));
+        CUDA_TRY(ctx, ctx->d_crc_out32.ensure(n * 4));
+        CUDA_TRY(ctx, ctx->d_crc_out64.ensure(n * 8));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_crc_ranges.p, rg.data(), n * sizeof(LzbCrcRange), cudaMemcpyHostToDevice, s_));
+        if (nseg) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_crc_segmap.p, segmap.data(), nseg * 4, cudaMemcpyHostToDevice, s_));
+            lzb_crc_partial_kernel<<<(unsigned)((nseg + 127) / 128), 128, 0, s_>>>(
+                out_, ctx->d_crc_ranges.as<LzbCrcRange>(), ctx->d_crc_segmap.as<uint32_t>(), nseg,
+                ctx->d_crc_part32.as<uint32_t>(), ctx->d_crc_part64.as<uint64_t>());
+            CUDA_TRY(ctx, cudaGetLastError());
+        }
+        lzb_crc_fold_kernel<<<(n + 63) / 64, 64, 0, s_>>>(ctx->d_crc_ranges.as<LzbCrcRange>(), n,
+                                                          ctx->d_crc_part32.as<uint32_t>(), ctx->d_crc_part64.as<uint64_t>(),
+                                                          ctx->d_crc_out32.as<uint32_t>(), ctx->d_crc_out64.as<uint64_t>());
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaMemcpyAsync(crc32, ctx->d_crc_out32.p, n * 4, cudaMemcpyDeviceToHost, s_));
+        CUDA_TRY(ctx, cudaMemcpyAsync(crc64, ctx->d_crc_out64.p, n * 8, cudaMemcpyDeviceToHost, s_));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s_));
+        return LZB_RC_OK;
+    }
+
+   private:
+    // .lzma allows lc+lp up to 12 (a 6 MiB literal table per stream), which does not fit the shared-memory
+    // tables of K1: those streams are reported LZB_E_UNSUPPORTED, everything else is decoded normally.
+    int decode_without_big_tables(const LzbItem* items, uint32_t n, LzbResult* results) {
+        std::vector<LzbItem> sub;
+        std::vector<uint32_t> idx;
+        uint32_t lclp = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const bool big = items[i].kind == LZB_ITEM_LZMA && (uint32_t)items[i].lc + items[i].lp > 4;
+            if (big) {
+                memset(&results[i], 0, sizeof results[i]);
+                results[i].code = LZB_E_UNSUPPORTED;
+                results[i].a0 = (uint32_t)items[i].lc + items[i].lp;
+            } else {
+                if (items[i].kind == LZB_ITEM_LZMA) lclp = std::max<uint32_t>(lclp, (uint32_t)items[i].lc + items[i].lp);
+                else if (items[i].kind == LZB_ITEM_LZMA2) lclp = 4;
+                sub.push_back(items[i]);
+                idx.push_back(i);
+            }
+        }
+        if (sub.empty()) return LZB_RC_OK;
+        std::vector<LzbResult> subres(sub.size());
+        int rc = run(sub.data(), (uint32_t)sub.size(), lclp, subres.data());
+        if (rc != LZB_RC_OK) return rc;
+        for (size_t k = 0; k < idx.size(); k++) results[idx[k]] = subres[k];
+        return LZB_RC_OK;
+    }
+    int run(const LzbItem* items, uint32_t n, uint32_t lclp, LzbResult* results) {
+        lzb_ctx* ctx = ctx_;
+        std::vector<uint32_t> order;
+        order_by_length(items, n, order);
+        CUDA_TRY(ctx, ctx->d_items.ensure(n * sizeof(LzbItem)));
+        CUDA_TRY(ctx, ctx->d_results.ensure(n * sizeof(LzbResult)));
+        CUDA_TRY(ctx, ctx->d_order.ensure(n * 4));
+        CUDA_TRY(ctx, ctx->d_counter.ensure(64));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items.p, items, n * sizeof(LzbItem), cudaMemcpyHostToDevice, s_));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_order.p, order.data(), n * 4, cudaMemcpyHostToDevice, s_));
+        LaunchCfg cfg = decode_config(ctx, n, lclp);
+        int rc = launch_decode(ctx, s_, ctx->d_items.as<LzbItem>(), ctx->d_order.as<uint32_t>(), n, in_, out_,
+                               ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>(), cfg);
+        if (rc != LZB_RC_OK) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(results, ctx->d_results.p, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s_));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s_));
+        return LZB_RC_OK;
+    }
+    lzb_ctx* ctx_;
+    cudaStream_t s_;
+    const uint8_t* in_;
+    uint8_t* out_;
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int lzb_abi_version(void) { return LZB_ABI_VERSION; }
+
+extern "C" int lzb_create(lzb_ctx** out, int device) {
+    if (!out) return LZB_RC_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return LZB_RC_NO_DEVICE;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return LZB_RC_NO_DEVICE;
+    if (device >= count) return LZB_RC_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return LZB_RC_NO_DEVICE;
+    lzb_ctx* ctx = new lzb_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return LZB_RC_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return LZB_RC_OK;
+}
+
+extern "C" void lzb_destroy(lzb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_items, &ctx->d_results, &ctx->d_order, &ctx->d_counter, &ctx->d_scan,
+                      &ctx->d_off, &ctx->d_crc_ranges, &ctx->d_crc_segmap, &ctx->d_crc_part32, &ctx->d_crc_part64,
+                      &ctx->d_crc_out32, &ctx->d_crc_out64};
+    for (DevBuf* b : bufs) b->release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* lzb_last_error(const lzb_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+extern "C" int lzb_scan(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* in, const uint64_t* in_off, uint32_t n,
+                        uint64_t* capacity) {
+    if (!ctx || !in_off || !capacity || (n && !in) || fmt < 0 || fmt > 2) return LZB_RC_BAD_ARG;
+    for (uint32_t i = 0; i < n; i++) capacity[i] = lzb::scan_capacity(fmt, opt, in + in_off[i], in_off[i + 1] - in_off[i]);
+    return LZB_RC_OK;
+}
+
+extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* in, const uint64_t* in_off,
+                                uint32_t n, uint8_t* out, const uint64_t* out_off, uint64_t* out_len, uint64_t* consumed,
+                                lzb_status* st) {
+    if (!ctx || !in_off || !out_off || !out_len || !consumed || !st || fmt < 0 || fmt > 2) return LZB_RC_BAD_ARG;
+    if (n == 0) return LZB_RC_OK;
+    if (!in || !out) return LZB_RC_BAD_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t in_lo = in_off[0], in_hi = in_off[n], out_lo = out_off[0], out_hi = out_off[n];
+    // device copies keep the low 4 address bits of the host offsets so that (base + offset) stays 16-byte congruent
+    CUDA_TRY(ctx, ctx->d_in.ensure((in_hi - in_lo) + 64));
+    CUDA_TRY(ctx, ctx->d_out.ensure((out_hi - out_lo) + 64));
+    uint8_t* d_in0 = ctx->d_in.as<uint8_t>() + (in_lo & 15);
+    uint8_t* d_out0 = ctx->d_out.as<uint8_t>() + (out_lo & 15);
+    if (in_hi > in_lo)
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, ctx->stream));
+    CudaExecutor ex(ctx, ctx->stream, d_in0 - in_lo, d_out0 - out_lo);
+    std::vector<lzb::StreamOut> outs(n);
+    int rc = lzb::decode_batch(ex, fmt, opt, in, in_off, n, out_off, outs.data());  // planning reads the host copy
+    if (rc != LZB_RC_OK) return rc;
+    if (out_hi > out_lo)
+        CUDA_TRY(ctx, cudaMemcpyAsync(out + out_lo, d_out0, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < n; i++) {
+        out_len[i] = outs[i].out_len;
+        consumed[i] = outs[i].consumed;
+        st[i] = outs[i].st;
+    }
+    return LZB_RC_OK;
+}
+
+// ---- device-resident batches ----
+struct lzb_batch {
+    lzb_ctx* ctx = nullptr;
+    uint32_t n = 0;
+    int fmt = 0;
+    const uint8_t* d_in = nullptr;
+    uint8_t* d_out = nullptr;
+    DevBuf d_items, d_results, d_order, d_counter, d_scan, d_off;
+    std::vector<LzbItem> items;  // host copy (hdr_len, preset info)
+    LaunchCfg cfg{};
+};
+
+extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in, const uint64_t* in_off,
+                                 uint32_t n, uint8_t* d_out, const uint64_t* out_off, lzb_batch** out) {
+    static const lzb_options defaults = {0, 0, 0, {0, 0, 0, 0, 0}, 0, 0};
+    if (!ctx || !out || !in_off || !out_off || (fmt != LZB_FMT_LZMA && fmt != LZB_FMT_LZMA2) || n == 0 || !d_in || !d_out)
+        return LZB_RC_BAD_ARG;
+    if (((uintptr_t)d_in & 15) || ((uintptr_t)d_out & 15)) return LZB_RC_BAD_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    lzb_batch* b = new lzb_batch();
+    b->ctx = ctx;
+    b->n = n;
+    b->fmt = fmt;
+    b->d_in = d_in;
+    b->d_out = d_out;
+    cudaStream_t s = ctx->stream;
+    int rc = LZB_RC_OK;
+    auto fail = [&](int code) {
+        lzb_batch_destroy(b);
+        return code;
+    };
+#define B_TRY(call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            snprintf(ctx->err, sizeof(ctx->err), "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(e_ == cudaErrorMemoryAllocation ? LZB_RC_OOM : LZB_RC_CUDA);                  \
+        }                                                                                             \
+    } while (0)
+    B_TRY(b->d_items.ensure(n * sizeof(LzbItem)));
+    B_TRY(b->d_results.ensure(n * sizeof(LzbResult)));
+    B_TRY(b->d_order.ensure(n * 4));
+    B_TRY(b->d_counter.ensure(64));
+    B_TRY(b->d_scan.ensure(n * sizeof(LzbScan)));
+    B_TRY(b->d_off.ensure(2 * (size_t)(n + 1) * 8));
+    uint64_t* d_in_off = b->d_off.as<uint64_t>();
+    uint64_t* d_out_off = d_in_off + (n + 1);
+    B_TRY(cudaMemcpyAsync(d_in_off, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    B_TRY(cudaMemcpyAsync(d_out_off, out_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    lzb_scan_kernel<<<(n + 127) / 128, 128, 0, s>>>(fmt, opt ? *opt : defaults, d_in, d_in_off, d_out_off, n,
+                                                    b->d_items.as<LzbItem>(), b->d_scan.as<LzbScan>());
+    B_TRY(cudaGetLastError());
+    std::vector<LzbScan> scan(n);
+    b->items.resize(n);
+    B_TRY(cudaMemcpyAsync(scan.data(), b->d_scan.p, n * sizeof(LzbScan), cudaMemcpyDeviceToHost, s));
+    B_TRY(cudaMemcpyAsync(b->items.data(), b->d_items.p, n * sizeof(LzbItem), cudaMemcpyDeviceToHost, s));
+    B_TRY(cudaStreamSynchronize(s));
+    uint32_t lclp = 0;
+    for (uint32_t i = 0; i < n; i++)
+        if (b->items[i].kind != LZB_ITEM_PRESET) lclp = std::max<uint32_t>(lclp, scan[i].max_lclp);
+    if (fmt == LZB_FMT_LZMA2 && lclp > 4) lclp = 4;
+    if (lzb_table_u16(lclp) * 2 > (uint32_t)ctx->smem_optin) {
+        // .lzma allows lc+lp up to 12 (a 6 MiB literal table): beyond shared memory on this path
+        for (uint32_t i = 0; i < n; i++) {
+            if (b->items[i].kind != LZB_ITEM_PRESET && scan[i].max_lclp > 4) {
+                b->items[i].kind = LZB_ITEM_PRESET;
+                b->items[i].preset_code = LZB_E_UNSUPPORTED;
+            }
+        }
+        B_TRY(cudaMemcpyAsync(b->d_items.p, b->items.data(), n * sizeof(LzbItem), cudaMemcpyHostToDevice, s));
+        lclp = 4;
+    }
+    std::vector<uint32_t> order;
+    order_by_length(b->items.data(), n, order);
+    B_TRY(cudaMemcpyAsync(b->d_order.p, order.data(), n * 4, cudaMemcpyHostToDevice, s));
+    B_TRY(cudaStreamSynchronize(s));
+    b->cfg = decode_config(ctx, n, lclp);
+    (void)rc;
+    *out = b;
+    return LZB_RC_OK;
+#undef B_TRY
+}
+
+extern "C" int lzb_batch_launch(lzb_batch* b, void* cuda_stream) {
+    if (!b) return LZB_RC_BAD_ARG;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : b->ctx->stream;
+    return launch_decode(b->ctx, s, b->d_items.as<LzbItem>(), b->d_order.as<uint32_t>(), b->n, b->d_in, b->d_out,
+                         b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>(), b->cfg);
+}
+
+extern "C" int lzb_batch_kernels_per_launch(const lzb_batch* b) { return b ? 1 : 0; }
+
+extern "C" int lzb_batch_collect(lzb_batch* b, void* cuda_stream, uint64_t* out_len, uint64_t* consumed, lzb_status* st) {
+    if (!b) return LZB_RC_BAD_ARG;
+    lzb_ctx* ctx = b->ctx;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    std::vector<LzbResult> res(b->n);
+    CUDA_TRY(ctx, cudaMemcpyAsync(res.data(), b->d_results.p, b->n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < b->n; i++) {
+        if (st) lzb::status_from_result(res[i], &st[i]);
+        if (out_len) out_len[i] = res[i].sink_len;
+        if (consumed) consumed[i] = b->items[i].hdr_len + res[i].consumed;
+    }
+    return LZB_RC_OK;
+}
+
+extern "C" void lzb_batch_destroy(lzb_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    DevBuf* bufs[] = {&b->d_items, &b->d_results, &b->d_order, &b->d_counter, &b->d_scan, &b->d_off};
+    for (DevBuf* x : bufs) x->release();
+    delete b;
+}
+
+extern "C" int lzb_decode_batch_device(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in,
+                                       const uint64_t* in_off, uint32_t n, uint8_t* d_out, const uint64_t* out_off,
+                                       uint64_t* out_len, uint64_t* consumed, lzb_status* st, void* cuda_stream) {
+    if (n == 0) return LZB_RC_OK;
+    lzb_batch* b = nullptr;
+    int rc = lzb_batch_prepare(ctx, fmt, opt, d_in, in_off, n, d_out, out_off, &b);
+    if (rc != LZB_RC_OK) return rc;
+    if (cuda_stream) cudaStreamSynchronize(ctx->stream);  // prepare ran on the ctx stream
+    rc = lzb_batch_launch(b, cuda_stream);
+    if (rc == LZB_RC_OK) rc = lzb_batch_collect(b, cuda_stream, out_len, consumed, st);
+    lzb_batch_destroy(b);
+    return rc;
+}
+
+extern "C" int lzb_decompress_alloc(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* in, size_t in_len,
+                                    uint8_t** out, size_t* out_len, size_t* consumed, lzb_status* st) {
+    if (!ctx || !out || !out_len || !consumed || !st || (in_len && !in) || fmt < 0 || fmt > 2) return LZB_RC_BAD_ARG;
+    static const uint8_t empty = 0;
+    if (!in) in = &empty;
+    *out = nullptr;
+    *out_len = 0;
+    *consumed = 0;
+    uint64_t cap = lzb::scan_capacity(fmt, opt, in, in_len);
+    const uint64_t limit = 0xFFFFF000ull;
+    for (;;) {
+        cap = std::min<uint64_t>(cap, limit);
+        uint8_t* buf = (uint8_t*)malloc((size_t)cap + 16);
+        if (!buf) return LZB_RC_OOM;
+        uint64_t in_off[2] = {0, in_len}, out_off[2] = {0, cap}, ol = 0, cons = 0;
+        int rc = lzb_decode_batch(ctx, fmt, opt, in, in_off, 1, buf, out_off, &ol, &cons, st);
+        if (rc != LZB_RC_OK) {
+            free(buf);
+            return rc;
+        }
+        if (st->code == LZB_E_CAPACITY && cap < limit) {  // end-marker .lzma / malformed framing: grow and retry
+            free(buf);
+            cap = std::max<uint64_t>(cap * 2, st->a0 + 65536);
+            continue;
+        }
+        if (st->code == LZB_E_CAPACITY) {
+            st->code = LZB_E_UNSUPPORTED;
+            st->kind = LZB_KIND_INTERNAL;
+        }
+        *out = buf;
+        *out_len = (size_t)ol;
+        *consumed = (size_t)cons;
+        return LZB_RC_OK;
+    }
+}
+
+extern "C" void lzb_free(void* p) { free(p); }
+
+extern "C" int lzb_crc_device(lzb_ctx* ctx, const uint8_t* d_data, const uint64_t* off, const uint64_t* len, uint32_t n,
+                              uint32_t* crc32, uint64_t* crc64, void* cuda_stream) {
+    if (!ctx || !d_data || !off || !len || !crc32 || !crc64) return LZB_RC_BAD_ARG;
+    if (n == 0) return LZB_RC_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<lzb::CrcRange> r(n);
+    for (uint32_t i = 0; i < n; i++) r[i] = lzb::CrcRange{off[i], len[i]};
+    CudaExecutor ex(ctx, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, nullptr, const_cast<uint8_t*>(d_data));
+    return ex.crc(r.data(), n, crc32, crc64);
+}

@@ -1,0 +1,292 @@
+// lzb_kernels.cu -- sm_100a kernels of the many-stream LZMA / LZMA2 / XZ decoder.
+//
+//   K1  lzb_decode_kernel   one warp = one independent stream: LZMA2 chunk walk (lzma2.rs:52-229),
+//                           range decoder (rangecoder.rs:60-151), symbol state machine
+//                           (lzma.rs:278-393, 526-592) and LZ window copy (lzbuffer.rs:125-143,272-297)
+//                           fused in one persistent kernel; probability tables live in shared memory.
+//   K2  lzb_scan_kernel     one thread = one stream: .lzma header parse (lzma.rs:96-161) or LZMA2
+//                           chunk-header walk (lzma2.rs:128-136,204-207) -> work items + size summary.
+//   K3  lzb_crc_*           CRC-32/ISO-HDLC + CRC-64/XZ of decoded ranges (xz.rs:295-333).
+//
+// Behavioural contract: SURVEY.md 3.5 (bit-exact with the reference including its leniencies and
+// its error precedence).  Every lane of a warp runs the same scalar decode (uniform control flow,
+// shared-memory reads are broadcasts); lanes only differ inside the window/stored copies.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lzb_types.h"
+
+#define FULL_MASK 0xffffffffu
+
+#include "lzb_decode_core.h"
+
+// ------------------------------------------------------------------------------------------------
+// K1 launcher
+// ------------------------------------------------------------------------------------------------
+// Persistent kernel: warps pull stream indices (pre-sorted longest first by the host) from a counter.
+extern "C" __global__ void __launch_bounds__(512, 1)
+    lzb_decode_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
+                      const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
+                      unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint16_t* T = reinterpret_cast<uint16_t*>(smem + (size_t)warp * warp_smem_bytes);
+    for (;;) {
+        unsigned int slot = 0;
+        if (lane == 0) slot = atomicAdd(counter, 1u);
+        slot = __shfl_sync(FULL_MASK, slot, 0);
+        if (slot >= n_items) break;
+        const uint32_t idx = order ? order[slot] : slot;
+        decode_item(items + idx, in_blob, out_blob, T, tab_lclp, results + idx, lane);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: per-stream scan -> work items (+ size summary).  One thread per stream.
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void lzb_scan_kernel(int fmt, lzb_options opt, const uint8_t* __restrict__ in_blob,
+                                           const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ out_off,
+                                           uint32_t n, LzbItem* items, LzbScan* scan) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = in_blob + in_off[i];
+    const uint64_t len = in_off[i + 1] - in_off[i];
+    LzbItem it;
+    LzbScan sc;
+    it.in_off = in_off[i];
+    it.in_len = len;
+    it.out_off = out_off ? out_off[i] : 0;
+    it.out_cap = out_off ? out_off[i + 1] - out_off[i] : 0;
+    it.unpacked = LZB_UNKNOWN_SIZE;
+    it.memlimit = opt.has_memlimit ? opt.memlimit : ~0ull;
+    it.dict_size = 0;
+    it.kind = LZB_ITEM_LZMA2;
+    it.lc = it.lp = it.pb = 0;
+    it.hdr_len = 0;
+    it.preset_code = 0;
+    it.preset_a0 = 0;
+    sc.unpacked = 0;
+    sc.flags = 0;
+    sc.max_lclp = 0;
+    sc.pad[0] = sc.pad[1] = sc.pad[2] = 0;
+
+    if (fmt == LZB_FMT_LZMA) {  // LzmaParams::read_header, lzma.rs:96-161
+        const uint32_t hdr = opt.unpacked_mode == LZB_UNPACKED_USE_PROVIDED ? 5u : 13u;
+        it.kind = LZB_ITEM_LZMA;
+        if (len < 1) {
+            it.kind = LZB_ITEM_PRESET;
+            it.preset_code = LZB_E_HEADER_TOO_SHORT;
+        } else if (p[0] >= 225) {
+            it.kind = LZB_ITEM_PRESET;
+            it.preset_code = LZB_E_LZMA_PROPS;
+            it.preset_a0 = p[0];
+        } else if (len < hdr) {
+            it.kind = LZB_ITEM_PRESET;
+            it.preset_code = LZB_E_HEADER_TOO_SHORT;
+        } else {
+            uint32_t props = p[0];
+            it.lc = props % 9;
+            props /= 9;
+            it.lp = props % 5;
+            it.pb = props / 5;
+            uint32_t ds = (uint32_t)p[1] | ((uint32_t)p[2] << 8) | ((uint32_t)p[3] << 16) | ((uint32_t)p[4] << 24);
+            it.dict_size = ds < 0x1000u ? 0x1000u : ds;
+            uint64_t hv = LZB_UNKNOWN_SIZE;
+            if (hdr == 13) {
+                hv = 0;
+                for (int k = 7; k >= 0; k--) hv = (hv << 8) | p[5 + k];
+            }
+            if (opt.unpacked_mode == LZB_UNPACKED_READ_FROM_HEADER)
+                it.unpacked = hv;  // 0xFFFF_FFFF_FFFF_FFFF == marker mandatory == unknown
+            else
+                it.unpacked = opt.has_provided ? opt.provided : LZB_UNKNOWN_SIZE;
+            it.in_off += hdr;
+            it.in_len -= hdr;
+            it.hdr_len = hdr;
+            sc.max_lclp = it.lc + it.lp;
+            if (it.unpacked != LZB_UNKNOWN_SIZE) {
+                sc.unpacked = it.unpacked;
+                sc.flags = 1;
+            } else {
+                sc.unpacked = len * 8 + 4096;  // heuristic; decode reports LZB_E_CAPACITY if too small
+            }
+        }
+    } else {  // LZMA2 chunk-header walk (well-formed framing assumed; the decode kernel re-walks exactly)
+        uint64_t q = 0, total = 0;
+        uint32_t lclp = 0, maxl = 0;
+        for (;;) {
+            if (q >= len) break;
+            uint32_t status = p[q++];
+            if (status == 0) {
+                sc.flags = 1;
+                break;
+            }
+            if (status == 1 || status == 2) {
+                if (len - q < 2) break;
+                uint64_t nb = (((uint32_t)p[q] << 8) | p[q + 1]) + 1;
+                q += 2;
+                if (len - q < nb) break;
+                q += nb;
+                total += nb;
+                continue;
+            }
+            if (status < 0x80) break;
+            if (len - q < 4) break;
+            uint64_t unpacked = ((((uint32_t)(status & 0x1F)) << 16) | ((uint32_t)p[q] << 8) | p[q + 1]) + 1;
+            uint64_t packed = (((uint32_t)p[q + 2] << 8) | p[q + 3]) + 1;
+            q += 4;
+            if (status >= 0xC0) {
+                if (q >= len) break;
+                uint32_t props = p[q++];
+                if (props >= 225) break;
+                uint32_t c = props % 9, l = (props / 9) % 5;
+                if (c + l > 4) break;
+                lclp = c + l;
+            }
+            if (lclp > maxl) maxl = lclp;
+            total += unpacked;
+            if (len - q < packed) break;
+            q += packed;
+        }
+        sc.unpacked = total;
+        sc.max_lclp = (uint8_t)maxl;
+    }
+    if (len > 0xFFFFE000ull) {
+        it.kind = LZB_ITEM_PRESET;
+        it.preset_code = LZB_E_UNSUPPORTED;
+    }
+    items[i] = it;
+    scan[i] = sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: CRC-32/ISO-HDLC and CRC-64/XZ of byte ranges (crate `crc` catalogue algorithms, src/xz/crc.rs:3-4).
+// Phase a: one thread per 4 KiB segment (byte-table CRC from shared memory).
+// Phase b: one thread per range folds its segments: crc = shift(crc, 8*seg_len) ^ seg_crc  (GF(2) mulmod).
+// ------------------------------------------------------------------------------------------------
+#define CRC_SEG 4096u
+#define CRC32_POLY 0xEDB88320u
+#define CRC64_POLY 0xC96C5795D7870F42ull
+
+struct LzbCrcRange {
+    uint64_t off, len;
+    uint64_t first_seg;  // index of this range's first segment in the partial arrays
+};
+
+extern "C" __global__ void lzb_crc_partial_kernel(const uint8_t* __restrict__ data, const LzbCrcRange* __restrict__ ranges,
+                                                  const uint32_t* __restrict__ seg_range, uint64_t n_segs,
+                                                  uint32_t* part32, uint64_t* part64) {
+    __shared__ uint32_t t32[256];
+    __shared__ uint64_t t64[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = i;
+        uint64_t e = i;
+        for (int k = 0; k < 8; k++) {
+            c = (c & 1) ? (c >> 1) ^ CRC32_POLY : c >> 1;
+            e = (e & 1) ? (e >> 1) ^ CRC64_POLY : e >> 1;
+        }
+        t32[i] = c;
+        t64[i] = e;
+    }
+    __syncthreads();
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_segs) return;
+    const LzbCrcRange r = ranges[seg_range[s]];
+    const uint64_t k = s - r.first_seg;
+    const uint64_t beg = k * CRC_SEG;
+    const uint32_t n = (uint32_t)min((uint64_t)CRC_SEG, r.len - beg);
+    const uint8_t* p = data + r.off + beg;
+    // raw (non-inverted) register from zero: linear in the message, which is what the fold needs
+    uint32_t c = 0;
+    uint64_t e = 0;
+    uint32_t i = 0;
+    for (; i < n && ((uintptr_t)(p + i) & 15u); i++) {
+        uint8_t b = p[i];
+        c = t32[(c ^ b) & 0xFF] ^ (c >> 8);
+        e = t64[(e ^ b) & 0xFF] ^ (e >> 8);
+    }
+    for (; i + 16 <= n; i += 16) {
+        uint4 v = *reinterpret_cast<const uint4*>(p + i);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int b8 = 0; b8 < 4; b8++) {
+                uint32_t b = (w[j] >> (8 * b8)) & 0xFF;
+                c = t32[(c ^ b) & 0xFF] ^ (c >> 8);
+                e = t64[(e ^ b) & 0xFF] ^ (e >> 8);
+            }
+        }
+    }
+    for (; i < n; i++) {
+        uint8_t b = p[i];
+        c = t32[(c ^ b) & 0xFF] ^ (c >> 8);
+        e = t64[(e ^ b) & 0xFF] ^ (e >> 8);
+    }
+    part32[s] = c;
+    part64[s] = e;
+}
+
+// a(x) * b(x) mod P in the reflected representation (bit 31 / bit 63 = x^0)
+__device__ __forceinline__ uint32_t mulmod32(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) {
+        if (a & 0x80000000u) r ^= b;
+        a <<= 1;
+        b = (b & 1) ? (b >> 1) ^ CRC32_POLY : b >> 1;
+    }
+    return r;
+}
+__device__ __forceinline__ uint64_t mulmod64(uint64_t a, uint64_t b) {
+    uint64_t r = 0;
+    for (int i = 0; i < 64; i++) {
+        if (a & 0x8000000000000000ull) r ^= b;
+        a <<= 1;
+        b = (b & 1) ? (b >> 1) ^ CRC64_POLY : b >> 1;
+    }
+    return r;
+}
+// x^(8*nbytes) mod P
+__device__ uint32_t xpow32(uint64_t nbytes) {
+    uint32_t r = 0x80000000u, sq = 0x00800000u;  // 1, x^8
+    while (nbytes) {
+        if (nbytes & 1) r = mulmod32(r, sq);
+        sq = mulmod32(sq, sq);
+        nbytes >>= 1;
+    }
+    return r;
+}
+__device__ uint64_t xpow64(uint64_t nbytes) {
+    uint64_t r = 0x8000000000000000ull, sq = 0x0080000000000000ull;
+    while (nbytes) {
+        if (nbytes & 1) r = mulmod64(r, sq);
+        sq = mulmod64(sq, sq);
+        nbytes >>= 1;
+    }
+    return r;
+}
+
+extern "C" __global__ void lzb_crc_fold_kernel(const LzbCrcRange* __restrict__ ranges, uint32_t n_ranges,
+                                               const uint32_t* __restrict__ part32, const uint64_t* __restrict__ part64,
+                                               uint32_t* crc32, uint64_t* crc64) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_ranges) return;
+    const LzbCrcRange rg = ranges[r];
+    const uint64_t nseg = (rg.len + CRC_SEG - 1) / CRC_SEG;
+    const uint32_t f32 = xpow32(CRC_SEG);
+    const uint64_t f64 = xpow64(CRC_SEG);
+    // register starts at all-ones (init), each segment: reg = reg * x^(8*len) + raw(segment)
+    uint32_t c = 0xFFFFFFFFu;
+    uint64_t e = ~0ull;
+    for (uint64_t k = 0; k < nseg; k++) {
+        const uint64_t sl = min((uint64_t)CRC_SEG, rg.len - k * CRC_SEG);
+        const uint32_t m32 = sl == CRC_SEG ? f32 : xpow32(sl);
+        const uint64_t m64 = sl == CRC_SEG ? f64 : xpow64(sl);
+        c = mulmod32(c, m32) ^ part32[rg.first_seg + k];
+        e = mulmod64(e, m64) ^ part64[rg.first_seg + k];
+    }
+    crc32[r] = c ^ 0xFFFFFFFFu;
+    crc64[r] = ~e;
+}

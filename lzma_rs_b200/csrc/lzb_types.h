@@ -1,0 +1,65 @@
+// lzb_types.h -- work-item / result records shared by the host side and the CUDA kernels.
+#pragma once
+#include <stdint.h>
+
+#include "lzma_b200.h"
+
+// One independent compressed stream (a .lzma payload, a raw LZMA2 stream, or one .xz block).
+// Offsets are relative to the input / output blobs handed to the kernel.
+struct LzbItem {
+    uint64_t in_off;    // first byte the decoder reads (LZMA: the range-coder bytes after the header)
+    uint64_t in_len;    // bytes readable from in_off (to the end of the caller's input for this stream)
+    uint64_t out_off;   // where this stream's output starts in the output blob
+    uint64_t out_cap;   // capacity in bytes
+    uint64_t unpacked;  // LZMA: expected unpacked size, or LZB_UNKNOWN_SIZE (end-marker mode)
+    uint64_t memlimit;  // LZMA: Options::memlimit (UINT64_MAX = unlimited)
+    uint32_t dict_size; // LZMA: max(header dict size, 0x1000)   (lzma.rs:122-126)
+    uint8_t kind;       // LZB_ITEM_*
+    uint8_t lc, lp, pb; // LZMA properties (LZMA2 reads its own from chunk headers)
+    uint32_t hdr_len;   // bytes of container header already consumed before in_off (LZMA: 13 or 5)
+    int32_t preset_code;// LZB_ITEM_PRESET: status decided before the decode (header errors)
+    uint64_t preset_a0;
+};
+
+enum { LZB_ITEM_LZMA = 0, LZB_ITEM_LZMA2 = 1, LZB_ITEM_PRESET = 2 };
+#define LZB_UNKNOWN_SIZE 0xFFFFFFFFFFFFFFFFull
+
+// Per-stream result written by the decode kernel.
+struct LzbResult {
+    int32_t code;      // LZB_OK / LZB_E_*
+    uint32_t chunks;   // LZMA2 chunks walked (diagnostic)
+    uint64_t a0, a1;   // message arguments of the failing site
+    uint64_t out_len;  // bytes produced into the output buffer
+    uint64_t sink_len; // bytes the reference would have handed to its io::Write sink
+    uint64_t consumed; // input bytes consumed from in_off
+};
+
+// Per-stream scan summary (K2).
+struct LzbScan {
+    uint64_t unpacked; // exact for well-formed LZMA2 / known-size LZMA; heuristic otherwise
+    uint32_t flags;    // bit0: walk ended at a 0x00 control byte (well-formed framing)
+    uint8_t max_lclp;  // largest lc+lp any chunk (or the .lzma header) asks for
+    uint8_t pad[3];
+};
+
+// Probability-table layout in shared memory (u16 indices); see DESIGN.md "K1".
+enum {
+    T_IS_MATCH = 0,      // [12][16]  (state<<4)+pos_state        lzma.rs:175,289
+    T_IS_REP = 192,      // [12]                                  lzma.rs:176
+    T_IS_REP_G0 = 204,   // [12]
+    T_IS_REP_G1 = 216,   // [12]
+    T_IS_REP_G2 = 228,   // [12]
+    T_IS_REP0LONG = 240, // [12][16]                              lzma.rs:180,317
+    T_POS_SLOT = 432,    // [4][64]                               lzma.rs:172
+    T_POS_DEC = 688,     // [115] (+1 pad)                        lzma.rs:174
+    T_ALIGN = 804,       // [16]                                  lzma.rs:173
+    T_LEN = 820,         // choice, choice2, low[16][8], mid[16][8], high[256]   rangecoder.rs:202-209
+    T_REP_LEN = 1334,    // same
+    T_LIT = 1848,        // [1<<(lc+lp)][0x300]                   lzma.rs:194
+    T_LEN_SIZE = 514,
+    T_LEN_LOW = 2,
+    T_LEN_MID = 2 + 128,
+    T_LEN_HIGH = 2 + 256
+};
+
+static inline uint32_t lzb_table_u16(uint32_t lclp) { return (uint32_t)T_LIT + (0x300u << lclp); }

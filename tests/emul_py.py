@@ -1,0 +1,72 @@
+"""Loads tests/host_emulation/liblzb_emul.so: K1's decode core compiled as plain C++ (1-lane warp) behind the
+product's host planning code.  CPU-tier test infrastructure only; never used by the product or by GPU tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from lzma_rs_b200 import _native
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_DIR = os.path.join(_HERE, "host_emulation")
+_SO = os.path.join(_DIR, "liblzb_emul.so")
+_SRCS = [os.path.join(_DIR, "emul.cpp"), os.path.join(_ROOT, "lzma_rs_b200", "csrc", "lzb_plan.cpp")]
+_DEPS = _SRCS + [os.path.join(_ROOT, "lzma_rs_b200", "csrc", f) for f in
+                 ("lzb_decode_core.h", "lzb_plan.h", "lzb_types.h")] + [os.path.join(_ROOT, "include", "lzma_b200.h")]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if (not os.path.exists(_SO)) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in _DEPS):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                                   "-I" + os.path.join(_ROOT, "include"),
+                                   "-I" + os.path.join(_ROOT, "lzma_rs_b200", "csrc"), "-o", _SO] + _SRCS)
+        _lib = C.CDLL(_SO)
+        vp = C.c_void_p
+        _lib.emul_decode_batch.argtypes = [C.c_int, C.POINTER(_native.Options), vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
+        _lib.emul_scan_capacity.argtypes = [C.c_int, C.POINTER(_native.Options), vp, C.c_uint64]
+        _lib.emul_scan_capacity.restype = C.c_uint64
+        _lib.lzb_format_error.argtypes = [C.POINTER(_native.Status), C.c_char_p, C.c_size_t]
+        _lib.lzb_format_error.restype = C.c_size_t
+    return _lib
+
+
+class Result:
+    def __init__(self, data, consumed, status, display):
+        self.data, self.consumed, self.status, self.display = data, consumed, status, display
+
+    @property
+    def ok(self):
+        return int(self.status["code"]) == 0
+
+
+def decode_batch(fmt, streams, opt=None, capacities=None):
+    """Same contract as lzma_rs_b200.Context.decode_batch, executed by the host emulation."""
+    L = lib()
+    opt = opt or _native.make_options()
+    blob, in_off = _native.pack_streams(streams)
+    n = len(streams)
+    if capacities is None:
+        capacities = [L.emul_scan_capacity(fmt, C.byref(opt), blob.ctypes.data + int(in_off[i]),
+                                           int(in_off[i + 1] - in_off[i])) for i in range(n)]
+    capacities = np.asarray(capacities, dtype=np.uint64)
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum((capacities + np.uint64(15)) // np.uint64(16) * np.uint64(16), out=out_off[1:])
+    out = np.zeros(int(out_off[-1]) + 16, dtype=np.uint8)
+    out_len = np.zeros(n, dtype=np.uint64)
+    consumed = np.zeros(n, dtype=np.uint64)
+    st = np.zeros(n, dtype=_native.STATUS_DTYPE)
+    rc = L.emul_decode_batch(fmt, C.byref(opt), blob.ctypes.data, in_off.ctypes.data, n, out.ctypes.data,
+                             out_off.ctypes.data, out_len.ctypes.data, consumed.ctypes.data, st.ctypes.data)
+    assert rc == 0, rc
+    res = []
+    for i in range(n):
+        o = int(out_off[i])
+        disp = "" if st[i]["code"] == 0 else _native.format_status(L, st[i])
+        res.append(Result(out[o:o + int(out_len[i])].tobytes(), int(consumed[i]), st[i].copy(), disp))
+    return res

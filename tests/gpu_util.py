@@ -1,0 +1,61 @@
+"""Helpers for the GPU tests: the product library driven through its C ABI (host and device entry points)."""
+import ctypes as C
+
+import numpy as np
+
+from lzma_rs_b200 import Context, _native, decompress
+
+
+def options_from(opts):
+    mode = opts.get("unpacked_mode", 0)
+    us = decompress.UnpackedSize(mode, opts.get("provided"))
+    return decompress.Options(unpacked_size=us, memlimit=opts.get("memlimit"))
+
+
+def host_decode(ctx, fmt, streams, opts):
+    """lzb_decode_batch (host buffers) with the LZB_E_CAPACITY retry lzb_decompress_alloc performs."""
+    o = options_from(opts)
+    res = ctx.decode_batch(fmt, streams, o)
+    for i, r in enumerate(res):
+        cap = None
+        while int(r.status["code"]) == _native.E_CAPACITY:
+            cap = max(int(r.status["a0"]) * 2, 1 << 16) if cap is None else cap * 2
+            r = ctx.decode_batch(fmt, [streams[i]], o, capacities=[cap])[0]
+        res[i] = r
+    return res
+
+
+class DeviceBatch:
+    """Raw streams resident in device memory (torch tensors), decoded through lzb_batch_* / lzb_decode_batch_device."""
+
+    def __init__(self, ctx, fmt, streams, capacities, opts=None):
+        import torch
+        self.ctx, self.fmt, self.n = ctx, fmt, len(streams)
+        self.lib = _native.load()
+        blob, self.in_off = _native.pack_streams(streams)
+        caps = (np.asarray(capacities, dtype=np.uint64) + np.uint64(15)) // np.uint64(16) * np.uint64(16)
+        self.out_off = np.zeros(self.n + 1, dtype=np.uint64)
+        np.cumsum(caps, out=self.out_off[1:])
+        self.d_in = torch.from_numpy(blob).cuda()
+        self.d_out = torch.zeros(int(self.out_off[-1]) + 16, dtype=torch.uint8, device="cuda")
+        self.opt = options_from(opts or {})._native()
+        self.out_len = np.zeros(self.n, dtype=np.uint64)
+        self.consumed = np.zeros(self.n, dtype=np.uint64)
+        self.st = np.zeros(self.n, dtype=_native.STATUS_DTYPE)
+
+    def decode(self):
+        import torch
+        rc = self.lib.lzb_decode_batch_device(self.ctx.handle, self.fmt, C.byref(self.opt), self.d_in.data_ptr(),
+                                              self.in_off.ctypes.data, self.n, self.d_out.data_ptr(),
+                                              self.out_off.ctypes.data, self.out_len.ctypes.data,
+                                              self.consumed.ctypes.data, self.st.ctypes.data, None)
+        assert rc == 0, (rc, self.ctx.last_error())
+        torch.cuda.synchronize()
+        return self
+
+    def output(self, i):
+        o = int(self.out_off[i])
+        return self.d_out[o:o + int(self.out_len[i])].cpu().numpy().tobytes()
+
+    def display(self, i):
+        return "" if self.st[i]["code"] == 0 else _native.format_status(self.lib, self.st[i])

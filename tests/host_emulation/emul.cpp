@@ -1,0 +1,82 @@
+// emul.cpp -- TEST INFRASTRUCTURE (never linked into the product library).
+// Builds K1's decode core (lzma_rs_b200/csrc/lzb_decode_core.h) as plain C++ with a 1-lane "warp", plugs it
+// into the product's host planning code (lzb_plan.cpp) through the Executor interface, and exposes the same
+// batch entry point as the C ABI.  This lets the CPU-only test tier check the decode logic, the container walk
+// and the status mapping against the oracle without a GPU.  The real GPU parity tests are tests/test_gpu_*.py.
+#include <string.h>
+
+#include <vector>
+
+#include "../../lzma_rs_b200/csrc/lzb_decode_core.h"
+#include "../../lzma_rs_b200/csrc/lzb_plan.h"
+
+namespace {
+class HostEmulExecutor : public lzb::Executor {
+   public:
+    HostEmulExecutor(const uint8_t* in, uint8_t* out) : in_(in), out_(out) {}
+    int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, LzbResult* results) override {
+        std::vector<uint16_t> T(lzb_table_u16(max_lclp) + 8);
+        for (uint32_t i = 0; i < n; i++) {
+            memset(&results[i], 0, sizeof results[i]);
+            decode_item(items + i, in_, out_, T.data(), max_lclp, results + i, 0);
+            if (results[i].code == LZB_E_UNSUPPORTED && results[i].a1 == max_lclp && results[i].a0 <= 4) {
+                std::vector<uint16_t> T4(lzb_table_u16(4) + 8);  // framing scan under-estimated lc+lp: retry with the max
+                decode_item(items + i, in_, out_, T4.data(), 4, results + i, 0);
+            }
+        }
+        return LZB_RC_OK;
+    }
+    int crc(const lzb::CrcRange* r, uint32_t n, uint32_t* c32, uint64_t* c64) override {
+        static uint32_t t32[256];
+        static uint64_t t64[256];
+        static bool init = false;
+        if (!init) {
+            for (uint32_t i = 0; i < 256; i++) {
+                uint32_t c = i;
+                uint64_t e = i;
+                for (int k = 0; k < 8; k++) {
+                    c = (c & 1) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+                    e = (e & 1) ? (e >> 1) ^ 0xC96C5795D7870F42ull : e >> 1;
+                }
+                t32[i] = c;
+                t64[i] = e;
+            }
+            init = true;
+        }
+        for (uint32_t i = 0; i < n; i++) {
+            uint32_t c = 0xFFFFFFFFu;
+            uint64_t e = ~0ull;
+            for (uint64_t k = 0; k < r[i].len; k++) {
+                uint8_t b = out_[r[i].off + k];
+                c = t32[(c ^ b) & 0xFF] ^ (c >> 8);
+                e = t64[(e ^ b) & 0xFF] ^ (e >> 8);
+            }
+            c32[i] = c ^ 0xFFFFFFFFu;
+            c64[i] = ~e;
+        }
+        return LZB_RC_OK;
+    }
+
+   private:
+    const uint8_t* in_;
+    uint8_t* out_;
+};
+}  // namespace
+
+extern "C" int emul_decode_batch(int fmt, const lzb_options* opt, const uint8_t* in, const uint64_t* in_off, uint32_t n,
+                                 uint8_t* out, const uint64_t* out_off, uint64_t* out_len, uint64_t* consumed,
+                                 lzb_status* st) {
+    HostEmulExecutor ex(in, out);
+    std::vector<lzb::StreamOut> outs(n);
+    int rc = lzb::decode_batch(ex, fmt, opt, in, in_off, n, out_off, outs.data());
+    for (uint32_t i = 0; i < n; i++) {
+        out_len[i] = outs[i].out_len;
+        consumed[i] = outs[i].consumed;
+        st[i] = outs[i].st;
+    }
+    return rc;
+}
+
+extern "C" uint64_t emul_scan_capacity(int fmt, const lzb_options* opt, const uint8_t* p, uint64_t len) {
+    return lzb::scan_capacity(fmt, opt, p, len);
+}

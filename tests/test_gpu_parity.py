@@ -1,0 +1,166 @@
+"""GPU tier: the CUDA path (through the C ABI) against the oracle, bit-exact, on the whole parity corpus, the
+reference's golden vectors, and BASELINE-sized batches via size-independent properties."""
+import hashlib
+import io
+
+import numpy as np
+import pytest
+
+import cases
+import corpus
+import oracle_py as oracle
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from lzma_rs_b200 import Context
+    c = Context()
+    yield c
+    c.close()
+
+
+def _host(ctx):
+    import gpu_util
+    return lambda fmt, streams, opts: gpu_util.host_decode(ctx, fmt, streams, opts)
+
+
+@pytest.mark.parametrize("family", ["valid_lzma2_cases", "valid_lzma_cases", "hand_encoded_cases",
+                                    "truncation_and_corruption_cases", "xz_cases"])
+def test_cuda_path_matches_oracle(ctx, family):
+    bad, n = [], 0
+    for (fmt, okey), named in parity.group_cases(getattr(cases, family)()).items():
+        bad += parity.check_group(_host(ctx), fmt, dict(okey), named)
+        n += len(named)
+    assert not bad, f"{len(bad)}/{n} mismatches:\n" + "\n".join(bad[:40])
+
+
+def test_golden_vectors_on_gpu(ctx, golden):
+    """Every golden vector of the reference's own tests (tests/golden/, see make_golden.py) through the CUDA path."""
+    fmt = {"lzma": 0, "xz": 2}
+    for f in ("lzma", "xz"):
+        vs = list(golden.vectors(fmt=f))
+        res = _host(ctx)(fmt[f], [golden.compressed(v) for v in vs], {})
+        for v, r in zip(vs, res):
+            assert hashlib.sha256(r.data).hexdigest() == v["plain_sha256"], v["name"]
+            if "error" in v:
+                how, want = v["error_match"], v["error"]
+                assert (r.display == want if how == "exact" else r.display.startswith(want) if how == "prefix"
+                        else want in r.display), (v["name"], r.display)
+            else:
+                assert r.ok and r.consumed == v["length"], (v["name"], r.display)
+
+
+def test_reference_api_mirror(ctx, golden):
+    """lzma_rs::{lzma_decompress, lzma2_decompress, xz_decompress} mirrors: reader/writer roles and error types."""
+    import lzma_rs_b200 as L
+    v = next(x for x in golden.vectors() if x["name"] == "foo.txt.lzma")
+    out = io.BytesIO()
+    L.lzma_decompress(io.BytesIO(golden.compressed(v)), out)
+    assert hashlib.sha256(out.getvalue()).hexdigest() == v["plain_sha256"]
+    v = next(x for x in golden.vectors() if x["name"] == "good-1-lzma2-3.xz")
+    assert hashlib.sha256(L.xz_decompress(golden.compressed(v))).hexdigest() == v["plain_sha256"]
+    data = corpus.mixed_text(77, 100_000)
+    rd = io.BytesIO(corpus.raw_lzma2(data) + b"tail")
+    assert L.lzma2_decompress(rd) == data
+    assert rd.read() == b"tail"  # only the consumed bytes were taken from the reader
+    with pytest.raises(L.error.HeaderTooShort):
+        L.lzma_decompress(b"")
+    with pytest.raises(L.error.LzmaError, match="must be < 225"):
+        L.lzma_decompress(b"\xff" * 32)
+    v = next(x for x in golden.vectors() if x["name"] == "corrupt-footer.xz")
+    out = io.BytesIO()
+    with pytest.raises(L.error.XzError) as ei:
+        L.xz_decompress(golden.compressed(v), out)
+    assert str(ei.value) == "xz error: Invalid footer CRC32: expected 0x01234567 but got 0x8b0d303e"
+    assert hashlib.sha256(out.getvalue()).hexdigest() == v["plain_sha256"]  # the valid block was already written
+    opts = L.decompress.Options(unpacked_size=L.decompress.UnpackedSize.ReadHeaderButUseProvided(None), memlimit=0)
+    with pytest.raises(L.error.LzmaError, match="exceeded memory limit of 0"):
+        L.lzma_decompress_with_options(corpus.dumb_lzma(b"Some data"), None, opts)
+
+
+def test_device_resident_batch(ctx):
+    """lzb_decode_batch_device: inputs and outputs stay in HBM (what bench.py times)."""
+    import gpu_util
+    plains = [corpus.mixed_text(500 + i, int(s)) for i, s in enumerate([0, 1, 100, 65536, 65536, 200_000, 300_000, 4097])]
+    comp = [corpus.raw_lzma2(p, dict_size=1 << 20) for p in plains]
+    b = gpu_util.DeviceBatch(ctx, 1, comp, [len(p) for p in plains]).decode()
+    for i, p in enumerate(plains):
+        assert b.st[i]["code"] == 0, b.display(i)
+        assert b.output(i) == p and int(b.consumed[i]) == len(comp[i])
+    # .lzma on the device path + exact capacity too small -> LZB_E_CAPACITY
+    comp1 = [corpus.lzma_alone_known_size(p, dict_size=1 << 16) for p in plains[2:6]]
+    b = gpu_util.DeviceBatch(ctx, 0, comp1, [len(p) + 288 for p in plains[2:6]]).decode()
+    for i, p in enumerate(plains[2:6]):
+        assert b.st[i]["code"] == 0 and b.output(i) == p, b.display(i)
+    b = gpu_util.DeviceBatch(ctx, 1, comp[3:5], [1000, 65536]).decode()
+    assert b.st[0]["code"] == -1 and b.st[1]["code"] == 0
+
+
+def test_device_crc(ctx):
+    import ctypes as C
+    import torch
+    import zlib
+    from lzma_rs_b200 import _native
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, size=3_000_000, dtype=np.uint8)
+    d = torch.from_numpy(data).cuda()
+    off = np.array([0, 1, 17, 4096, 5000, 100_003, 1_000_000, 0], dtype=np.uint64)
+    ln = np.array([0, 1, 4095, 4096, 4097, 300_001, 2_000_000, 3_000_000], dtype=np.uint64)
+    c32 = np.zeros(len(off), dtype=np.uint32)
+    c64 = np.zeros(len(off), dtype=np.uint64)
+    rc = _native.load().lzb_crc_device(ctx.handle, d.data_ptr(), off.ctypes.data, ln.ctypes.data, len(off),
+                                       c32.ctypes.data, c64.ctypes.data, None)
+    assert rc == 0
+    for i in range(len(off)):
+        seg = data[int(off[i]):int(off[i] + ln[i])].tobytes()
+        assert int(c32[i]) == zlib.crc32(seg), i
+        assert int(c64[i]) == oracle.crc64(seg), i
+
+
+def test_config2_scale_properties(ctx):
+    """BASELINE config 2 shape (many 64 KiB LZMA2 streams): round trip against the plaintexts the streams were made
+    from + checksum-of-checksums against the oracle; 1024 streams keeps the oracle side to seconds."""
+    import gpu_util
+    n = 1024
+    comp, plain = corpus.build_lzma2_corpus(2, n, lambda i: 65536, 1 << 18, distinct=256, threads=8)
+    b = gpu_util.DeviceBatch(ctx, 1, comp, [len(p) for p in plain]).decode()
+    assert (b.st["code"] == 0).all()
+    h_gpu, h_ref = hashlib.sha256(), hashlib.sha256()
+    for i in range(n):
+        out = b.output(i)
+        assert out == plain[i], i
+        h_gpu.update(hashlib.sha256(out).digest())
+    for i in range(0, n, 16):  # oracle on a sample (every 16th stream) + plaintext identity on all
+        r = oracle.lzma2_decompress(comp[i])
+        assert r.ok and r.out == plain[i]
+    for i in range(n):
+        h_ref.update(hashlib.sha256(plain[i]).digest())
+    assert h_gpu.digest() == h_ref.digest()
+
+
+def test_config5_rep0_stress(ctx):
+    """BASELINE config 5: all-overlapping rep0 matches (dist=1, len=273)."""
+    import gpu_util
+    n = 256
+    streams = [corpus.rep0_stress_lzma2(262144, byte=i & 0xFF) for i in range(n)]
+    b = gpu_util.DeviceBatch(ctx, 1, streams, [262144] * n).decode()
+    assert (b.st["code"] == 0).all()
+    for i in range(n):
+        assert b.output(i) == bytes([i & 0xFF]) * 262144
+
+
+def test_config4_xz_multiblock(ctx):
+    """BASELINE config 4 shape: multi-block .xz files with CRC32 block checks."""
+    files, plains = [], []
+    for i in range(32):
+        p = corpus.mixed_text(4_000_000 + i, 1 << 20)
+        plains.append(p)
+        files.append(corpus.xz_file(p, block_size=1 << 18, check=corpus.CHECK_CRC32))
+    res = _host(ctx)(2, files, {})
+    for r, p, f in zip(res, plains, files):
+        assert r.ok and r.data == p and r.consumed == len(f), r.display
