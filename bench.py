@@ -195,8 +195,10 @@ def main():
 
     d_in = torch.from_numpy(blob).cuda()
     d_out = torch.zeros(int(out_off[-1]) + 16, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # an explicit stream: the library treats a NULL handle as "use the ctx stream"
+    torch.cuda.synchronize()
     sptr = C.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
     opt = _native.make_options()
     batch = C.c_void_p()
     rc = lib.lzb_batch_prepare(ctx.handle, _native.FMT_LZMA2, C.byref(opt), d_in.data_ptr(), in_off.ctypes.data, n,

@@ -140,9 +140,13 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
         goto finish;         \
     } while (0)
 
+// LIT_GLOBAL = false: all probability tables in shared memory (lc+lp <= tab_lclp <= 4; every LZMA2 stream).
+// LIT_GLOBAL = true : .lzma streams with lc+lp > 4 (legal up to 12, lzma.rs:62-66): the literal table
+//                     (0x300 << (lc+lp) u16, up to 6 MiB) lives in a per-warp global workspace `glit`.
+template <bool LIT_GLOBAL>
 LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t* __restrict__ in_blob,
-                                         uint8_t* out_blob, uint16_t* T, uint32_t tab_lclp, LzbResult* res,
-                                         int lane) {
+                                  uint8_t* out_blob, uint16_t* T, uint16_t* glit, uint32_t tab_lclp, LzbResult* res,
+                                  int lane) {
     Dec d;
     const bool is_lzma1 = itp->kind == LZB_ITEM_LZMA;
     const uint32_t p0 = (uint32_t)(itp->in_off & 3ull);
@@ -150,7 +154,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
     const uint32_t stream_lim = p0 + (uint32_t)itp->in_len;
     uint8_t* out = out_blob + itp->out_off;
     const uint32_t cap = (uint32_t)LZB_MIN(itp->out_cap, (uint64_t)0xFFFFF000u);
-    const uint32_t tab_u16 = T_LIT + (0x300u << tab_lclp);
+    const uint32_t tab_u16 = LIT_GLOBAL ? (uint32_t)T_LIT : T_LIT + (0x300u << tab_lclp);
+    uint16_t* const lit = LIT_GLOBAL ? glit : T + T_LIT;
     uint32_t opos = 0, dict_base = 0;
     uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
     uint32_t lc = 0, lp = 0, pb = 0;
@@ -195,6 +200,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
         if (lc + lp > tab_lclp) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
     }
     fill_tables(T, tab_u16, lane);
+    if (LIT_GLOBAL) fill_tables(glit, 0x300u << (lc + lp), lane);  // .lzma only: props never change mid-stream
 
     for (;;) {  // LZMA2 chunk loop (lzma2.rs:59-78); a .lzma stream is a single pass
         if (is_lzma1) {
@@ -292,7 +298,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
             if (!rc_bit(d, T + T_IS_MATCH + (state << 4) + pos_state)) {
                 // ---- literal, lzma.rs:287-307 + decode_literal 526-561
-                uint16_t* probs = T + T_LIT + (((len & lp_mask) << lc) + (prev_byte >> (8 - lc))) * 0x300u;
+                uint16_t* probs = lit + (((len & lp_mask) << lc) + (prev_byte >> (8 - lc))) * 0x300u;
                 uint32_t sym = 1;
                 if (state >= 7) {
                     if (!mb_valid) {  // last_n(rep[0] + 1), lzbuffer.rs:98-108 / 240-256

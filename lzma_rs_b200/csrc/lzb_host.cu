@@ -20,6 +20,9 @@ struct LzbCrcRange {
 
 extern "C" __global__ void lzb_decode_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
                                              LzbResult*, unsigned int*, uint32_t, uint32_t);
+extern "C" __global__ void lzb_decode_biglit_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
+                                                    LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*,
+                                                    unsigned long long);
 extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, const uint64_t*, const uint64_t*, uint32_t,
                                            LzbItem*, LzbScan*);
 extern "C" __global__ void lzb_crc_partial_kernel(const uint8_t*, const LzbCrcRange*, const uint32_t*, uint64_t,
@@ -60,11 +63,11 @@ struct lzb_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     int smem_optin = 0;
-    int smem_configured = -1;
+    int smem_configured = -1, smem_configured_big = -1;
     char err[320] = {0};
     std::mutex mu;
     DevBuf d_in, d_out, d_items, d_results, d_order, d_counter, d_scan, d_off, d_crc_ranges, d_crc_segmap, d_crc_part32,
-        d_crc_part64, d_crc_out32, d_crc_out64;
+        d_crc_part64, d_crc_out32, d_crc_out64, d_litws;
 };
 
 #define CUDA_TRY(ctx, call)                                                                         \
@@ -97,26 +100,86 @@ LaunchCfg decode_config(const lzb_ctx* ctx, uint32_t n, uint32_t lclp) {
     return c;
 }
 
-// Enqueues counter reset + K1 on `s`.  items/order/results/counter are device pointers.
-int launch_decode(lzb_ctx* ctx, cudaStream_t s, const LzbItem* d_items, const uint32_t* d_order, uint32_t n,
-                  const uint8_t* d_in_base, uint8_t* d_out_base, LzbResult* d_results, unsigned int* d_counter,
-                  const LaunchCfg& c) {
-    const int smem = (int)(c.warps * c.warp_bytes);
-    if (smem > ctx->smem_configured) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(lzb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
-        ctx->smem_configured = ctx->smem_optin;
+// One decode = up to two launches: streams whose tables fit shared memory (every LZMA2 stream; .lzma with
+// lc+lp <= 4) and .lzma streams with lc+lp > 4 whose literal table goes to a global workspace.
+struct DecodePlan {
+    std::vector<uint32_t> order_small, order_big;  // item indices, longest compressed stream first
+    LaunchCfg cfg_small{}, cfg_big{};
+    uint64_t big_stride_u16 = 0;  // workspace u16 per warp
+};
+
+void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lzma2_lclp_hint, DecodePlan* p) {
+    uint32_t lclp_small = 0, lclp_big = 0;
+    p->order_small.clear();
+    p->order_big.clear();
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t lclp = (uint32_t)items[i].lc + items[i].lp;
+        if (items[i].kind == LZB_ITEM_LZMA && lclp > 4) {
+            p->order_big.push_back(i);
+            lclp_big = std::max(lclp_big, lclp);
+        } else {
+            p->order_small.push_back(i);
+            if (items[i].kind == LZB_ITEM_LZMA) lclp_small = std::max(lclp_small, lclp);
+            if (items[i].kind == LZB_ITEM_LZMA2) lclp_small = std::max(lclp_small, std::min<uint32_t>(lzma2_lclp_hint, 4));
+        }
     }
-    CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), s));
-    lzb_decode_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, n, d_in_base, d_out_base, d_results, d_counter,
-                                                         c.lclp, c.warp_bytes);
-    CUDA_TRY(ctx, cudaGetLastError());
+    auto by_len = [&](uint32_t a, uint32_t b) { return items[a].in_len > items[b].in_len; };
+    std::stable_sort(p->order_small.begin(), p->order_small.end(), by_len);
+    std::stable_sort(p->order_big.begin(), p->order_big.end(), by_len);
+    p->cfg_small = decode_config(ctx, (uint32_t)p->order_small.size(), lclp_small);
+    if (!p->order_big.empty()) {
+        LaunchCfg& c = p->cfg_big;
+        c.lclp = lclp_big;
+        c.warp_bytes = ((uint32_t)T_LIT * 2 + 15u) & ~15u;
+        p->big_stride_u16 = (uint64_t)0x300u << lclp_big;
+        const uint64_t ws_budget = 1ull << 30;  // bound the workspace to 1 GiB
+        uint32_t total_warps = (uint32_t)std::min<uint64_t>(p->order_big.size(), (uint64_t)ctx->sm_count * 16);
+        total_warps = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(total_warps, ws_budget / (p->big_stride_u16 * 2)));
+        c.warps = std::max<uint32_t>(1, std::min<uint32_t>(16, (total_warps + ctx->sm_count - 1) / ctx->sm_count));
+        c.grid = std::max<uint32_t>(1, total_warps / c.warps);
+    }
+}
+
+// Enqueues counter resets + K1 launch(es) on `s`.  All pointers are device pointers; d_order holds order_small
+// followed by order_big; d_counter holds two counters.
+int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem* d_items, const uint32_t* d_order,
+                const uint8_t* d_in_base, uint8_t* d_out_base, LzbResult* d_results, unsigned int* d_counter) {
+    CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned int), s));
+    const uint32_t ns = (uint32_t)p.order_small.size(), nb = (uint32_t)p.order_big.size();
+    if (ns) {
+        const LaunchCfg& c = p.cfg_small;
+        const int smem = (int)(c.warps * c.warp_bytes);
+        if (smem > ctx->smem_configured) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(lzb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+            ctx->smem_configured = ctx->smem_optin;
+        }
+        lzb_decode_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, d_in_base, d_out_base, d_results,
+                                                             d_counter, c.lclp, c.warp_bytes);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    if (nb) {
+        const LaunchCfg& c = p.cfg_big;
+        const int smem = (int)(c.warps * c.warp_bytes);
+        if (smem > ctx->smem_configured_big) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(lzb_decode_biglit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               ctx->smem_optin));
+            ctx->smem_configured_big = ctx->smem_optin;
+        }
+        CUDA_TRY(ctx, ctx->d_litws.ensure((size_t)c.grid * c.warps * p.big_stride_u16 * 2));
+        lzb_decode_biglit_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order + ns, nb, d_in_base, d_out_base,
+                                                                    d_results, d_counter + 1, c.lclp, c.warp_bytes,
+                                                                    ctx->d_litws.as<uint16_t>(), p.big_stride_u16);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     return LZB_RC_OK;
 }
 
-void order_by_length(const LzbItem* items, uint32_t n, std::vector<uint32_t>& order) {
-    order.resize(n);
-    std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return items[a].in_len > items[b].in_len; });
+int upload_order(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, DevBuf& d_order) {
+    const size_t ns = p.order_small.size(), nb = p.order_big.size();
+    CUDA_TRY(ctx, d_order.ensure((ns + nb) * 4 + 4));
+    if (ns) CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, p.order_small.data(), ns * 4, cudaMemcpyHostToDevice, s));
+    if (nb) CUDA_TRY(ctx, cudaMemcpyAsync(d_order.as<uint32_t>() + ns, p.order_big.data(), nb * 4, cudaMemcpyHostToDevice, s));
+    return LZB_RC_OK;
 }
 
 // The one shipped Executor: work items run on the GPU.
@@ -126,13 +189,13 @@ class CudaExecutor : public lzb::Executor {
         : ctx_(ctx), s_(s), in_(d_in_base), out_(d_out_base) {}
 
     int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, LzbResult* results) override {
-        if (max_lclp > 4) return decode_without_big_tables(items, n, results);
         int rc = run(items, n, max_lclp, results);
         if (rc != LZB_RC_OK) return rc;
-        // the framing scan can under-estimate lc+lp on malformed streams: rerun just those with the LZMA2 maximum
+        // the framing scan can under-estimate lc+lp on malformed LZMA2 streams: rerun just those with the maximum
         std::vector<uint32_t> redo;
         for (uint32_t i = 0; i < n; i++)
-            if (results[i].code == LZB_E_UNSUPPORTED && results[i].a1 == max_lclp && results[i].a0 <= 4 && max_lclp < 4)
+            if (items[i].kind == LZB_ITEM_LZMA2 && results[i].code == LZB_E_UNSUPPORTED && results[i].a0 <= 4 &&
+                results[i].a1 < 4)
                 redo.push_back(i);
         if (!redo.empty()) {
             std::vector<LzbItem> sub(redo.size());
@@ -183,45 +246,18 @@ class CudaExecutor : public lzb::Executor {
     }
 
    private:
-    // .lzma allows lc+lp up to 12 (a 6 MiB literal table per stream), which does not fit the shared-memory
-    // tables of K1: those streams are reported LZB_E_UNSUPPORTED, everything else is decoded normally.
-    int decode_without_big_tables(const LzbItem* items, uint32_t n, LzbResult* results) {
-        std::vector<LzbItem> sub;
-        std::vector<uint32_t> idx;
-        uint32_t lclp = 0;
-        for (uint32_t i = 0; i < n; i++) {
-            const bool big = items[i].kind == LZB_ITEM_LZMA && (uint32_t)items[i].lc + items[i].lp > 4;
-            if (big) {
-                memset(&results[i], 0, sizeof results[i]);
-                results[i].code = LZB_E_UNSUPPORTED;
-                results[i].a0 = (uint32_t)items[i].lc + items[i].lp;
-            } else {
-                if (items[i].kind == LZB_ITEM_LZMA) lclp = std::max<uint32_t>(lclp, (uint32_t)items[i].lc + items[i].lp);
-                else if (items[i].kind == LZB_ITEM_LZMA2) lclp = 4;
-                sub.push_back(items[i]);
-                idx.push_back(i);
-            }
-        }
-        if (sub.empty()) return LZB_RC_OK;
-        std::vector<LzbResult> subres(sub.size());
-        int rc = run(sub.data(), (uint32_t)sub.size(), lclp, subres.data());
-        if (rc != LZB_RC_OK) return rc;
-        for (size_t k = 0; k < idx.size(); k++) results[idx[k]] = subres[k];
-        return LZB_RC_OK;
-    }
-    int run(const LzbItem* items, uint32_t n, uint32_t lclp, LzbResult* results) {
+    int run(const LzbItem* items, uint32_t n, uint32_t lclp_hint, LzbResult* results) {
         lzb_ctx* ctx = ctx_;
-        std::vector<uint32_t> order;
-        order_by_length(items, n, order);
+        DecodePlan plan;
+        make_plan(ctx, items, n, lclp_hint, &plan);
         CUDA_TRY(ctx, ctx->d_items.ensure(n * sizeof(LzbItem)));
         CUDA_TRY(ctx, ctx->d_results.ensure(n * sizeof(LzbResult)));
-        CUDA_TRY(ctx, ctx->d_order.ensure(n * 4));
         CUDA_TRY(ctx, ctx->d_counter.ensure(64));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items.p, items, n * sizeof(LzbItem), cudaMemcpyHostToDevice, s_));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_order.p, order.data(), n * 4, cudaMemcpyHostToDevice, s_));
-        LaunchCfg cfg = decode_config(ctx, n, lclp);
-        int rc = launch_decode(ctx, s_, ctx->d_items.as<LzbItem>(), ctx->d_order.as<uint32_t>(), n, in_, out_,
-                               ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>(), cfg);
+        int rc = upload_order(ctx, s_, plan, ctx->d_order);
+        if (rc != LZB_RC_OK) return rc;
+        rc = launch_plan(ctx, s_, plan, ctx->d_items.as<LzbItem>(), ctx->d_order.as<uint32_t>(), in_, out_,
+                         ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>());
         if (rc != LZB_RC_OK) return rc;
         CUDA_TRY(ctx, cudaMemcpyAsync(results, ctx->d_results.p, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s_));
         CUDA_TRY(ctx, cudaStreamSynchronize(s_));
@@ -268,7 +304,7 @@ extern "C" void lzb_destroy(lzb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_items, &ctx->d_results, &ctx->d_order, &ctx->d_counter, &ctx->d_scan,
                       &ctx->d_off, &ctx->d_crc_ranges, &ctx->d_crc_segmap, &ctx->d_crc_part32, &ctx->d_crc_part64,
-                      &ctx->d_crc_out32, &ctx->d_crc_out64};
+                      &ctx->d_crc_out32, &ctx->d_crc_out64, &ctx->d_litws};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -323,7 +359,7 @@ struct lzb_batch {
     uint8_t* d_out = nullptr;
     DevBuf d_items, d_results, d_order, d_counter, d_scan, d_off;
     std::vector<LzbItem> items;  // host copy (hdr_len, preset info)
-    LaunchCfg cfg{};
+    DecodePlan plan;
 };
 
 extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in, const uint64_t* in_off,
@@ -342,7 +378,6 @@ extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, 
     b->d_in = d_in;
     b->d_out = d_out;
     cudaStream_t s = ctx->stream;
-    int rc = LZB_RC_OK;
     auto fail = [&](int code) {
         lzb_batch_destroy(b);
         return code;
@@ -357,7 +392,6 @@ extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, 
     } while (0)
     B_TRY(b->d_items.ensure(n * sizeof(LzbItem)));
     B_TRY(b->d_results.ensure(n * sizeof(LzbResult)));
-    B_TRY(b->d_order.ensure(n * 4));
     B_TRY(b->d_counter.ensure(64));
     B_TRY(b->d_scan.ensure(n * sizeof(LzbScan)));
     B_TRY(b->d_off.ensure(2 * (size_t)(n + 1) * 8));
@@ -375,25 +409,10 @@ extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, 
     B_TRY(cudaStreamSynchronize(s));
     uint32_t lclp = 0;
     for (uint32_t i = 0; i < n; i++)
-        if (b->items[i].kind != LZB_ITEM_PRESET) lclp = std::max<uint32_t>(lclp, scan[i].max_lclp);
-    if (fmt == LZB_FMT_LZMA2 && lclp > 4) lclp = 4;
-    if (lzb_table_u16(lclp) * 2 > (uint32_t)ctx->smem_optin) {
-        // .lzma allows lc+lp up to 12 (a 6 MiB literal table): beyond shared memory on this path
-        for (uint32_t i = 0; i < n; i++) {
-            if (b->items[i].kind != LZB_ITEM_PRESET && scan[i].max_lclp > 4) {
-                b->items[i].kind = LZB_ITEM_PRESET;
-                b->items[i].preset_code = LZB_E_UNSUPPORTED;
-            }
-        }
-        B_TRY(cudaMemcpyAsync(b->d_items.p, b->items.data(), n * sizeof(LzbItem), cudaMemcpyHostToDevice, s));
-        lclp = 4;
-    }
-    std::vector<uint32_t> order;
-    order_by_length(b->items.data(), n, order);
-    B_TRY(cudaMemcpyAsync(b->d_order.p, order.data(), n * 4, cudaMemcpyHostToDevice, s));
+        if (b->items[i].kind == LZB_ITEM_LZMA2) lclp = std::max<uint32_t>(lclp, scan[i].max_lclp);
+    make_plan(ctx, b->items.data(), n, lclp, &b->plan);
+    if (upload_order(ctx, s, b->plan, b->d_order) != LZB_RC_OK) return fail(LZB_RC_CUDA);
     B_TRY(cudaStreamSynchronize(s));
-    b->cfg = decode_config(ctx, n, lclp);
-    (void)rc;
     *out = b;
     return LZB_RC_OK;
 #undef B_TRY
@@ -402,11 +421,13 @@ extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, 
 extern "C" int lzb_batch_launch(lzb_batch* b, void* cuda_stream) {
     if (!b) return LZB_RC_BAD_ARG;
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : b->ctx->stream;
-    return launch_decode(b->ctx, s, b->d_items.as<LzbItem>(), b->d_order.as<uint32_t>(), b->n, b->d_in, b->d_out,
-                         b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>(), b->cfg);
+    return launch_plan(b->ctx, s, b->plan, b->d_items.as<LzbItem>(), b->d_order.as<uint32_t>(), b->d_in, b->d_out,
+                       b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>());
 }
 
-extern "C" int lzb_batch_kernels_per_launch(const lzb_batch* b) { return b ? 1 : 0; }
+extern "C" int lzb_batch_kernels_per_launch(const lzb_batch* b) {
+    return b ? (int)!b->plan.order_small.empty() + (int)!b->plan.order_big.empty() : 0;
+}
 
 extern "C" int lzb_batch_collect(lzb_batch* b, void* cuda_stream, uint64_t* out_len, uint64_t* consumed, lzb_status* st) {
     if (!b) return LZB_RC_BAD_ARG;

@@ -23,11 +23,12 @@
 // ------------------------------------------------------------------------------------------------
 // K1 launcher
 // ------------------------------------------------------------------------------------------------
-// Persistent kernel: warps pull stream indices (pre-sorted longest first by the host) from a counter.
-extern "C" __global__ void __launch_bounds__(512, 1)
-    lzb_decode_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
-                      const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
-                      unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes) {
+// Persistent kernels: warps pull stream indices (pre-sorted longest first by the host) from a counter.
+template <bool LIT_GLOBAL>
+__device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order,
+                                            uint32_t n_items, const uint8_t* __restrict__ in_blob, uint8_t* out_blob,
+                                            LzbResult* results, unsigned int* counter, uint32_t tab_lclp,
+                                            uint32_t warp_smem_bytes, uint16_t* glit) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -38,9 +39,27 @@ extern "C" __global__ void __launch_bounds__(512, 1)
         slot = __shfl_sync(FULL_MASK, slot, 0);
         if (slot >= n_items) break;
         const uint32_t idx = order ? order[slot] : slot;
-        decode_item(items + idx, in_blob, out_blob, T, tab_lclp, results + idx, lane);
+        decode_item<LIT_GLOBAL>(items + idx, in_blob, out_blob, T, glit, tab_lclp, results + idx, lane);
         __syncwarp();
     }
+}
+
+extern "C" __global__ void __launch_bounds__(512, 1)
+    lzb_decode_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
+                      const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
+                      unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes) {
+    decode_loop<false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, nullptr);
+}
+
+// .lzma streams with lc+lp > 4: literal table in a per-warp global workspace (ws + warp_id * ws_stride_u16).
+extern "C" __global__ void __launch_bounds__(512, 1)
+    lzb_decode_biglit_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
+                             const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
+                             unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
+                             unsigned long long ws_stride_u16) {
+    const unsigned long long wid = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    decode_loop<true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes,
+                      ws + wid * ws_stride_u16);
 }
 
 // ------------------------------------------------------------------------------------------------

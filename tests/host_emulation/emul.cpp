@@ -15,13 +15,20 @@ class HostEmulExecutor : public lzb::Executor {
    public:
     HostEmulExecutor(const uint8_t* in, uint8_t* out) : in_(in), out_(out) {}
     int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, LzbResult* results) override {
-        std::vector<uint16_t> T(lzb_table_u16(max_lclp) + 8);
+        const uint32_t small_lclp = max_lclp > 4 ? 4 : max_lclp;
+        std::vector<uint16_t> T(lzb_table_u16(small_lclp) + 8), T4, G;
         for (uint32_t i = 0; i < n; i++) {
             memset(&results[i], 0, sizeof results[i]);
-            decode_item(items + i, in_, out_, T.data(), max_lclp, results + i, 0);
-            if (results[i].code == LZB_E_UNSUPPORTED && results[i].a1 == max_lclp && results[i].a0 <= 4) {
-                std::vector<uint16_t> T4(lzb_table_u16(4) + 8);  // framing scan under-estimated lc+lp: retry with the max
-                decode_item(items + i, in_, out_, T4.data(), 4, results + i, 0);
+            const uint32_t lclp = (uint32_t)items[i].lc + items[i].lp;
+            if (items[i].kind == LZB_ITEM_LZMA && lclp > 4) {  // literal table outside "shared memory"
+                G.assign((size_t)0x300u << lclp, 0);
+                decode_item<true>(items + i, in_, out_, T.data(), G.data(), lclp, results + i, 0);
+                continue;
+            }
+            decode_item<false>(items + i, in_, out_, T.data(), nullptr, small_lclp, results + i, 0);
+            if (results[i].code == LZB_E_UNSUPPORTED && results[i].a1 == small_lclp && results[i].a0 <= 4) {
+                T4.resize(lzb_table_u16(4) + 8);  // framing scan under-estimated lc+lp: retry with the LZMA2 maximum
+                decode_item<false>(items + i, in_, out_, T4.data(), nullptr, 4, results + i, 0);
             }
         }
         return LZB_RC_OK;
