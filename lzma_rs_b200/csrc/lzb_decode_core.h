@@ -68,17 +68,25 @@ LZB_DEV void rc_normalize(Dec& d) {
     }
 }
 
-// decode_bit, rangecoder.rs:93-120 (update == true off the stream API).
+// The arithmetic of decode_bit (rangecoder.rs:93-120) on a probability already in a register; returns the bit,
+// `np` = updated probability.  one: p -= p >> 5; zero: p += (2048 - p) >> 5  ==  p + ((K - p) >>arith 5) with
+// K = one ? 31 : 2048  (floor((31 - p) / 32) == -(p >> 5)).  Normalisation is the caller's next step.
+LZB_DEV bool rc_step(Dec& d, uint32_t pv, uint32_t& np) {
+    const uint32_t bound = (d.range >> 11) * pv;
+    const bool one = d.code >= bound;
+    const uint32_t rb = d.range - bound;
+    d.range = one ? rb : bound;
+    if (one) d.code -= bound;
+    const uint32_t k = one ? 31u : 2048u;
+    np = pv + (uint32_t)((int32_t)(k - pv) >> 5);
+    return one;
+}
+
+// decode_bit on a table entry
 LZB_DEV uint32_t rc_bit(Dec& d, uint16_t* prob) {
-    uint32_t pv = *prob;
-    uint32_t bound = (d.range >> 11) * pv;
-    bool one = d.code >= bound;
-    d.range = one ? d.range - bound : bound;
-    d.code = one ? d.code - bound : d.code;
-    // one: p -= p >> 5 ; zero: p += (2048 - p) >> 5  ==  p -= (p + off) >> 5 (arithmetic), off = one ? 0 : 31-2048
-    int off = one ? 0 : (31 - 2048);
-    pv = pv - (uint32_t)(((int)pv + off) >> 5);
-    *prob = (uint16_t)pv;
+    uint32_t np;
+    const bool one = rc_step(d, *prob, np);
+    *prob = (uint16_t)np;
     rc_normalize(d);
     return one ? 1u : 0u;
 }
@@ -86,41 +94,72 @@ LZB_DEV uint32_t rc_bit(Dec& d, uint16_t* prob) {
 // get(count), rangecoder.rs:72-90
 LZB_DEV uint32_t rc_direct(Dec& d, uint32_t count) {
     uint32_t r = 0;
+#pragma unroll 1
     for (uint32_t i = 0; i < count; i++) {
         d.range >>= 1;
-        uint32_t b = d.code >= d.range;
+        const bool b = d.code >= d.range;
         if (b) d.code -= d.range;
         rc_normalize(d);
-        r = (r << 1) | b;
+        r = (r << 1) | (b ? 1u : 0u);
     }
     return r;
 }
 
-// parse_bit_tree, rangecoder.rs:122-134
-template <int NB>
-LZB_DEV uint32_t rc_tree(Dec& d, uint16_t* probs) {
+// Both children of tree node m are adjacent u16 (indices 2m, 2m+1): one aligned 32-bit load fetches the next
+// level's probability before the current decision is known, taking the LDS latency off the serial chain.
+LZB_DEV uint32_t ld_pair(const uint16_t* p) {
+#ifdef __CUDACC__
+    return *reinterpret_cast<const uint32_t*>(p);
+#else
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 16);
+#endif
+}
+
+// Bit-tree walk (parse_bit_tree, rangecoder.rs:122-134) of `nb` levels over a 4-byte aligned table; returns
+// the final node index m in [2^nb, 2^(nb+1)).  Forward value = m - 2^nb; the reverse trees
+// (parse_reverse_bit_tree, 136-151) walk the same nodes, so their value is the bit reversal of that.
+template <bool UNROLL, int NB_CONST>
+LZB_DEV uint32_t rc_tree_walk(Dec& d, uint16_t* probs, uint32_t nb_rt) {
+    const uint32_t nb = UNROLL ? (uint32_t)NB_CONST : nb_rt;
     uint32_t m = 1;
+    uint32_t pv = probs[1];
+    uint32_t pair = nb > 1 ? ld_pair(probs + 2) : 0u;
+    if (UNROLL) {
 #pragma unroll
-    for (int i = 0; i < NB; i++) m = (m << 1) | rc_bit(d, probs + m);
-    return m - (1u << NB);
-}
-
-// parse_reverse_bit_tree, rangecoder.rs:136-151
-LZB_DEV uint32_t rc_rtree(Dec& d, uint16_t* probs, uint32_t nb) {
-    uint32_t m = 1, r = 0;
-    for (uint32_t i = 0; i < nb; i++) {
-        uint32_t b = rc_bit(d, probs + m);
-        m = (m << 1) | b;
-        r |= b << i;
+        for (int i = 0; i < NB_CONST; i++) {
+            uint32_t np;
+            const bool one = rc_step(d, pv, np);
+            probs[m] = (uint16_t)np;
+            m = (m << 1) | (one ? 1u : 0u);
+            pv = one ? (pair >> 16) : (pair & 0xFFFFu);
+            if (i + 2 < NB_CONST) pair = ld_pair(probs + 2 * m);
+            rc_normalize(d);
+        }
+    } else {
+#pragma unroll 1
+        for (uint32_t i = 0; i < nb; i++) {
+            uint32_t np;
+            const bool one = rc_step(d, pv, np);
+            probs[m] = (uint16_t)np;
+            m = (m << 1) | (one ? 1u : 0u);
+            pv = one ? (pair >> 16) : (pair & 0xFFFFu);
+            if (i + 2 < nb) pair = ld_pair(probs + 2 * m);
+            rc_normalize(d);
+        }
     }
-    return r;
+    return m;
 }
 
-// LenDecoder::decode, rangecoder.rs:256-269
-LZB_DEV uint32_t rc_len(Dec& d, uint16_t* L, uint32_t pos_state) {
-    if (!rc_bit(d, L + 0)) return rc_tree<3>(d, L + T_LEN_LOW + pos_state * 8);
-    if (!rc_bit(d, L + 1)) return 8 + rc_tree<3>(d, L + T_LEN_MID + pos_state * 8);
-    return 16 + rc_tree<8>(d, L + T_LEN_HIGH);
+LZB_DEV uint32_t rc_tree_rt(Dec& d, uint16_t* probs, uint32_t nb) { return rc_tree_walk<false, 0>(d, probs, nb); }
+
+LZB_DEV uint32_t rev_bits(uint32_t v, uint32_t nb) {  // the low nb bits of v, reversed
+#ifdef __CUDACC__
+    return __brev(v) >> (32 - nb);
+#else
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < nb; i++) r |= ((v >> i) & 1u) << (nb - 1 - i);
+    return r;
+#endif
 }
 
 LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
@@ -296,9 +335,22 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
             }
             const uint32_t pos_state = len & pb_mask;
 
-            if (!rc_bit(d, T + T_IS_MATCH + (state << 4) + pos_state)) {
+            // literal context row (decode_literal, lzma.rs:526-538).  After a literal (state < 7) prev_byte is in a
+            // register, so the root of the plain literal tree is fetched while is_match is being decoded.
+            uint16_t* probs = lit + (((len & lp_mask) << lc) + (prev_byte >> (8 - lc))) * 0x300u;
+            const uint32_t p_is_match = T[T_IS_MATCH + (state << 4) + pos_state];
+            uint32_t lit_pv = 0, lit_pair = 0;
+            if (state < 7) {
+                lit_pv = probs[1];
+                lit_pair = ld_pair(probs + 2);
+            }
+            uint32_t np_im;
+            const bool is_lz = rc_step(d, p_is_match, np_im);
+            T[T_IS_MATCH + (state << 4) + pos_state] = (uint16_t)np_im;
+            rc_normalize(d);
+
+            if (!is_lz) {
                 // ---- literal, lzma.rs:287-307 + decode_literal 526-561
-                uint16_t* probs = lit + (((len & lp_mask) << lc) + (prev_byte >> (8 - lc))) * 0x300u;
                 uint32_t sym = 1;
                 if (state >= 7) {
                     if (!mb_valid) {  // last_n(rep[0] + 1), lzbuffer.rs:98-108 / 240-256
@@ -309,15 +361,29 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                         match_byte = out[opos - rep0 - 1];
                     }
                     uint32_t mb = match_byte;
+#pragma unroll 1
                     do {
-                        uint32_t match_bit = (mb >> 7) & 1u;
+                        const uint32_t match_bit = (mb >> 7) & 1u;
                         mb <<= 1;
-                        uint32_t bit = rc_bit(d, probs + ((1u + match_bit) << 8) + sym);
+                        const uint32_t bit = rc_bit(d, probs + ((1u + match_bit) << 8) + sym);
                         sym = (sym << 1) | bit;
                         if (match_bit != bit) break;
                     } while (sym < 0x100);
+#pragma unroll 1
+                    while (sym < 0x100) sym = (sym << 1) | rc_bit(d, probs + sym);
+                } else {  // plain 8-level walk with the next level's pair prefetched
+                    uint32_t pv = lit_pv, pair = lit_pair;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        uint32_t np;
+                        const bool one = rc_step(d, pv, np);
+                        probs[sym] = (uint16_t)np;
+                        sym = (sym << 1) | (one ? 1u : 0u);
+                        pv = one ? (pair >> 16) : (pair & 0xFFFFu);
+                        if (i < 6) pair = ld_pair(probs + 2 * sym);
+                        rc_normalize(d);
+                    }
                 }
-                while (sym < 0x100) sym = (sym << 1) | rc_bit(d, probs + sym);
                 if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
                 if (opos >= mem_stop) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
                 if (opos >= cap) FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);
@@ -331,64 +397,76 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
             // ---- LZ, lzma.rs:309-390
             uint32_t mlen;
-            if (rc_bit(d, T + T_IS_REP + state)) {
+            {
+                const bool is_rep = rc_bit(d, T + T_IS_REP + state) != 0;
                 bool short_rep = false;
-                if (!rc_bit(d, T + T_IS_REP_G0 + state)) {
-                    if (!rc_bit(d, T + T_IS_REP0LONG + (state << 4) + pos_state)) short_rep = true;
-                } else {
-                    uint32_t dist;
-                    if (!rc_bit(d, T + T_IS_REP_G1 + state)) {
-                        dist = rep1;
+                if (is_rep) {  // lzma.rs:312-345
+                    if (!rc_bit(d, T + T_IS_REP_G0 + state)) {
+                        if (!rc_bit(d, T + T_IS_REP0LONG + (state << 4) + pos_state)) short_rep = true;
                     } else {
-                        if (!rc_bit(d, T + T_IS_REP_G2 + state)) {
-                            dist = rep2;
+                        uint32_t dist;
+                        if (!rc_bit(d, T + T_IS_REP_G1 + state)) {
+                            dist = rep1;
                         } else {
-                            dist = rep3;
-                            rep3 = rep2;
+                            if (!rc_bit(d, T + T_IS_REP_G2 + state)) {
+                                dist = rep2;
+                            } else {
+                                dist = rep3;
+                                rep3 = rep2;
+                            }
+                            rep2 = rep1;
                         }
-                        rep2 = rep1;
+                        rep1 = rep0;
+                        rep0 = dist;
                     }
+                } else {  // lzma.rs:355-361
+                    rep3 = rep2;
+                    rep2 = rep1;
                     rep1 = rep0;
-                    rep0 = dist;
                 }
                 if (short_rep) {
                     state = state < 7 ? 9 : 11;
                     mlen = 1;
                 } else {
-                    mlen = rc_len(d, T + T_REP_LEN, pos_state) + 2;
-                    state = state < 7 ? 8 : 11;
-                }
-                if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
-            } else {
-                rep3 = rep2;
-                rep2 = rep1;
-                rep1 = rep0;
-                const uint32_t l = rc_len(d, T + T_LEN, pos_state);
-                state = state < 7 ? 7 : 10;
-                // decode_distance, lzma.rs:563-592
-                const uint32_t pos_slot = rc_tree<6>(d, T + T_POS_SLOT + (l < 3 ? l : 3) * 64);
-                if (pos_slot < 4) {
-                    rep0 = pos_slot;
-                } else {
-                    const uint32_t nd = (pos_slot >> 1) - 1;
-                    uint32_t r = (2u | (pos_slot & 1u)) << nd;
-                    if (pos_slot < 14) {
-                        r += rc_rtree(d, T + T_POS_DEC + r - pos_slot, nd);
+                    // LenDecoder::decode, rangecoder.rs:256-269 (len_decoder / rep_len_decoder share this code)
+                    uint16_t* L = T + (is_rep ? T_REP_LEN : T_LEN);
+                    uint32_t l;
+                    if (!rc_bit(d, L + 0)) {
+                        l = rc_tree_rt(d, L + T_LEN_LOW + pos_state * 8, 3) - 8;
+                    } else if (!rc_bit(d, L + 1)) {
+                        l = rc_tree_rt(d, L + T_LEN_MID + pos_state * 8, 3);
                     } else {
-                        r += rc_direct(d, nd - 4) << 4;
-                        r += rc_rtree(d, T + T_ALIGN, 4);
+                        l = rc_tree_rt(d, L + T_LEN_HIGH, 8) - 256 + 16;
                     }
-                    rep0 = r;
+                    if (is_rep) {
+                        state = state < 7 ? 8 : 11;
+                    } else {
+                        state = state < 7 ? 7 : 10;
+                        // decode_distance, lzma.rs:563-592
+                        const uint32_t pos_slot = rc_tree_rt(d, T + T_POS_SLOT + (l < 3 ? l : 3) * 64, 6) - 64;
+                        if (pos_slot < 4) {
+                            rep0 = pos_slot;
+                        } else {
+                            const uint32_t nd = (pos_slot >> 1) - 1;
+                            uint32_t r = (2u | (pos_slot & 1u)) << nd;
+                            if (pos_slot < 14) {  // per-slot reverse tree (own aligned block, see lzb_types.h)
+                                const uint32_t off = 2u * ((1u << nd) - 2u) + ((pos_slot & 1u) << nd);
+                                r += rev_bits(rc_tree_rt(d, T + T_POS_DEC + off, nd), nd);
+                            } else {
+                                r += rc_direct(d, nd - 4) << 4;
+                                r += rev_bits(rc_tree_rt(d, T + T_ALIGN, 4), 4);
+                            }
+                            rep0 = r;
+                        }
+                        if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
+                        if (rep0 == 0xFFFFFFFFu) {  // end-of-stream marker, lzma.rs:373-381
+                            if (d.code == 0 && d.p == d.lim) goto chunk_done;  // Finished: fall to the size check
+                            FAIL(LZB_E_EOS_MORE_BYTES, 0, 0);
+                        }
+                    }
+                    mlen = l + 2;
                 }
                 if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
-                if (rep0 == 0xFFFFFFFFu) {  // end-of-stream marker, lzma.rs:373-381
-                    if (d.code == 0 && d.p == d.lim) {
-                        has_target = has_target;  // Finished: fall to the size check below
-                        goto chunk_done;
-                    }
-                    FAIL(LZB_E_EOS_MORE_BYTES, 0, 0);
-                }
-                mlen = l + 2;
             }
 
             // ---- append_lz(mlen, rep0 + 1), lzbuffer.rs:125-143 / 272-297

@@ -31,7 +31,10 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
                                             uint32_t warp_smem_bytes, uint16_t* glit) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // broadcast from lane 0 so that the compiler's divergence analysis sees the warp index (and with it every
+    // shared-memory table address and every value loaded through it) as warp-uniform: uniform branches then need
+    // no BSSY/BSYNC reconvergence pairs in the bit loop
+    const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
     uint16_t* T = reinterpret_cast<uint16_t*>(smem + (size_t)warp * warp_smem_bytes);
     for (;;) {
         unsigned int slot = 0;

@@ -51,11 +51,12 @@ enum {
     T_IS_REP_G2 = 228,   // [12]
     T_IS_REP0LONG = 240, // [12][16]                              lzma.rs:180,317
     T_POS_SLOT = 432,    // [4][64]                               lzma.rs:172
-    T_POS_DEC = 688,     // [115] (+1 pad)                        lzma.rs:174
-    T_ALIGN = 804,       // [16]                                  lzma.rs:173
-    T_LEN = 820,         // choice, choice2, low[16][8], mid[16][8], high[256]   rangecoder.rs:202-209
-    T_REP_LEN = 1334,    // same
-    T_LIT = 1848,        // [1<<(lc+lp)][0x300]                   lzma.rs:194
+    T_POS_DEC = 688,     // 10 reverse trees (slots 4..13), one 4-byte aligned block each: 124 entries
+                         // (the reference packs them into [115] with overlapping offsets, lzma.rs:174,579-585)
+    T_ALIGN = 812,       // [16]                                  lzma.rs:173
+    T_LEN = 828,         // choice, choice2, low[16][8], mid[16][8], high[256]   rangecoder.rs:202-209
+    T_REP_LEN = 1342,    // same
+    T_LIT = 1856,        // [1<<(lc+lp)][0x300]                   lzma.rs:194
     T_LEN_SIZE = 514,
     T_LEN_LOW = 2,
     T_LEN_MID = 2 + 128,
