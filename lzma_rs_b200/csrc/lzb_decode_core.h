@@ -31,6 +31,13 @@ static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { r
 
 #define RC_TOP (1u << 24)
 
+// Keeps a loop-invariant value in a register instead of letting the compiler rematerialise it every symbol.
+#ifdef __CUDACC__
+#define LZB_KEEP(x) asm volatile("" : "+r"(x))
+#else
+#define LZB_KEEP(x) ((void)0)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // range decoder + input window
 // ------------------------------------------------------------------------------------------------
@@ -323,21 +330,28 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                  (uint32_t)inb[d.p + 4];
         rd_seek(d, d.p + 5);
 
-        const uint32_t pb_mask = (1u << pb) - 1, lp_mask = (1u << lp) - 1;
+        uint32_t pb_mask = (1u << pb) - 1, lp_mask = (1u << lp) - 1, lit_shift = 8 - lc;
+        // symbol-loop exits as absolute output positions: `stop_at` = where the expected size is reached
+        // (lzma.rs:442-445); `lit_limit` = first position a literal may not be written to (capacity / memlimit)
+        uint32_t stop_at = has_target ? dict_base + target : 0xFFFFFFFFu;
+        if (has_target && target > 0xFFFFFFFFu - dict_base) stop_at = 0xFFFFFFFFu;
+        uint32_t lit_limit = cap < mem_stop ? cap : mem_stop;
+        LZB_KEEP(pb_mask);
+        LZB_KEEP(lp_mask);
+        LZB_KEEP(lit_shift);
+        LZB_KEEP(stop_at);
+        LZB_KEEP(lit_limit);
 
         // process_mode(Finish), lzma.rs:435-455, 496-511
         for (;;) {
+            if (opos >= stop_at) break;
+            if (!has_target && d.code == 0 && d.p == d.lim) break;  // is_finished_ok, rangecoder.rs:50-52
             const uint32_t len = opos - dict_base;
-            if (has_target) {
-                if (len >= target) break;
-            } else if (d.code == 0 && d.p == d.lim) {  // is_finished_ok, rangecoder.rs:50-52
-                break;
-            }
             const uint32_t pos_state = len & pb_mask;
 
             // literal context row (decode_literal, lzma.rs:526-538).  After a literal (state < 7) prev_byte is in a
             // register, so the root of the plain literal tree is fetched while is_match is being decoded.
-            uint16_t* probs = lit + (((len & lp_mask) << lc) + (prev_byte >> (8 - lc))) * 0x300u;
+            uint16_t* probs = lit + (((len & lp_mask) << lc) + (prev_byte >> lit_shift)) * 0x300u;
             const uint32_t p_is_match = T[T_IS_MATCH + (state << 4) + pos_state];
             uint32_t lit_pv = 0, lit_pair = 0;
             if (state < 7) {
@@ -385,12 +399,15 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     }
                 }
                 if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
-                if (opos >= mem_stop) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
-                if (opos >= cap) FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);
+                if (opos >= lit_limit) {
+                    if (opos >= mem_stop) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
+                    FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);
+                }
                 prev_byte = sym & 0xFFu;
                 if (lane == 0) out[opos] = (uint8_t)prev_byte;
                 opos += 1;
-                state = state < 4 ? 0 : (state < 10 ? state - 3 : state - 6);
+                // state after a literal (lzma.rs:299-305): 0,0,0,0,1,2,3,4,5,6,4,5 as packed nibbles
+                state = (uint32_t)(0x546543210000ull >> (state * 4)) & 0xFu;
                 mb_valid = false;
                 continue;
             }
@@ -431,10 +448,10 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     // LenDecoder::decode, rangecoder.rs:256-269 (len_decoder / rep_len_decoder share this code)
                     uint16_t* L = T + (is_rep ? T_REP_LEN : T_LEN);
                     uint32_t l;
-                    if (!rc_bit(d, L + 0)) {
-                        l = rc_tree_rt(d, L + T_LEN_LOW + pos_state * 8, 3) - 8;
-                    } else if (!rc_bit(d, L + 1)) {
-                        l = rc_tree_rt(d, L + T_LEN_MID + pos_state * 8, 3);
+                    const uint32_t c1 = rc_bit(d, L + 0);
+                    const uint32_t c2 = c1 ? rc_bit(d, L + 1) : 0u;
+                    if (!c2) {  // low (c1 == 0) and mid (c1 == 1) coders: one 3-level walk site
+                        l = rc_tree_walk<true, 3>(d, L + (c1 ? T_LEN_MID : T_LEN_LOW) + pos_state * 8, 3) - 8 + c1 * 8;
                     } else {
                         l = rc_tree_rt(d, L + T_LEN_HIGH, 8) - 256 + 16;
                     }
@@ -443,7 +460,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     } else {
                         state = state < 7 ? 7 : 10;
                         // decode_distance, lzma.rs:563-592
-                        const uint32_t pos_slot = rc_tree_rt(d, T + T_POS_SLOT + (l < 3 ? l : 3) * 64, 6) - 64;
+                        const uint32_t pos_slot = rc_tree_walk<true, 6>(d, T + T_POS_SLOT + (l < 3 ? l : 3) * 64, 6) - 64;
                         if (pos_slot < 4) {
                             rep0 = pos_slot;
                         } else {
