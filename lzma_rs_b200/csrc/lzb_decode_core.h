@@ -14,6 +14,7 @@
 #define LZB_LANES 32
 #define LZB_DEV __device__ __forceinline__
 #define LZB_DEV_NOINLINE __device__ __noinline__
+#define LZB_MEM __device__ __forceinline__
 #define LZB_SYNCWARP() __syncwarp()
 #define LZB_LDG(p) __ldg(p)
 #define LZB_MIN(a, b) min(a, b)
@@ -21,6 +22,7 @@
 #define LZB_LANES 1
 #define LZB_DEV static inline
 #define LZB_DEV_NOINLINE static
+#define LZB_MEM inline
 #define LZB_SYNCWARP() ((void)0)
 #define LZB_LDG(p) (*(p))
 #define LZB_MIN(a, b) ((a) < (b) ? (a) : (b))
@@ -75,27 +77,97 @@ LZB_DEV void rc_normalize(Dec& d) {
     }
 }
 
-// The arithmetic of decode_bit (rangecoder.rs:93-120) on a probability already in a register; returns the bit,
-// `np` = updated probability.  one: p -= p >> 5; zero: p += (2048 - p) >> 5  ==  p + ((K - p) >>arith 5) with
-// K = one ? 31 : 2048  (floor((31 - p) / 32) == -(p >> 5)).  Normalisation is the caller's next step.
-LZB_DEV bool rc_step(Dec& d, uint32_t pv, uint32_t& np) {
+#ifndef LZB_PAIR_PREFETCH
+#define LZB_PAIR_PREFETCH 1
+#endif
+
+// The arithmetic of decode_bit (rangecoder.rs:93-120) on a probability already in a register.  Returns the bit
+// (0/1); `np` = updated probability: one: p -= p >> 5; zero: p += (2048 - p) >> 5  ==  p + ((K - p) >>arith 5),
+// K = one ? 31 : 2048 = 2048 - 2017 * bit  (floor((31 - p) / 32) == -(p >> 5)).  Normalisation is the caller's
+// next step.  On the device the compare / range select / conditional code update are pinned in PTX so that the
+// bit stays an opaque register for the constant-bank IMADs around it.
+LZB_DEV uint32_t rc_step(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np) {
     const uint32_t bound = (d.range >> 11) * pv;
-    const bool one = d.code >= bound;
-    const uint32_t rb = d.range - bound;
-    d.range = one ? rb : bound;
-    if (one) d.code -= bound;
-    const uint32_t k = one ? 31u : 2048u;
-    np = pv + (uint32_t)((int32_t)(k - pv) >> 5);
-    return one;
+    uint32_t bit;
+#ifdef __CUDACC__
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 rb;\n\t"
+        "setp.ge.u32 p, %2, %3;\n\t"
+        "sub.u32 rb, %1, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "selp.u32 %1, rb, %3, p;\n\t"
+        "@p sub.u32 %2, %2, %3;\n\t}"
+        : "=r"(bit), "+r"(d.range), "+r"(d.code)
+        : "r"(bound));
+#else
+    bit = d.code >= bound ? 1u : 0u;
+    d.range = bit ? d.range - bound : bound;
+    if (bit) d.code -= bound;
+#endif
+    const uint32_t k = bit * kc.m2017 + kc.k2048;  // 31 or 2048
+    const uint32_t t = pv * kc.m1 + k;             // K - p
+    np = pv + (uint32_t)((int32_t)t >> 5);
+    return bit;
+}
+
+// ---- probability-table handles: u16 index in, value out -------------------------------------------------------
+// TabPtr : plain pointers (host emulation; the global literal workspace of the lc+lp > 4 variant).
+// TabSm  : 32-bit shared-space addresses with explicit ld/st.shared (device): addresses are IMADs off the
+//          constant bank, and the compiler cannot turn the accesses into generic loads.
+struct TabPtr {
+    uint16_t* b;
+    LZB_MEM uint32_t ld16(const LzbKC&, uint32_t i) const { return b[i]; }
+    LZB_MEM uint32_t ld_children(const LzbKC&, uint32_t m) const {  // probs[2m] | probs[2m+1] << 16
+        return (uint32_t)b[2 * m] | ((uint32_t)b[2 * m + 1] << 16);
+    }
+    LZB_MEM void st16(const LzbKC&, uint32_t i, uint32_t v) const { b[i] = (uint16_t)v; }
+    LZB_MEM TabPtr at(const LzbKC&, uint32_t off) const {
+        TabPtr t = {b + off};
+        return t;
+    }
+};
+#ifdef __CUDACC__
+struct TabSm {
+    uint32_t a;  // byte address in the shared window
+    LZB_MEM uint32_t ld16(const LzbKC& kc, uint32_t i) const {
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(i * kc.two + a) : "memory");
+        return v;
+    }
+    LZB_MEM uint32_t ld_children(const LzbKC& kc, uint32_t m) const {  // needs a 4-byte aligned table base
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(m * kc.four + a) : "memory");
+        return v;
+    }
+    LZB_MEM void st16(const LzbKC& kc, uint32_t i, uint32_t v) const {
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(i * kc.two + a), "h"((uint16_t)v) : "memory");
+    }
+    LZB_MEM TabSm at(const LzbKC& kc, uint32_t off) const {
+        TabSm t = {off * kc.two + a};
+        return t;
+    }
+};
+#endif
+
+// child probability for the decoded bit out of a prefetched pair
+LZB_DEV uint32_t pick_child(const LzbKC& kc, uint32_t pair, uint32_t bit) {
+#ifdef __CUDACC__
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(pair), "r"(bit * kc.k22 + kc.k4410));  // bytes {0,1} or {2,3}
+    return r;
+#else
+    (void)kc;
+    return bit ? (pair >> 16) : (pair & 0xFFFFu);
+#endif
 }
 
 // decode_bit on a table entry
-LZB_DEV uint32_t rc_bit(Dec& d, uint16_t* prob) {
+template <class Tab>
+LZB_DEV uint32_t rc_bit(Dec& d, const LzbKC& kc, const Tab& t, uint32_t idx) {
     uint32_t np;
-    const bool one = rc_step(d, *prob, np);
-    *prob = (uint16_t)np;
+    const uint32_t bit = rc_step(d, kc, t.ld16(kc, idx), np);
+    t.st16(kc, idx, np);
     rc_normalize(d);
-    return one ? 1u : 0u;
+    return bit;
 }
 
 // get(count), rangecoder.rs:72-90
@@ -112,52 +184,46 @@ LZB_DEV uint32_t rc_direct(Dec& d, uint32_t count) {
     return r;
 }
 
-// Both children of tree node m are adjacent u16 (indices 2m, 2m+1): one aligned 32-bit load fetches the next
-// level's probability before the current decision is known, taking the LDS latency off the serial chain.
-LZB_DEV uint32_t ld_pair(const uint16_t* p) {
-#ifdef __CUDACC__
-    return *reinterpret_cast<const uint32_t*>(p);
-#else
-    return (uint32_t)p[0] | ((uint32_t)p[1] << 16);
-#endif
-}
-
-// Bit-tree walk (parse_bit_tree, rangecoder.rs:122-134) of `nb` levels over a 4-byte aligned table; returns
-// the final node index m in [2^nb, 2^(nb+1)).  Forward value = m - 2^nb; the reverse trees
-// (parse_reverse_bit_tree, 136-151) walk the same nodes, so their value is the bit reversal of that.
-template <bool UNROLL, int NB_CONST>
-LZB_DEV uint32_t rc_tree_walk(Dec& d, uint16_t* probs, uint32_t nb_rt) {
+// Bit-tree walk (parse_bit_tree, rangecoder.rs:122-134) of `nb` levels; `t` is the tree's table (node m at index m,
+// 4-byte aligned base).  Returns the final node index m in [2^nb, 2^(nb+1)): forward value = m - 2^nb; the reverse
+// trees (parse_reverse_bit_tree, 136-151) walk the same nodes, so their value is the bit reversal of that.
+// With LZB_PAIR_PREFETCH both children of the current node (adjacent u16) are fetched with one 32-bit load before
+// the decision is known, which takes the shared-memory latency off the serial chain.
+template <bool UNROLL, int NB_CONST, class Tab>
+LZB_DEV uint32_t rc_tree_walk(Dec& d, const LzbKC& kc, const Tab& t, uint32_t nb_rt) {
     const uint32_t nb = UNROLL ? (uint32_t)NB_CONST : nb_rt;
     uint32_t m = 1;
-    uint32_t pv = probs[1];
-    uint32_t pair = nb > 1 ? ld_pair(probs + 2) : 0u;
+    uint32_t pv = t.ld16(kc, 1);
+    uint32_t pair = (LZB_PAIR_PREFETCH && nb > 1) ? t.ld_children(kc, 1) : 0u;
+#define LZB_TREE_STEP(I, NBV)                                            \
+    {                                                                    \
+        uint32_t np;                                                     \
+        const uint32_t bit = rc_step(d, kc, pv, np);                     \
+        t.st16(kc, m, np);                                               \
+        m = m * kc.two + bit;                                            \
+        if (LZB_PAIR_PREFETCH) {                                         \
+            pv = pick_child(kc, pair, bit);                              \
+            if ((uint32_t)(I) + 2 < (NBV)) pair = t.ld_children(kc, m);  \
+        } else if ((uint32_t)(I) + 1 < (NBV)) {                          \
+            pv = t.ld16(kc, m);                                          \
+        }                                                                \
+        rc_normalize(d);                                                 \
+    }
     if (UNROLL) {
 #pragma unroll
-        for (int i = 0; i < NB_CONST; i++) {
-            uint32_t np;
-            const bool one = rc_step(d, pv, np);
-            probs[m] = (uint16_t)np;
-            m = (m << 1) | (one ? 1u : 0u);
-            pv = one ? (pair >> 16) : (pair & 0xFFFFu);
-            if (i + 2 < NB_CONST) pair = ld_pair(probs + 2 * m);
-            rc_normalize(d);
-        }
+        for (int i = 0; i < NB_CONST; i++) LZB_TREE_STEP(i, (uint32_t)NB_CONST)
     } else {
 #pragma unroll 1
-        for (uint32_t i = 0; i < nb; i++) {
-            uint32_t np;
-            const bool one = rc_step(d, pv, np);
-            probs[m] = (uint16_t)np;
-            m = (m << 1) | (one ? 1u : 0u);
-            pv = one ? (pair >> 16) : (pair & 0xFFFFu);
-            if (i + 2 < nb) pair = ld_pair(probs + 2 * m);
-            rc_normalize(d);
-        }
+        for (uint32_t i = 0; i < nb; i++) LZB_TREE_STEP(i, nb)
     }
+#undef LZB_TREE_STEP
     return m;
 }
 
-LZB_DEV uint32_t rc_tree_rt(Dec& d, uint16_t* probs, uint32_t nb) { return rc_tree_walk<false, 0>(d, probs, nb); }
+template <class Tab>
+LZB_DEV uint32_t rc_tree_rt(Dec& d, const LzbKC& kc, const Tab& t, uint32_t nb) {
+    return rc_tree_walk<false, 0>(d, kc, t, nb);
+}
 
 LZB_DEV uint32_t rev_bits(uint32_t v, uint32_t nb) {  // the low nb bits of v, reversed
 #ifdef __CUDACC__
@@ -189,10 +255,11 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
 // LIT_GLOBAL = false: all probability tables in shared memory (lc+lp <= tab_lclp <= 4; every LZMA2 stream).
 // LIT_GLOBAL = true : .lzma streams with lc+lp > 4 (legal up to 12, lzma.rs:62-66): the literal table
 //                     (0x300 << (lc+lp) u16, up to 6 MiB) lives in a per-warp global workspace `glit`.
-template <bool LIT_GLOBAL>
+// MainTab / LitTab: table handles for the 1856 small-table entries and for the literal table.
+template <bool LIT_GLOBAL, class MainTab, class LitTab>
 LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t* __restrict__ in_blob,
-                                  uint8_t* out_blob, uint16_t* T, uint16_t* glit, uint32_t tab_lclp, LzbResult* res,
-                                  int lane) {
+                                  uint8_t* out_blob, uint16_t* T, uint16_t* glit, const MainTab tab,
+                                  const LitTab lit, const LzbKC kc, uint32_t tab_lclp, LzbResult* res, int lane) {
     Dec d;
     const bool is_lzma1 = itp->kind == LZB_ITEM_LZMA;
     const uint32_t p0 = (uint32_t)(itp->in_off & 3ull);
@@ -201,7 +268,6 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
     uint8_t* out = out_blob + itp->out_off;
     const uint32_t cap = (uint32_t)LZB_MIN(itp->out_cap, (uint64_t)0xFFFFF000u);
     const uint32_t tab_u16 = LIT_GLOBAL ? (uint32_t)T_LIT : T_LIT + (0x300u << tab_lclp);
-    uint16_t* const lit = LIT_GLOBAL ? glit : T + T_LIT;
     uint32_t opos = 0, dict_base = 0;
     uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
     uint32_t lc = 0, lp = 0, pb = 0;
@@ -351,16 +417,17 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
             // literal context row (decode_literal, lzma.rs:526-538).  After a literal (state < 7) prev_byte is in a
             // register, so the root of the plain literal tree is fetched while is_match is being decoded.
-            uint16_t* probs = lit + (((len & lp_mask) << lc) + (prev_byte >> lit_shift)) * 0x300u;
-            const uint32_t p_is_match = T[T_IS_MATCH + (state << 4) + pos_state];
+            const LitTab probs = lit.at(kc, (((len & lp_mask) << lc) + (prev_byte >> lit_shift)) * 0x300u);
+            const uint32_t i_is_match = T_IS_MATCH + (state << 4) + pos_state;
+            const uint32_t p_is_match = tab.ld16(kc, i_is_match);
             uint32_t lit_pv = 0, lit_pair = 0;
             if (state < 7) {
-                lit_pv = probs[1];
-                lit_pair = ld_pair(probs + 2);
+                lit_pv = probs.ld16(kc, 1);
+                if (LZB_PAIR_PREFETCH) lit_pair = probs.ld_children(kc, 1);
             }
             uint32_t np_im;
-            const bool is_lz = rc_step(d, p_is_match, np_im);
-            T[T_IS_MATCH + (state << 4) + pos_state] = (uint16_t)np_im;
+            const uint32_t is_lz = rc_step(d, kc, p_is_match, np_im);
+            tab.st16(kc, i_is_match, np_im);
             rc_normalize(d);
 
             if (!is_lz) {
@@ -379,22 +446,26 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     do {
                         const uint32_t match_bit = (mb >> 7) & 1u;
                         mb <<= 1;
-                        const uint32_t bit = rc_bit(d, probs + ((1u + match_bit) << 8) + sym);
+                        const uint32_t bit = rc_bit(d, kc, probs, ((1u + match_bit) << 8) + sym);
                         sym = (sym << 1) | bit;
                         if (match_bit != bit) break;
                     } while (sym < 0x100);
 #pragma unroll 1
-                    while (sym < 0x100) sym = (sym << 1) | rc_bit(d, probs + sym);
-                } else {  // plain 8-level walk with the next level's pair prefetched
+                    while (sym < 0x100) sym = (sym << 1) | rc_bit(d, kc, probs, sym);
+                } else {  // plain 8-level walk (root fetched above, while is_match was being decoded)
                     uint32_t pv = lit_pv, pair = lit_pair;
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         uint32_t np;
-                        const bool one = rc_step(d, pv, np);
-                        probs[sym] = (uint16_t)np;
-                        sym = (sym << 1) | (one ? 1u : 0u);
-                        pv = one ? (pair >> 16) : (pair & 0xFFFFu);
-                        if (i < 6) pair = ld_pair(probs + 2 * sym);
+                        const uint32_t bit = rc_step(d, kc, pv, np);
+                        probs.st16(kc, sym, np);
+                        sym = sym * kc.two + bit;
+                        if (LZB_PAIR_PREFETCH) {
+                            pv = pick_child(kc, pair, bit);
+                            if (i < 6) pair = probs.ld_children(kc, sym);
+                        } else if (i < 7) {
+                            pv = probs.ld16(kc, sym);
+                        }
                         rc_normalize(d);
                     }
                 }
@@ -415,17 +486,17 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
             // ---- LZ, lzma.rs:309-390
             uint32_t mlen;
             {
-                const bool is_rep = rc_bit(d, T + T_IS_REP + state) != 0;
+                const bool is_rep = rc_bit(d, kc, tab, T_IS_REP + state) != 0;
                 bool short_rep = false;
                 if (is_rep) {  // lzma.rs:312-345
-                    if (!rc_bit(d, T + T_IS_REP_G0 + state)) {
-                        if (!rc_bit(d, T + T_IS_REP0LONG + (state << 4) + pos_state)) short_rep = true;
+                    if (!rc_bit(d, kc, tab, T_IS_REP_G0 + state)) {
+                        if (!rc_bit(d, kc, tab, T_IS_REP0LONG + (state << 4) + pos_state)) short_rep = true;
                     } else {
                         uint32_t dist;
-                        if (!rc_bit(d, T + T_IS_REP_G1 + state)) {
+                        if (!rc_bit(d, kc, tab, T_IS_REP_G1 + state)) {
                             dist = rep1;
                         } else {
-                            if (!rc_bit(d, T + T_IS_REP_G2 + state)) {
+                            if (!rc_bit(d, kc, tab, T_IS_REP_G2 + state)) {
                                 dist = rep2;
                             } else {
                                 dist = rep3;
@@ -446,21 +517,22 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     mlen = 1;
                 } else {
                     // LenDecoder::decode, rangecoder.rs:256-269 (len_decoder / rep_len_decoder share this code)
-                    uint16_t* L = T + (is_rep ? T_REP_LEN : T_LEN);
+                    const uint32_t L = is_rep ? (uint32_t)T_REP_LEN : (uint32_t)T_LEN;
                     uint32_t l;
-                    const uint32_t c1 = rc_bit(d, L + 0);
-                    const uint32_t c2 = c1 ? rc_bit(d, L + 1) : 0u;
+                    const uint32_t c1 = rc_bit(d, kc, tab, L + 0);
+                    const uint32_t c2 = c1 ? rc_bit(d, kc, tab, L + 1) : 0u;
                     if (!c2) {  // low (c1 == 0) and mid (c1 == 1) coders: one 3-level walk site
-                        l = rc_tree_walk<true, 3>(d, L + (c1 ? T_LEN_MID : T_LEN_LOW) + pos_state * 8, 3) - 8 + c1 * 8;
+                        const uint32_t base = L + (c1 ? (uint32_t)T_LEN_MID : (uint32_t)T_LEN_LOW) + pos_state * 8;
+                        l = rc_tree_walk<true, 3>(d, kc, tab.at(kc, base), 3) - 8 + c1 * 8;
                     } else {
-                        l = rc_tree_rt(d, L + T_LEN_HIGH, 8) - 256 + 16;
+                        l = rc_tree_rt(d, kc, tab.at(kc, L + T_LEN_HIGH), 8) - 256 + 16;
                     }
                     if (is_rep) {
                         state = state < 7 ? 8 : 11;
                     } else {
                         state = state < 7 ? 7 : 10;
                         // decode_distance, lzma.rs:563-592
-                        const uint32_t pos_slot = rc_tree_walk<true, 6>(d, T + T_POS_SLOT + (l < 3 ? l : 3) * 64, 6) - 64;
+                        const uint32_t pos_slot = rc_tree_walk<true, 6>(d, kc, tab.at(kc, T_POS_SLOT + (l < 3 ? l : 3) * 64), 6) - 64;
                         if (pos_slot < 4) {
                             rep0 = pos_slot;
                         } else {
@@ -468,10 +540,10 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                             uint32_t r = (2u | (pos_slot & 1u)) << nd;
                             if (pos_slot < 14) {  // per-slot reverse tree (own aligned block, see lzb_types.h)
                                 const uint32_t off = 2u * ((1u << nd) - 2u) + ((pos_slot & 1u) << nd);
-                                r += rev_bits(rc_tree_rt(d, T + T_POS_DEC + off, nd), nd);
+                                r += rev_bits(rc_tree_rt(d, kc, tab.at(kc, T_POS_DEC + off), nd), nd);
                             } else {
                                 r += rc_direct(d, nd - 4) << 4;
-                                r += rev_bits(rc_tree_rt(d, T + T_ALIGN, 4), 4);
+                                r += rev_bits(rc_tree_rt(d, kc, tab.at(kc, T_ALIGN), 4), 4);
                             }
                             rep0 = r;
                         }

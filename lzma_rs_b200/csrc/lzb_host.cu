@@ -19,10 +19,10 @@ struct LzbCrcRange {
 #define CRC_SEG 4096u
 
 extern "C" __global__ void lzb_decode_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
-                                             LzbResult*, unsigned int*, uint32_t, uint32_t);
+                                             LzbResult*, unsigned int*, uint32_t, uint32_t, const LzbKC);
 extern "C" __global__ void lzb_decode_biglit_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
                                                     LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*,
-                                                    unsigned long long);
+                                                    unsigned long long, const LzbKC);
 extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, const uint64_t*, const uint64_t*, uint32_t,
                                            LzbItem*, LzbScan*);
 extern "C" __global__ void lzb_crc_partial_kernel(const uint8_t*, const LzbCrcRange*, const uint32_t*, uint64_t,
@@ -146,6 +146,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
                 const uint8_t* d_in_base, uint8_t* d_out_base, LzbResult* d_results, unsigned int* d_counter) {
     CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned int), s));
     const uint32_t ns = (uint32_t)p.order_small.size(), nb = (uint32_t)p.order_big.size();
+    const LzbKC kc = LZB_KC_INIT;
     if (ns) {
         const LaunchCfg& c = p.cfg_small;
         const int smem = (int)(c.warps * c.warp_bytes);
@@ -154,7 +155,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
             ctx->smem_configured = ctx->smem_optin;
         }
         lzb_decode_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, d_in_base, d_out_base, d_results,
-                                                             d_counter, c.lclp, c.warp_bytes);
+                                                             d_counter, c.lclp, c.warp_bytes, kc);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     if (nb) {
@@ -168,7 +169,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         CUDA_TRY(ctx, ctx->d_litws.ensure((size_t)c.grid * c.warps * p.big_stride_u16 * 2));
         lzb_decode_biglit_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order + ns, nb, d_in_base, d_out_base,
                                                                     d_results, d_counter + 1, c.lclp, c.warp_bytes,
-                                                                    ctx->d_litws.as<uint16_t>(), p.big_stride_u16);
+                                                                    ctx->d_litws.as<uint16_t>(), p.big_stride_u16, kc);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     return LZB_RC_OK;

@@ -28,7 +28,7 @@ template <bool LIT_GLOBAL>
 __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order,
                                             uint32_t n_items, const uint8_t* __restrict__ in_blob, uint8_t* out_blob,
                                             LzbResult* results, unsigned int* counter, uint32_t tab_lclp,
-                                            uint32_t warp_smem_bytes, uint16_t* glit) {
+                                            uint32_t warp_smem_bytes, uint16_t* glit, const LzbKC& kc) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     // broadcast from lane 0 so that the compiler's divergence analysis sees the warp index (and with it every
@@ -36,13 +36,20 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
     // no BSSY/BSYNC reconvergence pairs in the bit loop
     const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
     uint16_t* T = reinterpret_cast<uint16_t*>(smem + (size_t)warp * warp_smem_bytes);
+    const TabSm tab = {(uint32_t)__cvta_generic_to_shared(T)};
     for (;;) {
         unsigned int slot = 0;
         if (lane == 0) slot = atomicAdd(counter, 1u);
         slot = __shfl_sync(FULL_MASK, slot, 0);
         if (slot >= n_items) break;
         const uint32_t idx = order ? order[slot] : slot;
-        decode_item<LIT_GLOBAL>(items + idx, in_blob, out_blob, T, glit, tab_lclp, results + idx, lane);
+        if (LIT_GLOBAL) {
+            const TabPtr lit = {glit};
+            decode_item<true>(items + idx, in_blob, out_blob, T, glit, tab, lit, kc, tab_lclp, results + idx, lane);
+        } else {
+            const TabSm lit = {tab.a + (uint32_t)T_LIT * 2u};
+            decode_item<false>(items + idx, in_blob, out_blob, T, glit, tab, lit, kc, tab_lclp, results + idx, lane);
+        }
         __syncwarp();
     }
 }
@@ -50,8 +57,10 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
 extern "C" __global__ void __launch_bounds__(512, 1)
     lzb_decode_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
                       const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
-                      unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes) {
-    decode_loop<false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, nullptr);
+                      unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes,
+                      const __grid_constant__ LzbKC kc) {
+    decode_loop<false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, nullptr,
+                       kc);
 }
 
 // .lzma streams with lc+lp > 4: literal table in a per-warp global workspace (ws + warp_id * ws_stride_u16).
@@ -59,10 +68,10 @@ extern "C" __global__ void __launch_bounds__(512, 1)
     lzb_decode_biglit_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
                              const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
                              unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
-                             unsigned long long ws_stride_u16) {
+                             unsigned long long ws_stride_u16, const __grid_constant__ LzbKC kc) {
     const unsigned long long wid = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     decode_loop<true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes,
-                      ws + wid * ws_stride_u16);
+                      ws + wid * ws_stride_u16, kc);
 }
 
 // ------------------------------------------------------------------------------------------------

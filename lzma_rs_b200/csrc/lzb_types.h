@@ -63,4 +63,12 @@ enum {
     T_LEN_HIGH = 2 + 256
 };
 
+// Multipliers / addends the bit loop reads from the kernel's constant bank.  Passing them as launch parameters keeps
+// nvcc/ptxas from strength-reducing `x * 2 + y` into ALU-pipe shifts and selects: as IMADs with a constant-bank
+// operand they run on the (otherwise idle) FMA pipe, which halves the ALU-pipe pressure that bounds K1.
+struct LzbKC {
+    uint32_t two, four, m1, m2017, k2048, k22, k4410;
+};
+#define LZB_KC_INIT {2u, 4u, 0xFFFFFFFFu, (uint32_t)-2017, 2048u, 0x22u, 0x4410u}
+
 static inline uint32_t lzb_table_u16(uint32_t lclp) { return (uint32_t)T_LIT + (0x300u << lclp); }

@@ -22,13 +22,13 @@ class HostEmulExecutor : public lzb::Executor {
             const uint32_t lclp = (uint32_t)items[i].lc + items[i].lp;
             if (items[i].kind == LZB_ITEM_LZMA && lclp > 4) {  // literal table outside "shared memory"
                 G.assign((size_t)0x300u << lclp, 0);
-                decode_item<true>(items + i, in_, out_, T.data(), G.data(), lclp, results + i, 0);
+                run<true>(items + i, T.data(), G.data(), lclp, results + i);
                 continue;
             }
-            decode_item<false>(items + i, in_, out_, T.data(), nullptr, small_lclp, results + i, 0);
+            run<false>(items + i, T.data(), nullptr, small_lclp, results + i);
             if (results[i].code == LZB_E_UNSUPPORTED && results[i].a1 == small_lclp && results[i].a0 <= 4) {
                 T4.resize(lzb_table_u16(4) + 8);  // framing scan under-estimated lc+lp: retry with the LZMA2 maximum
-                decode_item<false>(items + i, in_, out_, T4.data(), nullptr, 4, results + i, 0);
+                run<false>(items + i, T4.data(), nullptr, 4, results + i);
             }
         }
         return LZB_RC_OK;
@@ -65,6 +65,13 @@ class HostEmulExecutor : public lzb::Executor {
     }
 
    private:
+    template <bool BIG>
+    void run(const LzbItem* it, uint16_t* T, uint16_t* G, uint32_t lclp, LzbResult* res) {
+        const LzbKC kc = LZB_KC_INIT;
+        const TabPtr tab = {T};
+        const TabPtr lit = {BIG ? G : T + T_LIT};
+        decode_item<BIG>(it, in_, out_, T, G, tab, lit, kc, lclp, res, 0);
+    }
     const uint8_t* in_;
     uint8_t* out_;
 };
