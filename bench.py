@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--distinct", type=int, default=0, help="distinct streams to generate (0 = auto); the rest are tiled")
-    ap.add_argument("--cpu-sample", type=int, default=1024, help="streams of the workload the CPU baseline decodes")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="streams of the workload the CPU baseline decodes")
     ap.add_argument("--no-verify", action="store_true")
     a = ap.parse_args()
     assert a.warmup >= 3 or a.impl == "reference", "timing rules: at least 3 warm-up steps"
@@ -291,7 +291,13 @@ def main():
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kernel_ms = float(np.mean(step_ms))  # this rank's average launch duration, CUDA events on the launch stream
         achieved = (in_bytes + out_bytes) / (kernel_ms * 1e-3) / 1e9
-        cpu_gbs, cpu_dt, cpu_k, cpu_total = cpu_reference_run(comp, plain, 1, 1, ncpu, a.cpu_sample)
+        cpu_gbs, cpu_dt, cpu_k, cpu_total = cpu_reference_run(comp, plain, 2, 1, ncpu, a.cpu_sample)
+        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "r01_k1_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("streams") == n:
+                traffic = tj["dram_bytes_per_launch"]
         line = {
             "metric": "decompressed GB/s (batch of independent LZMA2 streams)", "value": value, "unit": "GB/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
@@ -307,7 +313,7 @@ def main():
                     "api": "lzb_decode_batch (C ABI) with pinned host buffers"},
             "gpu_launches": kernels_per_step * a.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "lzb_decode_kernel", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "lzb_decode_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": in_bytes + out_bytes, "kernel_ms": kernel_ms},
             "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": ncpu, "kind": "port",
                              "sample": f"{cpu_k} of {n} streams ({cpu_total} B out), one stream per task on {ncpu} "

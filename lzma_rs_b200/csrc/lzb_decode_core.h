@@ -78,7 +78,7 @@ LZB_DEV void rc_normalize(Dec& d) {
 }
 
 #ifndef LZB_PAIR_PREFETCH
-#define LZB_PAIR_PREFETCH 1
+#define LZB_PAIR_PREFETCH 0
 #endif
 
 // The arithmetic of decode_bit (rangecoder.rs:93-120) on a probability already in a register.  Returns the bit

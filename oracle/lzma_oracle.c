@@ -13,6 +13,7 @@
 #define _GNU_SOURCE
 #include "lzma_oracle.h"
 
+#include <malloc.h>
 #include <pthread.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -124,9 +125,13 @@ typedef struct {
     size_t len, cap;
 } bytes;
 
+/* Allocation hint for the batch driver (bench.py's CPU baseline): first capacity of every growable buffer of the
+ * current thread, so that a many-thread run is not serialised by realloc/mmap traffic.  0 = start small. */
+static __thread size_t tl_capacity_hint = 0;
+
 static void bytes_reserve(bytes *b, size_t extra) {
     if (b->len + extra > b->cap) {
-        size_t nc = b->cap ? b->cap : 4096;
+        size_t nc = b->cap ? b->cap : (tl_capacity_hint > 4096 ? tl_capacity_hint : 4096);
         while (nc < b->len + extra) nc *= 2;
         b->data = (uint8_t *)realloc(b->data, nc);
         if (!b->data) abort();
@@ -1226,6 +1231,7 @@ static void *batch_worker(void *arg) {
         int rc;
         uint64_t cap;
         if (i >= c->n) break;
+        tl_capacity_hint = (size_t)(c->out_off[i + 1] - c->out_off[i]) + 64;
         {
             const uint8_t *p = c->in + c->in_off[i];
             size_t len = (size_t)(c->in_off[i + 1] - c->in_off[i]);
@@ -1251,6 +1257,9 @@ int lzo_decompress_batch(int fmt, const uint8_t *in, const uint64_t *in_off, uin
     int t;
     if (nthreads < 1) nthreads = 1;
     pthread_once(&crc_once, crc_init);
+    /* keep per-stream buffers in the per-thread malloc arenas instead of mmap/munmap (process-wide lock) */
+    mallopt(M_MMAP_THRESHOLD, 1 << 28);
+    mallopt(M_TRIM_THRESHOLD, 1 << 29);
     c.fmt = fmt;
     c.in = in;
     c.in_off = in_off;
