@@ -1,0 +1,88 @@
+// lzma_rs.hpp -- C++ host-side mirror of the reference's decode API over the C ABI (include/lzma_b200.h).
+//
+//   lzma_rs::lzma_decompress(std::istream&, std::ostream&)                     src/lib.rs:44-49
+//   lzma_rs::lzma_decompress_with_options(in, out, decompress::Options)        src/lib.rs:52-60
+//   lzma_rs::lzma2_decompress(in, out)                                          src/lib.rs:83-88
+//   lzma_rs::xz_decompress(in, out)                                             src/lib.rs:100-105
+//
+// Errors are thrown as lzma_rs::error::Error whose what() is the reference's Display string and whose `kind`
+// is the error::Error variant.  Partial output is written before the throw, as in the reference.
+// Header-only; link with -llzma_b200.  There is no CPU fallback.
+#pragma once
+#include <cstdint>
+#include <istream>
+#include <iterator>
+#include <optional>
+#include <ostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "lzma_b200.h"
+
+namespace lzma_rs {
+
+namespace error {
+enum class Kind { IoError = 1, HeaderTooShort = 2, LzmaError = 3, XzError = 4, Internal = 5 };
+struct Error : std::runtime_error {
+    Kind kind;
+    lzb_status status;
+    Error(Kind k, const std::string& display, const lzb_status& st) : std::runtime_error(display), kind(k), status(st) {}
+};
+}  // namespace error
+
+namespace decompress {
+struct UnpackedSize {  // options.rs:24-43
+    enum Mode { ReadFromHeader = 0, ReadHeaderButUseProvided = 1, UseProvided = 2 } mode = ReadFromHeader;
+    std::optional<uint64_t> value;
+};
+struct Options {  // options.rs:3-20
+    UnpackedSize unpacked_size;
+    std::optional<size_t> memlimit;
+    bool allow_incomplete = false;  // stream API only
+};
+}  // namespace decompress
+
+namespace detail {
+inline lzb_ctx* ctx() {
+    static lzb_ctx* c = [] {
+        lzb_ctx* p = nullptr;
+        if (lzb_create(&p, -1) != LZB_RC_OK) throw std::runtime_error("lzb_create failed: no CUDA device (no CPU fallback)");
+        return p;
+    }();
+    return c;
+}
+inline void run(int fmt, const lzb_options* opt, std::istream& in, std::ostream& out) {
+    std::vector<uint8_t> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    uint8_t* o = nullptr;
+    size_t out_len = 0, consumed = 0;
+    lzb_status st{};
+    int rc = lzb_decompress_alloc(ctx(), fmt, opt, buf.data(), buf.size(), &o, &out_len, &consumed, &st);
+    if (rc != LZB_RC_OK) throw std::runtime_error(std::string("lzma_b200: ") + lzb_last_error(ctx()));
+    if (out_len) out.write(reinterpret_cast<const char*>(o), (std::streamsize)out_len);
+    lzb_free(o);
+    if (st.code != LZB_OK) {
+        char msg[512];
+        lzb_format_error(&st, msg, sizeof msg);
+        throw error::Error(static_cast<error::Kind>(st.kind), msg, st);
+    }
+    in.clear();
+    in.seekg((std::streamoff)consumed - (std::streamoff)buf.size(), std::ios::cur);  // unread trailing bytes stay
+    out.flush();
+}
+}  // namespace detail
+
+inline void lzma_decompress_with_options(std::istream& in, std::ostream& out, const decompress::Options& o) {
+    lzb_options n{};
+    n.unpacked_mode = (uint8_t)o.unpacked_size.mode;
+    n.has_provided = o.unpacked_size.value.has_value();
+    n.provided = o.unpacked_size.value.value_or(0);
+    n.has_memlimit = o.memlimit.has_value();
+    n.memlimit = o.memlimit.value_or(0);
+    detail::run(LZB_FMT_LZMA, &n, in, out);
+}
+inline void lzma_decompress(std::istream& in, std::ostream& out) { lzma_decompress_with_options(in, out, {}); }
+inline void lzma2_decompress(std::istream& in, std::ostream& out) { detail::run(LZB_FMT_LZMA2, nullptr, in, out); }
+inline void xz_decompress(std::istream& in, std::ostream& out) { detail::run(LZB_FMT_XZ, nullptr, in, out); }
+
+}  // namespace lzma_rs

@@ -1,0 +1,193 @@
+//! `lzma_b200`: the decode entry points of `lzma_rs` with the same signatures, executed on a B200 through the C ABI
+//! of `include/lzma_b200.h`.  Replace `use lzma_rs::{lzma_decompress, lzma2_decompress, xz_decompress}` with
+//! `use lzma_b200::{...}`; `decompress::{Options, UnpackedSize}` and `error::{Error, Result}` keep their shapes.
+//!
+//! NOT COMPILED in the build image (no Rust toolchain there) -- see INTEGRATION.md.
+use std::io;
+use std::os::raw::{c_char, c_int, c_void};
+use std::sync::Mutex;
+
+pub mod error {
+    use std::{fmt, io, result};
+    /// Same variants as `lzma_rs::error::Error` (src/error.rs:7-17).
+    #[derive(Debug)]
+    pub enum Error {
+        IoError(io::Error),
+        HeaderTooShort(io::Error),
+        LzmaError(String),
+        XzError(String),
+    }
+    pub type Result<T> = result::Result<T, Error>;
+    impl From<io::Error> for Error {
+        fn from(e: io::Error) -> Error {
+            Error::IoError(e)
+        }
+    }
+    impl fmt::Display for Error {
+        fn fmt(&self, f: &mut fmt::Formatter<'_>) -> fmt::Result {
+            match self {
+                Error::IoError(e) => write!(f, "io error: {}", e),
+                Error::HeaderTooShort(e) => write!(f, "header too short: {}", e),
+                Error::LzmaError(e) => write!(f, "lzma error: {}", e),
+                Error::XzError(e) => write!(f, "xz error: {}", e),
+            }
+        }
+    }
+    impl std::error::Error for Error {}
+}
+
+pub mod decompress {
+    /// `lzma_rs::decompress::UnpackedSize` (src/decode/options.rs:24-43)
+    #[derive(Clone, Copy, Debug, PartialEq, Eq, Default)]
+    pub enum UnpackedSize {
+        #[default]
+        ReadFromHeader,
+        ReadHeaderButUseProvided(Option<u64>),
+        UseProvided(Option<u64>),
+    }
+    /// `lzma_rs::decompress::Options` (src/decode/options.rs:3-20)
+    #[derive(Clone, Copy, Debug, PartialEq, Eq, Default)]
+    pub struct Options {
+        pub unpacked_size: UnpackedSize,
+        pub memlimit: Option<usize>,
+        pub allow_incomplete: bool,
+    }
+}
+
+// ---- C ABI (include/lzma_b200.h) ------------------------------------------------------------------------------
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+struct LzbOptions {
+    unpacked_mode: u8,
+    has_provided: u8,
+    has_memlimit: u8,
+    reserved: [u8; 5],
+    provided: u64,
+    memlimit: u64,
+}
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+struct LzbStatus {
+    code: i32,
+    kind: i32,
+    a0: u64,
+    a1: u64,
+    a2: u64,
+}
+#[repr(C)]
+struct LzbCtx {
+    _private: [u8; 0],
+}
+extern "C" {
+    fn lzb_create(ctx: *mut *mut LzbCtx, device: c_int) -> c_int;
+    fn lzb_decompress_alloc(
+        ctx: *mut LzbCtx, fmt: c_int, opt: *const LzbOptions, input: *const u8, in_len: usize, out: *mut *mut u8,
+        out_len: *mut usize, consumed: *mut usize, st: *mut LzbStatus,
+    ) -> c_int;
+    fn lzb_free(p: *mut c_void);
+    fn lzb_format_error(st: *const LzbStatus, buf: *mut c_char, buf_len: usize) -> usize;
+}
+const FMT_LZMA: c_int = 0;
+const FMT_LZMA2: c_int = 1;
+const FMT_XZ: c_int = 2;
+
+struct Ctx(*mut LzbCtx);
+unsafe impl Send for Ctx {}
+static CTX: Mutex<Option<Ctx>> = Mutex::new(None);
+
+fn with_ctx<T>(f: impl FnOnce(*mut LzbCtx) -> T) -> io::Result<T> {
+    let mut g = CTX.lock().unwrap();
+    if g.is_none() {
+        let mut p: *mut LzbCtx = std::ptr::null_mut();
+        let rc = unsafe { lzb_create(&mut p, -1) };
+        if rc != 0 {
+            return Err(io::Error::new(io::ErrorKind::Other, format!("lzb_create failed ({}): no CUDA device", rc)));
+        }
+        *g = Some(Ctx(p));
+    }
+    Ok(f(g.as_ref().unwrap().0))
+}
+
+fn to_error(st: &LzbStatus) -> error::Error {
+    // message = the reference's Display string without its "xxx error: " prefix
+    let mut buf = vec![0u8; 512];
+    let n = unsafe { lzb_format_error(st, buf.as_mut_ptr() as *mut c_char, buf.len()) }.min(buf.len() - 1);
+    let full = String::from_utf8_lossy(&buf[..n]).into_owned();
+    let strip = |p: &str| full.strip_prefix(p).unwrap_or(&full).to_string();
+    let eof = || io::Error::new(io::ErrorKind::UnexpectedEof, "failed to fill whole buffer");
+    match st.kind {
+        1 => error::Error::IoError(eof()),
+        2 => error::Error::HeaderTooShort(eof()),
+        3 => error::Error::LzmaError(strip("lzma error: ")),
+        4 => error::Error::XzError(strip("xz error: ")),
+        _ => error::Error::IoError(io::Error::new(io::ErrorKind::Other, full)),
+    }
+}
+
+fn run<R: io::BufRead, W: io::Write>(fmt: c_int, opt: &LzbOptions, input: &mut R, output: &mut W) -> error::Result<()> {
+    // The batch decoder wants the whole stream: buffer the reader, then give back what was not consumed.
+    let mut buf = Vec::new();
+    input.read_to_end(&mut buf)?;
+    let mut out: *mut u8 = std::ptr::null_mut();
+    let (mut out_len, mut consumed) = (0usize, 0usize);
+    let mut st = LzbStatus::default();
+    let rc = with_ctx(|c| unsafe {
+        lzb_decompress_alloc(c, fmt, opt, buf.as_ptr(), buf.len(), &mut out, &mut out_len, &mut consumed, &mut st)
+    })?;
+    if rc != 0 {
+        return Err(error::Error::IoError(io::Error::new(io::ErrorKind::Other, format!("lzma_b200 call failed: {}", rc))));
+    }
+    // like the reference, partial output reaches the sink even when the stream then fails
+    let res = if out_len > 0 { output.write_all(unsafe { std::slice::from_raw_parts(out, out_len) }) } else { Ok(()) };
+    unsafe { lzb_free(out as *mut c_void) };
+    res?;
+    if st.code != 0 {
+        return Err(to_error(&st));
+    }
+    // NOTE: a `&[u8]` / `Cursor` caller that needs the reference's "trailing bytes stay unread" behaviour should use
+    // `decompress_slice`, which returns `consumed`; a generic BufRead cannot be un-read.
+    let _ = consumed;
+    output.flush()?;
+    Ok(())
+}
+
+fn options(o: &decompress::Options) -> LzbOptions {
+    let mut r = LzbOptions::default();
+    match o.unpacked_size {
+        decompress::UnpackedSize::ReadFromHeader => r.unpacked_mode = 0,
+        decompress::UnpackedSize::ReadHeaderButUseProvided(x) => {
+            r.unpacked_mode = 1;
+            r.has_provided = x.is_some() as u8;
+            r.provided = x.unwrap_or(0);
+        }
+        decompress::UnpackedSize::UseProvided(x) => {
+            r.unpacked_mode = 2;
+            r.has_provided = x.is_some() as u8;
+            r.provided = x.unwrap_or(0);
+        }
+    }
+    if let Some(m) = o.memlimit {
+        r.has_memlimit = 1;
+        r.memlimit = m as u64;
+    }
+    r
+}
+
+/// `lzma_rs::lzma_decompress` (src/lib.rs:44-49)
+pub fn lzma_decompress<R: io::BufRead, W: io::Write>(input: &mut R, output: &mut W) -> error::Result<()> {
+    lzma_decompress_with_options(input, output, &decompress::Options::default())
+}
+/// `lzma_rs::lzma_decompress_with_options` (src/lib.rs:52-60)
+pub fn lzma_decompress_with_options<R: io::BufRead, W: io::Write>(
+    input: &mut R, output: &mut W, opts: &decompress::Options,
+) -> error::Result<()> {
+    run(FMT_LZMA, &options(opts), input, output)
+}
+/// `lzma_rs::lzma2_decompress` (src/lib.rs:83-88)
+pub fn lzma2_decompress<R: io::BufRead, W: io::Write>(input: &mut R, output: &mut W) -> error::Result<()> {
+    run(FMT_LZMA2, &LzbOptions::default(), input, output)
+}
+/// `lzma_rs::xz_decompress` (src/lib.rs:100-105)
+pub fn xz_decompress<R: io::BufRead, W: io::Write>(input: &mut R, output: &mut W) -> error::Result<()> {
+    run(FMT_XZ, &LzbOptions::default(), input, output)
+}

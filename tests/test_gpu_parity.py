@@ -164,3 +164,24 @@ def test_config4_xz_multiblock(ctx):
     res = _host(ctx)(2, files, {})
     for r, p, f in zip(res, plains, files):
         assert r.ok and r.data == p and r.consumed == len(f), r.display
+
+
+def test_cpp_host_mirror(ctx, golden, tmp_path):
+    """lzma_rs_b200/host/lzma_rs.hpp: the C++ mirror of the reference API, compiled with g++ against the C ABI."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host_check"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + root, "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "host_check.cpp"), "-L" + os.path.join(root, "lzma_rs_b200"),
+                           "-llzma_b200", "-Wl,-rpath," + os.path.join(root, "lzma_rs_b200"), "-o", str(exe)])
+    for name, fmt in [("foo.txt.lzma", "lzma"), ("good-1-lzma2-4.xz", "xz"), ("corrupt-footer.xz", "xz")]:
+        v = next(x for x in golden.vectors() if x["name"] == name)
+        src, dst = tmp_path / "in.bin", tmp_path / "out.bin"
+        src.write_bytes(golden.compressed(v))
+        r = subprocess.run([str(exe), fmt, str(src), str(dst)], capture_output=True, text=True)
+        assert hashlib.sha256(dst.read_bytes()).hexdigest() == v["plain_sha256"], name
+        if "error" in v:
+            assert r.returncode == 3 and r.stderr == v["error"], (name, r.stderr)
+        else:
+            assert r.returncode == 0, (name, r.stderr)
