@@ -252,14 +252,20 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
         goto finish;         \
     } while (0)
 
-// LIT_GLOBAL = false: all probability tables in shared memory (lc+lp <= tab_lclp <= 4; every LZMA2 stream).
-// LIT_GLOBAL = true : .lzma streams with lc+lp > 4 (legal up to 12, lzma.rs:62-66): the literal table
-//                     (0x300 << (lc+lp) u16, up to 6 MiB) lives in a per-warp global workspace `glit`.
-// MainTab / LitTab: table handles for the 1856 small-table entries and for the literal table.
-template <bool LIT_GLOBAL, class MainTab, class LitTab>
+// The literal table (lzma.rs:194, [1 << (lc+lp)][0x300]) is split by column:
+//   plain   columns 0x000..0x0FF  (every literal)                      -> `plain`,   row stride `plain_stride`
+//   matched columns 0x100..0x2FF  (first literal after a match only)   -> `matched`, row stride `matched_stride`,
+//                                                                         indexed (match_bit << 8) + node
+// LIT_GLOBAL = false: plain columns in shared memory (T + T_LIT, stride 0x100), matched columns in the per-warp global
+//                     workspace `gws` (stride 0x200); lc+lp <= tab_lclp <= 4, every LZMA2 stream.
+// LIT_GLOBAL = true : .lzma streams with lc+lp > 4 (legal up to 12, lzma.rs:62-66): the whole table (up to 6 MiB) in
+//                     `gws` with the reference's layout (stride 0x300; matched = +0x100).
+// MainTab / PlainTab / MatchedTab: handle types of the small tables and the two literal parts.
+template <bool LIT_GLOBAL, class MainTab, class PlainTab, class MatchedTab>
 LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t* __restrict__ in_blob,
-                                  uint8_t* out_blob, uint16_t* T, uint16_t* glit, const MainTab tab,
-                                  const LitTab lit, const LzbKC kc, uint32_t tab_lclp, LzbResult* res, int lane) {
+                                  uint8_t* out_blob, uint16_t* T, uint16_t* gws, const MainTab tab,
+                                  const PlainTab plain, const MatchedTab matched, const LzbKC kc, uint32_t tab_lclp,
+                                  LzbResult* res, int lane) {
     Dec d;
     const bool is_lzma1 = itp->kind == LZB_ITEM_LZMA;
     const uint32_t p0 = (uint32_t)(itp->in_off & 3ull);
@@ -267,7 +273,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
     const uint32_t stream_lim = p0 + (uint32_t)itp->in_len;
     uint8_t* out = out_blob + itp->out_off;
     const uint32_t cap = (uint32_t)LZB_MIN(itp->out_cap, (uint64_t)0xFFFFF000u);
-    const uint32_t tab_u16 = LIT_GLOBAL ? (uint32_t)T_LIT : T_LIT + (0x300u << tab_lclp);
+    const uint32_t tab_u16 = LIT_GLOBAL ? (uint32_t)T_LIT : T_LIT + (0x100u << tab_lclp);
+    const uint32_t plain_stride = LIT_GLOBAL ? 0x300u : 0x100u, matched_stride = LIT_GLOBAL ? 0x300u : 0x200u;
     uint32_t opos = 0, dict_base = 0;
     uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
     uint32_t lc = 0, lp = 0, pb = 0;
@@ -312,7 +319,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
         if (lc + lp > tab_lclp) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
     }
     fill_tables(T, tab_u16, lane);
-    if (LIT_GLOBAL) fill_tables(glit, 0x300u << (lc + lp), lane);  // .lzma only: props never change mid-stream
+    // global part: the whole literal table (LIT_GLOBAL; .lzma props never change mid-stream) or the matched columns
+    fill_tables(gws, LIT_GLOBAL ? 0x300u << (lc + lp) : 0x200u << tab_lclp, lane);
 
     for (;;) {  // LZMA2 chunk loop (lzma2.rs:59-78); a .lzma stream is a single pass
         if (is_lzma1) {
@@ -378,7 +386,10 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     if (lc + lp > 4) FAIL(LZB_E_L2_PROPS_LCLP, lc, lp);
                 }
                 if (lc + lp > tab_lclp) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
-                if (!tables_fresh) fill_tables(T, tab_u16, lane);  // reset_state, lzma.rs:216-249
+                if (!tables_fresh) {  // reset_state, lzma.rs:216-249
+                    fill_tables(T, tab_u16, lane);
+                    fill_tables(gws, 0x200u << tab_lclp, lane);
+                }
                 state = 0;
                 rep0 = rep1 = rep2 = rep3 = 0;
             }
@@ -417,7 +428,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
             // literal context row (decode_literal, lzma.rs:526-538).  After a literal (state < 7) prev_byte is in a
             // register, so the root of the plain literal tree is fetched while is_match is being decoded.
-            const LitTab probs = lit.at(kc, (((len & lp_mask) << lc) + (prev_byte >> lit_shift)) * 0x300u);
+            const uint32_t lit_row = ((len & lp_mask) << lc) + (prev_byte >> lit_shift);
+            const PlainTab probs = plain.at(kc, lit_row * plain_stride);
             const uint32_t i_is_match = T_IS_MATCH + (state << 4) + pos_state;
             const uint32_t p_is_match = tab.ld16(kc, i_is_match);
             uint32_t lit_pv = 0, lit_pair = 0;
@@ -442,11 +454,12 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                         match_byte = out[opos - rep0 - 1];
                     }
                     uint32_t mb = match_byte;
+                    const MatchedTab mprobs = matched.at(kc, lit_row * matched_stride);
 #pragma unroll 1
                     do {
                         const uint32_t match_bit = (mb >> 7) & 1u;
                         mb <<= 1;
-                        const uint32_t bit = rc_bit(d, kc, probs, ((1u + match_bit) << 8) + sym);
+                        const uint32_t bit = rc_bit(d, kc, mprobs, (match_bit << 8) + sym);
                         sym = (sym << 1) | bit;
                         if (match_bit != bit) break;
                     } while (sym < 0x100);

@@ -19,7 +19,8 @@ struct LzbCrcRange {
 #define CRC_SEG 4096u
 
 extern "C" __global__ void lzb_decode_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
-                                             LzbResult*, unsigned int*, uint32_t, uint32_t, const LzbKC);
+                                             LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long,
+                                             const LzbKC);
 extern "C" __global__ void lzb_decode_biglit_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
                                                     LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*,
                                                     unsigned long long, const LzbKC);
@@ -67,7 +68,7 @@ struct lzb_ctx {
     char err[320] = {0};
     std::mutex mu;
     DevBuf d_in, d_out, d_items, d_results, d_order, d_counter, d_scan, d_off, d_crc_ranges, d_crc_segmap, d_crc_part32,
-        d_crc_part64, d_crc_out32, d_crc_out64, d_litws;
+        d_crc_part64, d_crc_out32, d_crc_out64, d_litws, d_matchws;
 };
 
 #define CUDA_TRY(ctx, call)                                                                         \
@@ -90,7 +91,7 @@ LaunchCfg decode_config(const lzb_ctx* ctx, uint32_t n, uint32_t lclp) {
     LaunchCfg c;
     c.lclp = lclp;
     c.warp_bytes = (lzb_table_u16(lclp) * 2 + 15u) & ~15u;
-    uint32_t max_warps = std::min<uint32_t>(16, (uint32_t)ctx->smem_optin / c.warp_bytes);
+    uint32_t max_warps = std::min<uint32_t>(LZB_MAX_WARPS, (uint32_t)ctx->smem_optin / c.warp_bytes);
     if (max_warps < 1) max_warps = 1;
     uint32_t per_sm = (n + ctx->sm_count - 1) / ctx->sm_count;
     c.warps = std::min(std::max<uint32_t>(per_sm, 1), max_warps);
@@ -133,9 +134,9 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
         c.warp_bytes = ((uint32_t)T_LIT * 2 + 15u) & ~15u;
         p->big_stride_u16 = (uint64_t)0x300u << lclp_big;
         const uint64_t ws_budget = 1ull << 30;  // bound the workspace to 1 GiB
-        uint32_t total_warps = (uint32_t)std::min<uint64_t>(p->order_big.size(), (uint64_t)ctx->sm_count * 16);
+        uint32_t total_warps = (uint32_t)std::min<uint64_t>(p->order_big.size(), (uint64_t)ctx->sm_count * LZB_MAX_WARPS);
         total_warps = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(total_warps, ws_budget / (p->big_stride_u16 * 2)));
-        c.warps = std::max<uint32_t>(1, std::min<uint32_t>(16, (total_warps + ctx->sm_count - 1) / ctx->sm_count));
+        c.warps = std::max<uint32_t>(1, std::min<uint32_t>(LZB_MAX_WARPS, (total_warps + ctx->sm_count - 1) / ctx->sm_count));
         c.grid = std::max<uint32_t>(1, total_warps / c.warps);
     }
 }
@@ -154,8 +155,12 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
             CUDA_TRY(ctx, cudaFuncSetAttribute(lzb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
             ctx->smem_configured = ctx->smem_optin;
         }
+        // per-warp global workspace for the matched-literal columns (L2-resident: 8 KiB per warp at lc+lp = 3)
+        const uint64_t mstride = lzb_matched_u16(c.lclp);
+        CUDA_TRY(ctx, ctx->d_matchws.ensure((size_t)c.grid * c.warps * mstride * 2));
         lzb_decode_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, d_in_base, d_out_base, d_results,
-                                                             d_counter, c.lclp, c.warp_bytes, kc);
+                                                             d_counter, c.lclp, c.warp_bytes,
+                                                             ctx->d_matchws.as<uint16_t>(), mstride, kc);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     if (nb) {
@@ -305,7 +310,7 @@ extern "C" void lzb_destroy(lzb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_items, &ctx->d_results, &ctx->d_order, &ctx->d_counter, &ctx->d_scan,
                       &ctx->d_off, &ctx->d_crc_ranges, &ctx->d_crc_segmap, &ctx->d_crc_part32, &ctx->d_crc_part64,
-                      &ctx->d_crc_out32, &ctx->d_crc_out64, &ctx->d_litws};
+                      &ctx->d_crc_out32, &ctx->d_crc_out64, &ctx->d_litws, &ctx->d_matchws};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -28,7 +28,7 @@ template <bool LIT_GLOBAL>
 __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order,
                                             uint32_t n_items, const uint8_t* __restrict__ in_blob, uint8_t* out_blob,
                                             LzbResult* results, unsigned int* counter, uint32_t tab_lclp,
-                                            uint32_t warp_smem_bytes, uint16_t* glit, const LzbKC& kc) {
+                                            uint32_t warp_smem_bytes, uint16_t* gws, const LzbKC& kc) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     // broadcast from lane 0 so that the compiler's divergence analysis sees the warp index (and with it every
@@ -43,28 +43,30 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
         slot = __shfl_sync(FULL_MASK, slot, 0);
         if (slot >= n_items) break;
         const uint32_t idx = order ? order[slot] : slot;
-        if (LIT_GLOBAL) {
-            const TabPtr lit = {glit};
-            decode_item<true>(items + idx, in_blob, out_blob, T, glit, tab, lit, kc, tab_lclp, results + idx, lane);
-        } else {
-            const TabSm lit = {tab.a + (uint32_t)T_LIT * 2u};
-            decode_item<false>(items + idx, in_blob, out_blob, T, glit, tab, lit, kc, tab_lclp, results + idx, lane);
+        if (LIT_GLOBAL) {  // whole literal table in the global workspace (reference layout)
+            const TabPtr plain = {gws}, matched = {gws + 0x100};
+            decode_item<true>(items + idx, in_blob, out_blob, T, gws, tab, plain, matched, kc, tab_lclp, results + idx, lane);
+        } else {  // plain columns in shared memory, matched columns in the global workspace
+            const TabSm plain = {tab.a + (uint32_t)T_LIT * 2u};
+            const TabPtr matched = {gws};
+            decode_item<false>(items + idx, in_blob, out_blob, T, gws, tab, plain, matched, kc, tab_lclp, results + idx, lane);
         }
         __syncwarp();
     }
 }
 
-extern "C" __global__ void __launch_bounds__(512, 1)
+extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1)
     lzb_decode_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
                       const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
-                      unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes,
-                      const __grid_constant__ LzbKC kc) {
-    decode_loop<false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, nullptr,
-                       kc);
+                      unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
+                      unsigned long long ws_stride_u16, const __grid_constant__ LzbKC kc) {
+    const unsigned long long wid = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    decode_loop<false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes,
+                       ws + wid * ws_stride_u16, kc);
 }
 
 // .lzma streams with lc+lp > 4: literal table in a per-warp global workspace (ws + warp_id * ws_stride_u16).
-extern "C" __global__ void __launch_bounds__(512, 1)
+extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1)
     lzb_decode_biglit_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
                              const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
                              unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,

@@ -56,7 +56,8 @@ enum {
     T_ALIGN = 812,       // [16]                                  lzma.rs:173
     T_LEN = 828,         // choice, choice2, low[16][8], mid[16][8], high[256]   rangecoder.rs:202-209
     T_REP_LEN = 1342,    // same
-    T_LIT = 1856,        // [1<<(lc+lp)][0x300]                   lzma.rs:194
+    T_LIT = 1856,        // PLAIN part of the literal table: [1<<(lc+lp)][0x100] (columns 0..0xFF of lzma.rs:194);
+                         // the matched-literal columns 0x100..0x2FF live in a per-warp global workspace
     T_LEN_SIZE = 514,
     T_LEN_LOW = 2,
     T_LEN_MID = 2 + 128,
@@ -66,9 +67,16 @@ enum {
 // Multipliers / addends the bit loop reads from the kernel's constant bank.  Passing them as launch parameters keeps
 // nvcc/ptxas from strength-reducing `x * 2 + y` into ALU-pipe shifts and selects: as IMADs with a constant-bank
 // operand they run on the (otherwise idle) FMA pipe, which halves the ALU-pipe pressure that bounds K1.
+// Warps (= resident streams) per CTA, one CTA per SM: bounded by registers (65 536 / (32 * 24) = 85 per thread).
+#define LZB_MAX_WARPS 24
+
 struct LzbKC {
     uint32_t two, four, m1, m2017, k2048, k22, k4410;
 };
 #define LZB_KC_INIT {2u, 4u, 0xFFFFFFFFu, (uint32_t)-2017, 2048u, 0x22u, 0x4410u}
 
-static inline uint32_t lzb_table_u16(uint32_t lclp) { return (uint32_t)T_LIT + (0x300u << lclp); }
+// Shared-memory u16 per warp: small tables + plain literal columns.  Matched-literal columns (only touched by
+// the first literal after a match, until its first mismatching bit) go to global memory (L1/L2): that halves
+// the shared-memory footprint and raises residency from 14 to 24 streams per SM at lc+lp = 3.
+static inline uint32_t lzb_table_u16(uint32_t lclp) { return (uint32_t)T_LIT + (0x100u << lclp); }
+static inline uint32_t lzb_matched_u16(uint32_t lclp) { return 0x200u << lclp; }

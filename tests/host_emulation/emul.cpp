@@ -16,19 +16,20 @@ class HostEmulExecutor : public lzb::Executor {
     HostEmulExecutor(const uint8_t* in, uint8_t* out) : in_(in), out_(out) {}
     int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, LzbResult* results) override {
         const uint32_t small_lclp = max_lclp > 4 ? 4 : max_lclp;
-        std::vector<uint16_t> T(lzb_table_u16(small_lclp) + 8), T4, G;
+        std::vector<uint16_t> T(lzb_table_u16(small_lclp) + 8), M(lzb_matched_u16(small_lclp) + 8), T4, M4, G;
         for (uint32_t i = 0; i < n; i++) {
             memset(&results[i], 0, sizeof results[i]);
             const uint32_t lclp = (uint32_t)items[i].lc + items[i].lp;
-            if (items[i].kind == LZB_ITEM_LZMA && lclp > 4) {  // literal table outside "shared memory"
+            if (items[i].kind == LZB_ITEM_LZMA && lclp > 4) {  // whole literal table outside "shared memory"
                 G.assign((size_t)0x300u << lclp, 0);
                 run<true>(items + i, T.data(), G.data(), lclp, results + i);
                 continue;
             }
-            run<false>(items + i, T.data(), nullptr, small_lclp, results + i);
+            run<false>(items + i, T.data(), M.data(), small_lclp, results + i);
             if (results[i].code == LZB_E_UNSUPPORTED && results[i].a1 == small_lclp && results[i].a0 <= 4) {
                 T4.resize(lzb_table_u16(4) + 8);  // framing scan under-estimated lc+lp: retry with the LZMA2 maximum
-                run<false>(items + i, T4.data(), nullptr, 4, results + i);
+                M4.resize(lzb_matched_u16(4) + 8);
+                run<false>(items + i, T4.data(), M4.data(), 4, results + i);
             }
         }
         return LZB_RC_OK;
@@ -69,8 +70,9 @@ class HostEmulExecutor : public lzb::Executor {
     void run(const LzbItem* it, uint16_t* T, uint16_t* G, uint32_t lclp, LzbResult* res) {
         const LzbKC kc = LZB_KC_INIT;
         const TabPtr tab = {T};
-        const TabPtr lit = {BIG ? G : T + T_LIT};
-        decode_item<BIG>(it, in_, out_, T, G, tab, lit, kc, lclp, res, 0);
+        const TabPtr plain = {BIG ? G : T + T_LIT};
+        const TabPtr matched = {BIG ? G + 0x100 : G};
+        decode_item<BIG>(it, in_, out_, T, G, tab, plain, matched, kc, lclp, res, 0);
     }
     const uint8_t* in_;
     uint8_t* out_;
