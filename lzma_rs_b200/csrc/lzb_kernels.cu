@@ -28,7 +28,8 @@ template <bool LIT_GLOBAL>
 __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order,
                                             uint32_t n_items, const uint8_t* __restrict__ in_blob, uint8_t* out_blob,
                                             LzbResult* results, unsigned int* counter, uint32_t tab_lclp,
-                                            uint32_t warp_smem_bytes, uint16_t* gws, const LzbKC& kc) {
+                                            uint32_t warp_smem_bytes, uint16_t* ws, unsigned long long ws_stride_u16,
+                                            const LzbKC& kc) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     // broadcast from lane 0 so that the compiler's divergence analysis sees the warp index (and with it every
@@ -37,6 +38,8 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
     const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
     uint16_t* T = reinterpret_cast<uint16_t*>(smem + (size_t)warp * warp_smem_bytes);
     const TabSm tab = {(uint32_t)__cvta_generic_to_shared(T)};
+    // this warp's slice of the global workspace -- indexed with the broadcast (provably uniform) warp index as well
+    uint16_t* gws = ws + ((unsigned long long)blockIdx.x * (blockDim.x >> 5) + (unsigned)warp) * ws_stride_u16;
     for (;;) {
         unsigned int slot = 0;
         if (lane == 0) slot = atomicAdd(counter, 1u);
@@ -60,9 +63,8 @@ extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1)
                       const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
                       unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
                       unsigned long long ws_stride_u16, const __grid_constant__ LzbKC kc) {
-    const unsigned long long wid = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    decode_loop<false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes,
-                       ws + wid * ws_stride_u16, kc);
+    decode_loop<false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
+                       ws_stride_u16, kc);
 }
 
 // .lzma streams with lc+lp > 4: literal table in a per-warp global workspace (ws + warp_id * ws_stride_u16).
@@ -71,9 +73,8 @@ extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1)
                              const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
                              unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
                              unsigned long long ws_stride_u16, const __grid_constant__ LzbKC kc) {
-    const unsigned long long wid = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    decode_loop<true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes,
-                      ws + wid * ws_stride_u16, kc);
+    decode_loop<true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
+                      ws_stride_u16, kc);
 }
 
 // ------------------------------------------------------------------------------------------------
