@@ -68,7 +68,9 @@ enum {
 // nvcc/ptxas from strength-reducing `x * 2 + y` into ALU-pipe shifts and selects: as IMADs with a constant-bank
 // operand they run on the (otherwise idle) FMA pipe, which halves the ALU-pipe pressure that bounds K1.
 // Warps (= resident streams) per CTA, one CTA per SM: bounded by registers (65 536 / (32 * 24) = 85 per thread).
-#define LZB_MAX_WARPS 24
+#ifndef LZB_MAX_WARPS
+#define LZB_MAX_WARPS 28
+#endif
 
 struct LzbKC {
     uint32_t two, four, m1, m2017, k2048, k22, k4410;
