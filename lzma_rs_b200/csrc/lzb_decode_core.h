@@ -77,10 +77,6 @@ LZB_DEV void rc_normalize(Dec& d) {
     }
 }
 
-#ifndef LZB_PAIR_PREFETCH
-#define LZB_PAIR_PREFETCH 0
-#endif
-
 // The arithmetic of decode_bit (rangecoder.rs:93-120) on a probability already in a register.  Returns the bit
 // (0/1); `np` = updated probability: one: p -= p >> 5; zero: p += (2048 - p) >> 5  ==  p + ((K - p) >>arith 5),
 // K = one ? 31 : 2048 = 2048 - 2017 * bit  (floor((31 - p) / 32) == -(p >> 5)).  Normalisation is the caller's
@@ -109,6 +105,38 @@ LZB_DEV uint32_t rc_step(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np) {
     return bit;
 }
 
+// rc_step fused with the tree-node update.  A node is a handle-specific integer (TabSm: the byte address of the
+// node's probability; TabPtr: its index); the child for `bit` is 2 * node + (bit ? x1 : x0) with per-tree constants
+// x0 / x1 (TabSm: 0 - base and 2 - base; TabPtr: 0 and 1), so one select and one multiply-add replace
+// "bit to register, m = 2m + bit, address = base + 2m".  The probability addend K = bit ? 31 : 2048 is selected
+// from the same predicate.  Returns the child node; `np` = updated probability of the current node.
+LZB_DEV uint32_t rc_step_tree(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np, uint32_t node, uint32_t x0,
+                              uint32_t x1) {
+    const uint32_t bound = (d.range >> 11) * pv;
+    uint32_t child, t;
+#ifdef __CUDACC__
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 rb, kk, xx;\n\t"
+        "setp.ge.u32 p, %3, %4;\n\t"
+        "sub.u32 rb, %2, %4;\n\t"
+        "selp.u32 xx, %8, %7, p;\n\t"
+        "selp.u32 kk, 31, 2048, p;\n\t"
+        "selp.u32 %2, rb, %4, p;\n\t"
+        "@p sub.u32 %3, %3, %4;\n\t"
+        "mad.lo.u32 %0, %6, %9, xx;\n\t"
+        "mad.lo.u32 %1, %5, %10, kk;\n\t}"
+        : "=r"(child), "=r"(t), "+r"(d.range), "+r"(d.code)
+        : "r"(bound), "r"(pv), "r"(node), "r"(x0), "r"(x1), "r"(kc.two), "r"(kc.m1));
+#else
+    const uint32_t bit = d.code >= bound ? 1u : 0u;
+    d.range = bit ? d.range - bound : bound;
+    if (bit) d.code -= bound;
+    child = node * kc.two + (bit ? x1 : x0);
+    t = pv * kc.m1 + (bit ? 31u : 2048u);
+#endif
+    np = pv + (uint32_t)((int32_t)t >> 5);
+    return child;
+}
+
 // ---- probability-table handles: u16 index in, value out -------------------------------------------------------
 // TabPtr : plain pointers (host emulation; the global literal workspace of the lc+lp > 4 variant).
 // TabSm  : 32-bit shared-space addresses with explicit ld/st.shared (device): addresses are IMADs off the
@@ -116,10 +144,14 @@ LZB_DEV uint32_t rc_step(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np) {
 struct TabPtr {
     uint16_t* b;
     LZB_MEM uint32_t ld16(const LzbKC&, uint32_t i) const { return b[i]; }
-    LZB_MEM uint32_t ld_children(const LzbKC&, uint32_t m) const {  // probs[2m] | probs[2m+1] << 16
-        return (uint32_t)b[2 * m] | ((uint32_t)b[2 * m + 1] << 16);
-    }
     LZB_MEM void st16(const LzbKC&, uint32_t i, uint32_t v) const { b[i] = (uint16_t)v; }
+    // tree-node interface (node = index)
+    LZB_MEM uint32_t root(const LzbKC&) const { return 1u; }
+    LZB_MEM uint32_t x0(const LzbKC&) const { return 0u; }
+    LZB_MEM uint32_t x1(const LzbKC&) const { return 1u; }
+    LZB_MEM uint32_t ldn(const LzbKC&, uint32_t node) const { return b[node]; }
+    LZB_MEM void stn(const LzbKC&, uint32_t node, uint32_t v) const { b[node] = (uint16_t)v; }
+    LZB_MEM uint32_t node_index(const LzbKC&, uint32_t node) const { return node; }
     LZB_MEM TabPtr at(const LzbKC&, uint32_t off) const {
         TabPtr t = {b + off};
         return t;
@@ -133,32 +165,28 @@ struct TabSm {
         asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(i * kc.two + a) : "memory");
         return v;
     }
-    LZB_MEM uint32_t ld_children(const LzbKC& kc, uint32_t m) const {  // needs a 4-byte aligned table base
-        uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(m * kc.four + a) : "memory");
-        return v;
-    }
     LZB_MEM void st16(const LzbKC& kc, uint32_t i, uint32_t v) const {
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(i * kc.two + a), "h"((uint16_t)v) : "memory");
     }
+    // tree-node interface (node = byte address of the node's probability)
+    LZB_MEM uint32_t root(const LzbKC&) const { return a + 2u; }
+    LZB_MEM uint32_t x0(const LzbKC&) const { return 0u - a; }
+    LZB_MEM uint32_t x1(const LzbKC&) const { return 2u - a; }
+    LZB_MEM uint32_t ldn(const LzbKC&, uint32_t node) const {
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(node) : "memory");
+        return v;
+    }
+    LZB_MEM void stn(const LzbKC&, uint32_t node, uint32_t v) const {
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(node), "h"((uint16_t)v) : "memory");
+    }
+    LZB_MEM uint32_t node_index(const LzbKC&, uint32_t node) const { return (node - a) >> 1; }
     LZB_MEM TabSm at(const LzbKC& kc, uint32_t off) const {
         TabSm t = {off * kc.two + a};
         return t;
     }
 };
 #endif
-
-// child probability for the decoded bit out of a prefetched pair
-LZB_DEV uint32_t pick_child(const LzbKC& kc, uint32_t pair, uint32_t bit) {
-#ifdef __CUDACC__
-    uint32_t r;
-    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(pair), "r"(bit * kc.k22 + kc.k4410));  // bytes {0,1} or {2,3}
-    return r;
-#else
-    (void)kc;
-    return bit ? (pair >> 16) : (pair & 0xFFFFu);
-#endif
-}
 
 // decode_bit on a table entry
 template <class Tab>
@@ -184,30 +212,23 @@ LZB_DEV uint32_t rc_direct(Dec& d, uint32_t count) {
     return r;
 }
 
-// Bit-tree walk (parse_bit_tree, rangecoder.rs:122-134) of `nb` levels; `t` is the tree's table (node m at index m,
-// 4-byte aligned base).  Returns the final node index m in [2^nb, 2^(nb+1)): forward value = m - 2^nb; the reverse
-// trees (parse_reverse_bit_tree, 136-151) walk the same nodes, so their value is the bit reversal of that.
-// With LZB_PAIR_PREFETCH both children of the current node (adjacent u16) are fetched with one 32-bit load before
-// the decision is known, which takes the shared-memory latency off the serial chain.
+// Bit-tree walk (parse_bit_tree, rangecoder.rs:122-134) of `nb` levels; `t` is the tree's table (node m at index m).
+// Returns the final node index m in [2^nb, 2^(nb+1)): forward value = m - 2^nb; the reverse trees
+// (parse_reverse_bit_tree, 136-151) walk the same nodes, so their value is the bit reversal of that.
 template <bool UNROLL, int NB_CONST, class Tab>
 LZB_DEV uint32_t rc_tree_walk(Dec& d, const LzbKC& kc, const Tab& t, uint32_t nb_rt) {
     const uint32_t nb = UNROLL ? (uint32_t)NB_CONST : nb_rt;
-    uint32_t m = 1;
-    uint32_t pv = t.ld16(kc, 1);
-    uint32_t pair = (LZB_PAIR_PREFETCH && nb > 1) ? t.ld_children(kc, 1) : 0u;
-#define LZB_TREE_STEP(I, NBV)                                            \
-    {                                                                    \
-        uint32_t np;                                                     \
-        const uint32_t bit = rc_step(d, kc, pv, np);                     \
-        t.st16(kc, m, np);                                               \
-        m = m * kc.two + bit;                                            \
-        if (LZB_PAIR_PREFETCH) {                                         \
-            pv = pick_child(kc, pair, bit);                              \
-            if ((uint32_t)(I) + 2 < (NBV)) pair = t.ld_children(kc, m);  \
-        } else if ((uint32_t)(I) + 1 < (NBV)) {                          \
-            pv = t.ld16(kc, m);                                          \
-        }                                                                \
-        rc_normalize(d);                                                 \
+    const uint32_t x0 = t.x0(kc), x1 = t.x1(kc);
+    uint32_t node = t.root(kc);
+    uint32_t pv = t.ldn(kc, node);
+#define LZB_TREE_STEP(I, NBV)                                                   \
+    {                                                                           \
+        uint32_t np;                                                            \
+        const uint32_t child = rc_step_tree(d, kc, pv, np, node, x0, x1);       \
+        t.stn(kc, node, np);                                                    \
+        node = child;                                                           \
+        if ((uint32_t)(I) + 1 < (NBV)) pv = t.ldn(kc, node);                    \
+        rc_normalize(d);                                                        \
     }
     if (UNROLL) {
 #pragma unroll
@@ -217,7 +238,7 @@ LZB_DEV uint32_t rc_tree_walk(Dec& d, const LzbKC& kc, const Tab& t, uint32_t nb
         for (uint32_t i = 0; i < nb; i++) LZB_TREE_STEP(i, nb)
     }
 #undef LZB_TREE_STEP
-    return m;
+    return t.node_index(kc, node);
 }
 
 template <class Tab>
@@ -432,11 +453,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
             const PlainTab probs = plain.at(kc, lit_row * plain_stride);
             const uint32_t i_is_match = T_IS_MATCH + (state << 4) + pos_state;
             const uint32_t p_is_match = tab.ld16(kc, i_is_match);
-            uint32_t lit_pv = 0, lit_pair = 0;
-            if (state < 7) {
-                lit_pv = probs.ld16(kc, 1);
-                if (LZB_PAIR_PREFETCH) lit_pair = probs.ld_children(kc, 1);
-            }
+            uint32_t lit_pv = 0;
+            if (state < 7) lit_pv = probs.ldn(kc, probs.root(kc));
             uint32_t np_im;
             const uint32_t is_lz = rc_step(d, kc, p_is_match, np_im);
             tab.st16(kc, i_is_match, np_im);
@@ -466,21 +484,18 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 #pragma unroll 1
                     while (sym < 0x100) sym = (sym << 1) | rc_bit(d, kc, probs, sym);
                 } else {  // plain 8-level walk (root fetched above, while is_match was being decoded)
-                    uint32_t pv = lit_pv, pair = lit_pair;
+                    const uint32_t x0 = probs.x0(kc), x1 = probs.x1(kc);
+                    uint32_t node = probs.root(kc), pv = lit_pv;
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         uint32_t np;
-                        const uint32_t bit = rc_step(d, kc, pv, np);
-                        probs.st16(kc, sym, np);
-                        sym = sym * kc.two + bit;
-                        if (LZB_PAIR_PREFETCH) {
-                            pv = pick_child(kc, pair, bit);
-                            if (i < 6) pair = probs.ld_children(kc, sym);
-                        } else if (i < 7) {
-                            pv = probs.ld16(kc, sym);
-                        }
+                        const uint32_t child = rc_step_tree(d, kc, pv, np, node, x0, x1);
+                        probs.stn(kc, node, np);
+                        node = child;
+                        if (i < 7) pv = probs.ldn(kc, node);
                         rc_normalize(d);
                     }
+                    sym = probs.node_index(kc, node);
                 }
                 if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
                 if (opos >= lit_limit) {
