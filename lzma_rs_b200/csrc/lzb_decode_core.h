@@ -83,24 +83,27 @@ LZB_DEV void rc_normalize(Dec& d) {
 // next step.  On the device the compare / range select / conditional code update are pinned in PTX so that the
 // bit stays an opaque register for the constant-bank IMADs around it.
 LZB_DEV uint32_t rc_step(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np) {
-    const uint32_t bound = (d.range >> 11) * pv;
-    uint32_t bit;
+    uint32_t bit, t;
 #ifdef __CUDACC__
-    asm("{\n\t.reg .pred p;\n\t.reg .u32 rb;\n\t"
-        "setp.ge.u32 p, %2, %3;\n\t"
-        "sub.u32 rb, %1, %3;\n\t"
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 rs, bound, rb, kk;\n\t"
+        "mul.hi.u32 rs, %2, %6;\n\t"
+        "mul.lo.u32 bound, rs, %4;\n\t"
+        "setp.ge.u32 p, %3, bound;\n\t"
+        "sub.u32 rb, %2, bound;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
-        "selp.u32 %1, rb, %3, p;\n\t"
-        "@p sub.u32 %2, %2, %3;\n\t}"
-        : "=r"(bit), "+r"(d.range), "+r"(d.code)
-        : "r"(bound));
+        "selp.u32 kk, 31, 2048, p;\n\t"
+        "selp.u32 %2, rb, bound, p;\n\t"
+        "@p sub.u32 %3, %3, bound;\n\t"
+        "mad.lo.u32 %1, %4, %5, kk;\n\t}"
+        : "=r"(bit), "=r"(t), "+r"(d.range), "+r"(d.code)
+        : "r"(pv), "r"(kc.m1), "r"(kc.shr11));
 #else
+    const uint32_t bound = (d.range >> 11) * pv;
     bit = d.code >= bound ? 1u : 0u;
     d.range = bit ? d.range - bound : bound;
     if (bit) d.code -= bound;
+    t = pv * kc.m1 + (bit ? 31u : 2048u);  // K - p
 #endif
-    const uint32_t k = bit * kc.m2017 + kc.k2048;  // 31 or 2048
-    const uint32_t t = pv * kc.m1 + k;             // K - p
     np = pv + (uint32_t)((int32_t)t >> 5);
     return bit;
 }
@@ -112,21 +115,25 @@ LZB_DEV uint32_t rc_step(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np) {
 // from the same predicate.  Returns the child node; `np` = updated probability of the current node.
 LZB_DEV uint32_t rc_step_tree(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np, uint32_t node, uint32_t x0,
                               uint32_t x1) {
-    const uint32_t bound = (d.range >> 11) * pv;
     uint32_t child, t;
 #ifdef __CUDACC__
-    asm("{\n\t.reg .pred p;\n\t.reg .u32 rb, kk, xx;\n\t"
-        "setp.ge.u32 p, %3, %4;\n\t"
-        "sub.u32 rb, %2, %4;\n\t"
-        "selp.u32 xx, %8, %7, p;\n\t"
+    // range >> 11 as mul.hi by 2^21 and the multiply-adds with constant-bank multipliers keep this on the FMA pipe;
+    // compare + three selects are what is left for the ALU pipe
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 rs, bound, rb, kk, xx;\n\t"
+        "mul.hi.u32 rs, %2, %10;\n\t"
+        "mul.lo.u32 bound, rs, %4;\n\t"
+        "setp.ge.u32 p, %3, bound;\n\t"
+        "sub.u32 rb, %2, bound;\n\t"
+        "selp.u32 xx, %7, %6, p;\n\t"
         "selp.u32 kk, 31, 2048, p;\n\t"
-        "selp.u32 %2, rb, %4, p;\n\t"
-        "@p sub.u32 %3, %3, %4;\n\t"
-        "mad.lo.u32 %0, %6, %9, xx;\n\t"
-        "mad.lo.u32 %1, %5, %10, kk;\n\t}"
+        "selp.u32 %2, rb, bound, p;\n\t"
+        "@p sub.u32 %3, %3, bound;\n\t"
+        "mad.lo.u32 %0, %5, %8, xx;\n\t"
+        "mad.lo.u32 %1, %4, %9, kk;\n\t}"
         : "=r"(child), "=r"(t), "+r"(d.range), "+r"(d.code)
-        : "r"(bound), "r"(pv), "r"(node), "r"(x0), "r"(x1), "r"(kc.two), "r"(kc.m1));
+        : "r"(pv), "r"(node), "r"(x0), "r"(x1), "r"(kc.two), "r"(kc.m1), "r"(kc.shr11));
 #else
+    const uint32_t bound = (d.range >> 11) * pv;
     const uint32_t bit = d.code >= bound ? 1u : 0u;
     d.range = bit ? d.range - bound : bound;
     if (bit) d.code -= bound;

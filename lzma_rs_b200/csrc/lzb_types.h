@@ -73,9 +73,9 @@ enum {
 #endif
 
 struct LzbKC {
-    uint32_t two, four, m1, m2017, k2048, k22, k4410;
+    uint32_t two, four, m1, m2017, k2048, shr11;
 };
-#define LZB_KC_INIT {2u, 4u, 0xFFFFFFFFu, (uint32_t)-2017, 2048u, 0x22u, 0x4410u}
+#define LZB_KC_INIT {2u, 4u, 0xFFFFFFFFu, (uint32_t)-2017, 2048u, 1u << 21}
 
 // Shared-memory u16 per warp: small tables + plain literal columns.  Matched-literal columns (only touched by
 // the first literal after a match, until its first mismatching bit) go to global memory (L1/L2): that halves
