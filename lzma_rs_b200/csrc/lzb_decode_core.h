@@ -86,7 +86,7 @@ LZB_DEV uint32_t rc_step(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np) {
     uint32_t bit, t;
 #ifdef __CUDACC__
     asm("{\n\t.reg .pred p;\n\t.reg .u32 rs, bound, rb, kk;\n\t"
-        "mul.hi.u32 rs, %2, %6;\n\t"
+        "shr.u32 rs, %2, 11;\n\t"
         "mul.lo.u32 bound, rs, %4;\n\t"
         "setp.ge.u32 p, %3, bound;\n\t"
         "sub.u32 rb, %2, bound;\n\t"
@@ -96,7 +96,7 @@ LZB_DEV uint32_t rc_step(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np) {
         "@p sub.u32 %3, %3, bound;\n\t"
         "mad.lo.u32 %1, %4, %5, kk;\n\t}"
         : "=r"(bit), "=r"(t), "+r"(d.range), "+r"(d.code)
-        : "r"(pv), "r"(kc.m1), "r"(kc.shr11));
+        : "r"(pv), "r"(kc.m1));
 #else
     const uint32_t bound = (d.range >> 11) * pv;
     bit = d.code >= bound ? 1u : 0u;
@@ -117,10 +117,10 @@ LZB_DEV uint32_t rc_step_tree(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np
                               uint32_t x1) {
     uint32_t child, t;
 #ifdef __CUDACC__
-    // range >> 11 as mul.hi by 2^21 and the multiply-adds with constant-bank multipliers keep this on the FMA pipe;
-    // compare + three selects are what is left for the ALU pipe
+    // the multiply-adds with constant-bank multipliers run on the FMA pipe; shift, compare and three selects are
+    // what is left for the ALU pipe (range >> 11 as mul.hi by 2^21 was measured slower: IMAD.HI is not full rate)
     asm("{\n\t.reg .pred p;\n\t.reg .u32 rs, bound, rb, kk, xx;\n\t"
-        "mul.hi.u32 rs, %2, %10;\n\t"
+        "shr.u32 rs, %2, 11;\n\t"
         "mul.lo.u32 bound, rs, %4;\n\t"
         "setp.ge.u32 p, %3, bound;\n\t"
         "sub.u32 rb, %2, bound;\n\t"
@@ -131,7 +131,7 @@ LZB_DEV uint32_t rc_step_tree(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np
         "mad.lo.u32 %0, %5, %8, xx;\n\t"
         "mad.lo.u32 %1, %4, %9, kk;\n\t}"
         : "=r"(child), "=r"(t), "+r"(d.range), "+r"(d.code)
-        : "r"(pv), "r"(node), "r"(x0), "r"(x1), "r"(kc.two), "r"(kc.m1), "r"(kc.shr11));
+        : "r"(pv), "r"(node), "r"(x0), "r"(x1), "r"(kc.two), "r"(kc.m1));
 #else
     const uint32_t bound = (d.range >> 11) * pv;
     const uint32_t bit = d.code >= bound ? 1u : 0u;
