@@ -32,15 +32,34 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-CONFIG_INDEX = 2
-STREAM_BYTES = 65536
-DICT_SIZE = 1 << 18
 L2_BYTES = 126 * 1000 * 1000
+
+# BASELINE.json configs that are raw-LZMA2 batches.  c2 is the benchmark line (configs[1], the
+# largest single-GPU configuration the metric is quoted on); c3 / c5 are informational (`--config`).
+CONFIGS = {
+    "c2": dict(index=2, stream_bytes=65536, dict_size=1 << 18, streams=4096, kind="mixed",
+               name="C2: {n} independent raw LZMA2 streams x 65536 B (lc3 lp0 pb2, dict 256 KiB, seeded mixed "
+                    "literal/match text, liblzma preset 6) per GPU"),
+    "c3": dict(index=3, stream_bytes=262144, dict_size=1 << 20, streams=8192, kind="mixed",
+               name="C3 shard: {n} independent raw LZMA2 streams x 262144 B (dict 1 MiB, 3 chunks each) per GPU"),
+    "c5": dict(index=5, stream_bytes=262144, dict_size=1 << 20, streams=8192, kind="rep0",
+               name="C5: {n} raw LZMA2 streams x 262144 B of all-overlapping rep0 matches (dist=1, len=273) per GPU"),
+    "c4": dict(index=4, stream_bytes=1 << 20, dict_size=1 << 20, streams=1024, kind="xz",
+               name="C4: {n} .xz files x 1 MiB (4 blocks of 256 KiB each, LZMA2 filter, CRC32 block check) per GPU, "
+                    "host API only (container walk on the host, K1 decode + K3 CRC on the GPU)"),
+}
+CFG = CONFIGS["c2"]
 
 
 def _one_stream(args):
     import corpus
-    seed, size, dict_size = args
+    seed, size, dict_size, kind = args
+    if kind == "xz":
+        plain = corpus.mixed_text(seed, size)
+        return corpus.xz_file(plain, block_size=1 << 18, check=corpus.CHECK_CRC32, dict_size=dict_size), plain
+    if kind == "rep0":
+        plain = bytes([seed & 0xFF]) * size
+        return corpus.rep0_stress_lzma2(size, byte=seed & 0xFF), plain
     plain = corpus.mixed_text(seed, size)
     return corpus.raw_lzma2(plain, dict_size=dict_size, preset=6), plain
 
@@ -49,7 +68,8 @@ def build_corpus(rank, n_streams, distinct, workers):
     """Seeds: config_index * 1_000_003 + stream_index (+ rank offset so ranks hold different data)."""
     import multiprocessing as mp
     distinct = min(distinct, n_streams)
-    jobs = [(CONFIG_INDEX * 1_000_003 + rank * 100_003 + i, STREAM_BYTES, DICT_SIZE) for i in range(distinct)]
+    jobs = [(CFG["index"] * 1_000_003 + rank * 100_003 + i, CFG["stream_bytes"], CFG["dict_size"], CFG["kind"])
+            for i in range(distinct)]
     if workers > 1:
         with mp.get_context("fork").Pool(workers) as pool:
             base = pool.map(_one_stream, jobs, chunksize=max(1, distinct // (workers * 4)))
@@ -107,8 +127,33 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def effective_cpus():
+    """Host threads this process can really use: min(os.cpu_count(), sched affinity, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    return n, quota
+
+
 def cpu_reference_run(comp, plain, steps, warmup, threads, sample_streams):
-    """The lzma-rs-equivalent CPU path (C oracle) on `threads` host threads over a bounded sample of the workload."""
+    """The lzma-rs-equivalent CPU path (C oracle) over a bounded sample of the workload, one stream per task.
+    `threads` = candidate thread counts: the fastest is reported (a container CPU quota can make fewer threads
+    than os.cpu_count() faster)."""
     import oracle_py
     from lzma_rs_b200 import _native
     k = min(sample_streams, len(comp))
@@ -117,17 +162,75 @@ def cpu_reference_run(comp, plain, steps, warmup, threads, sample_streams):
     out_off = np.zeros(k + 1, dtype=np.uint64)
     np.cumsum(sizes, out=out_off[1:])
     total = int(out_off[-1])
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        out, out_len, kinds, failed = oracle_py.decompress_batch(1, blob, in_off, out_off, threads)
-        dt = time.perf_counter() - t0
-        assert failed == 0
-        if it >= warmup:
-            times.append(dt)
+    best = None
+    for th in threads:
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            out, out_len, kinds, failed = oracle_py.decompress_batch(1, blob, in_off, out_off, th)
+            dt = time.perf_counter() - t0
+            assert failed == 0
+            if it >= warmup:
+                times.append(dt)
+        dt = float(np.mean(times))
+        if best is None or dt < best[0]:
+            best = (dt, th)
     assert out[int(out_off[0]):int(out_off[1])].tobytes() == plain[0]
-    dt = float(np.mean(times))
-    return total / dt / 1e9, dt, k, total
+    dt, th = best
+    return total / dt / 1e9, dt, k, total, th
+
+
+def cpu_thread_candidates(ncpu, quota):
+    c = {ncpu, max(1, ncpu // 2)}
+    if quota:
+        c |= {max(1, int(round(quota))), max(1, int(round(quota * 2)))}
+    c |= {x for x in (16, 32, 64) if x <= ncpu}
+    return sorted(c)
+
+
+def bench_xz(a, lib, ctx, comp, plain, workload, world, rank):
+    """Informational: BASELINE config 4 through the reference-facing host API (there is no device-resident XZ entry)."""
+    import torch
+    from lzma_rs_b200 import _native
+    n = len(comp)
+    blob, in_off = _native.pack_streams(comp)
+    sizes = np.array([len(p) for p in plain], dtype=np.uint64)
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum((sizes + np.uint64(15)) // np.uint64(16) * np.uint64(16), out=out_off[1:])
+    h_in = torch.from_numpy(blob).pin_memory()
+    h_out = torch.empty(int(out_off[-1]) + 16, dtype=torch.uint8).pin_memory()
+    out_len = np.zeros(n, dtype=np.uint64)
+    cons = np.zeros(n, dtype=np.uint64)
+    st = np.zeros(n, dtype=_native.STATUS_DTYPE)
+    opt = _native.make_options()
+
+    def step():
+        r = lib.lzb_decode_batch(ctx.handle, _native.FMT_XZ, C.byref(opt), h_in.data_ptr(), in_off.ctypes.data, n,
+                                 h_out.data_ptr(), out_off.ctypes.data, out_len.ctypes.data, cons.ctypes.data,
+                                 st.ctypes.data)
+        assert r == 0, (r, ctx.last_error())
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / a.steps
+    assert (st["code"] == 0).all()
+    hv = h_out.numpy()
+    for i in range(0, n, 37):
+        o = int(out_off[i])
+        assert hv[o:o + int(out_len[i])].tobytes() == plain[i]
+    total = int(sizes.sum())
+    print(json.dumps({"metric": "decompressed GB/s (.xz files, host API, informational)", "value": total / dt / 1e9,
+                      "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
+                      "higher_is_better": True, "data": "synthetic", "dtype": "u8/u16/u32 integer",
+                      "config": {"workload": workload, "compressed_bytes": int(in_off[-1]), "decompressed_bytes": total},
+                      "e2e": {"value": total / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(in_off[-1]),
+                              "d2h_bytes_per_step": total}}))
+    ctx.close()
 
 
 def main():
@@ -136,37 +239,46 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=4096)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="c2 = the benchmark line; others informational")
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (0 = the config's own count)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct streams to generate (0 = auto); the rest are tiled")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="streams of the workload the CPU baseline decodes")
     ap.add_argument("--no-verify", action="store_true")
     a = ap.parse_args()
     assert a.warmup >= 3 or a.impl == "reference", "timing rules: at least 3 warm-up steps"
+    global CFG
+    CFG = CONFIGS[a.config]
+    a.streams = a.streams or CFG["streams"]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ncpu = os.cpu_count() or 1
     workers = max(1, min(32, ncpu // max(1, world)))
-    distinct = a.distinct or (a.streams if ncpu >= 16 else 1024)
+    distinct = a.distinct or (min(a.streams, 4096 if CFG["kind"] == "mixed" and CFG["stream_bytes"] <= 65536 else 1024)
+                              if ncpu >= 16 else min(a.streams, 1024))
+    if CFG["kind"] == "rep0":
+        distinct = min(distinct, 256)
 
-    workload = (f"C2: {a.streams} independent raw LZMA2 streams x {STREAM_BYTES} B (lc3 lp0 pb2, dict 256 KiB, "
-                f"seeded mixed literal/match text, liblzma preset 6) per GPU")
+    workload = CFG["name"].format(n=a.streams)
 
     # ---------------------------------------------------------------- reference arm: CPU path only
     if a.impl == "reference":
         if rank != 0:
             return
         comp, plain = build_corpus(0, min(a.streams, max(a.cpu_sample, 64)), distinct, workers)
-        gbs, dt, k, total = cpu_reference_run(comp, plain, a.steps, a.warmup, ncpu, a.cpu_sample)
+        ncap, quota = effective_cpus()
+        gbs, dt, k, total, used = cpu_reference_run(comp, plain, a.steps, a.warmup, cpu_thread_candidates(ncap, quota),
+                                                    a.cpu_sample)
         line = {"impl": "reference", "metric": "decompressed GB/s (batch of independent LZMA2 streams)", "value": gbs,
                 "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16/u32 integer",
                 "data": "synthetic", "config": {"workload": workload, "sample": f"{k} streams of the workload per step"},
-                "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": ncpu, "kind": "port",
+                "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": used, "kind": "port",
                                  "sample": f"{k} of {a.streams} streams ({total} B out) per step, one stream per task, "
-                                           f"{ncpu} pthreads; C restatement of lzma-rs src/decode (reference is Rust, "
-                                           "no rustc in the image)"},
+                                           f"best of thread counts {cpu_thread_candidates(ncap, quota)} -> {used} pthreads "
+                                           f"(os.cpu_count {ncpu}, cgroup quota {quota}); C restatement of lzma-rs "
+                                           "src/decode (reference is Rust, no rustc in the image)"},
                 "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -184,6 +296,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _native.load()
     ctx = Context(local_rank)
+
+    if CFG["kind"] == "xz":
+        return bench_xz(a, lib, ctx, comp, plain, workload, world, rank)
 
     n = len(comp)
     blob, in_off = _native.pack_streams(comp)
@@ -291,12 +406,14 @@ def main():
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kernel_ms = float(np.mean(step_ms))  # this rank's average launch duration, CUDA events on the launch stream
         achieved = (in_bytes + out_bytes) / (kernel_ms * 1e-3) / 1e9
-        cpu_gbs, cpu_dt, cpu_k, cpu_total = cpu_reference_run(comp, plain, 2, 1, ncpu, a.cpu_sample)
+        ncap, quota = effective_cpus()
+        cpu_gbs, cpu_dt, cpu_k, cpu_total, cpu_used = cpu_reference_run(comp, plain, 2, 1, cpu_thread_candidates(ncap, quota),
+                                                                        a.cpu_sample)
         traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu capture
         tpath = os.path.join(ROOT, "profiles", "r01_k1_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("streams") == n:
+            if tj.get("streams") == n and a.config == "c2":
                 traffic = tj["dram_bytes_per_launch"]
         line = {
             "metric": "decompressed GB/s (batch of independent LZMA2 streams)", "value": value, "unit": "GB/s",
@@ -315,9 +432,10 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "lzb_decode_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": in_bytes + out_bytes, "kernel_ms": kernel_ms},
-            "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": ncpu, "kind": "port",
-                             "sample": f"{cpu_k} of {n} streams ({cpu_total} B out), one stream per task on {ncpu} "
-                                       "pthreads; C restatement of lzma-rs src/decode (oracle/)"},
+            "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_used, "kind": "port",
+                             "sample": f"{cpu_k} of {n} streams ({cpu_total} B out), one stream per task, best of thread "
+                                       f"counts {cpu_thread_candidates(ncap, quota)} -> {cpu_used} pthreads (os.cpu_count "
+                                       f"{ncpu}, cgroup quota {quota}); C restatement of lzma-rs src/decode (oracle/)"},
             "clocks": clocks,
         }
         print(json.dumps(line))
