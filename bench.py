@@ -180,6 +180,14 @@ def cpu_reference_run(comp, plain, steps, warmup, threads, sample_streams):
     return total / dt / 1e9, dt, k, total, th
 
 
+def effective_cores(threads_used, ncap, quota):
+    """Cores the CPU baseline really had: its threads, capped by the affinity mask and the cgroup CPU quota."""
+    c = min(threads_used, ncap)
+    if quota:
+        c = min(c, max(1, int(round(quota))))
+    return c
+
+
 def cpu_thread_candidates(ncpu, quota):
     c = {ncpu, max(1, ncpu // 2)}
     if quota:
@@ -274,7 +282,7 @@ def main():
                 "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16/u32 integer",
                 "data": "synthetic", "config": {"workload": workload, "sample": f"{k} streams of the workload per step"},
-                "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": used, "kind": "port",
+                "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": effective_cores(used, ncap, quota), "kind": "port",
                                  "sample": f"{k} of {a.streams} streams ({total} B out) per step, one stream per task, "
                                            f"best of thread counts {cpu_thread_candidates(ncap, quota)} -> {used} pthreads "
                                            f"(os.cpu_count {ncpu}, cgroup quota {quota}); C restatement of lzma-rs "
@@ -432,7 +440,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "lzb_decode_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": in_bytes + out_bytes, "kernel_ms": kernel_ms},
-            "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_used, "kind": "port",
+            "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": effective_cores(cpu_used, ncap, quota), "kind": "port",
                              "sample": f"{cpu_k} of {n} streams ({cpu_total} B out), one stream per task, best of thread "
                                        f"counts {cpu_thread_candidates(ncap, quota)} -> {cpu_used} pthreads (os.cpu_count "
                                        f"{ncpu}, cgroup quota {quota}); C restatement of lzma-rs src/decode (oracle/)"},

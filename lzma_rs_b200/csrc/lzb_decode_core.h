@@ -65,7 +65,7 @@ LZB_DEV void rd_seek(Dec& d, uint32_t p) {
 // normalize, rangecoder.rs:60-69: ONE conditional 8-bit shift after every decision.  Reads past
 // `lim` are detected by the caller as p > lim at the symbol boundary (UnexpectedEof, rangecoder.rs:64).
 LZB_DEV void rc_normalize(Dec& d) {
-    if (d.range < RC_TOP) {
+    if (__builtin_expect(d.range < RC_TOP, 0)) {  // ~1 decision in 9: keep the common path fall-through
         d.range <<= 8;
         d.code = __funnelshift_l(d.cur, d.code, 8);  // (code << 8) | next byte
         d.cur <<= 8;
