@@ -280,6 +280,22 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
         goto finish;         \
     } while (0)
 
+// Copies out[from, to) (device window) to the same offsets of the host mirror; from is a multiple of 4096 and both
+// bases are 16-byte aligned (checked by the caller), so the body is 512-byte warp stores over PCIe.
+LZB_DEV void mirror_to_host(const uint8_t* out, uint8_t* hout, uint32_t from, uint32_t to, int lane) {
+    LZB_SYNCWARP();  // the window bytes were stored by other lanes
+    uint32_t i = from + (uint32_t)lane * 16u;
+    for (; i + 16u <= to; i += 16u * LZB_LANES) {
+#ifdef __CUDACC__
+        *reinterpret_cast<uint4*>(hout + i) = *reinterpret_cast<const uint4*>(out + i);
+#else
+        for (int k = 0; k < 16; k++) hout[i + k] = out[i + k];
+#endif
+    }
+    const uint32_t tail = to - ((to - from) & 15u);  // < 16 trailing bytes
+    for (uint32_t j = tail + (uint32_t)lane; j < to; j += LZB_LANES) hout[j] = out[j];
+}
+
 // The literal table (lzma.rs:194, [1 << (lc+lp)][0x300]) is split by column:
 //   plain   columns 0x000..0x0FF  (every literal)                      -> `plain`,   row stride `plain_stride`
 //   matched columns 0x100..0x2FF  (first literal after a match only)   -> `matched`, row stride `matched_stride`,
@@ -289,7 +305,9 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
 // LIT_GLOBAL = true : .lzma streams with lc+lp > 4 (legal up to 12, lzma.rs:62-66): the whole table (up to 6 MiB) in
 //                     `gws` with the reference's layout (stride 0x300; matched = +0x100).
 // MainTab / PlainTab / MatchedTab: handle types of the small tables and the two literal parts.
-template <bool LIT_GLOBAL, class MainTab, class PlainTab, class MatchedTab>
+// MIRROR: completed 4 KiB pages of the output are copied to the caller's pinned host buffer (itp->host_out) while
+//         the stream is still decoding, so that the host API needs no device-to-host copy after the kernel.
+template <bool LIT_GLOBAL, bool MIRROR, class MainTab, class PlainTab, class MatchedTab>
 LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t* __restrict__ in_blob,
                                   uint8_t* out_blob, uint16_t* T, uint16_t* gws, const MainTab tab,
                                   const PlainTab plain, const MatchedTab matched, const LzbKC kc, uint32_t tab_lclp,
@@ -304,6 +322,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
     const uint32_t tab_u16 = LIT_GLOBAL ? (uint32_t)T_LIT : T_LIT + (0x100u << tab_lclp);
     const uint32_t plain_stride = LIT_GLOBAL ? 0x300u : 0x100u, matched_stride = LIT_GLOBAL ? 0x300u : 0x200u;
     uint32_t opos = 0, dict_base = 0;
+    uint32_t mirrored = 0;  // MIRROR: bytes already copied to the host buffer (multiple of 4096)
+    uint8_t* const hout = MIRROR ? reinterpret_cast<uint8_t*>(itp->host_out) : nullptr;
     uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
     uint32_t lc = 0, lp = 0, pb = 0;
     uint32_t prev_byte = 0, match_byte = 0;
@@ -449,6 +469,11 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
         // process_mode(Finish), lzma.rs:435-455, 496-511
         for (;;) {
+            if (MIRROR && opos - mirrored >= 4096u && hout) {
+                const uint32_t upto = opos & ~4095u;
+                mirror_to_host(out, hout, mirrored, upto, lane);
+                mirrored = upto;
+            }
             if (opos >= stop_at) break;
             if (!has_target && d.code == 0 && d.p == d.lim) break;  // is_finished_ok, rangecoder.rs:50-52
             const uint32_t len = opos - dict_base;
@@ -631,6 +656,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
 finish:
     LZB_SYNCWARP();
+    if (MIRROR && hout && opos > mirrored) mirror_to_host(out, hout, mirrored, opos, lane);
     if (lane == 0) {
         uint64_t sink = opos;
         if (err != LZB_OK) {

@@ -21,6 +21,9 @@ struct LzbCrcRange {
 extern "C" __global__ void lzb_decode_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
                                              LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long,
                                              const LzbKC);
+extern "C" __global__ void lzb_decode_mirror_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
+                                                    LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*,
+                                                    unsigned long long, const LzbKC);
 extern "C" __global__ void lzb_decode_biglit_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
                                                     LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*,
                                                     unsigned long long, const LzbKC);
@@ -64,7 +67,7 @@ struct lzb_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     int smem_optin = 0;
-    int smem_configured = -1, smem_configured_big = -1;
+    int smem_configured = -1, smem_configured_big = -1, smem_configured_mirror = -1;
     char err[320] = {0};
     std::mutex mu;
     DevBuf d_in, d_out, d_items, d_results, d_order, d_counter, d_scan, d_off, d_crc_ranges, d_crc_segmap, d_crc_part32,
@@ -147,7 +150,8 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
 // Enqueues counter resets + K1 launch(es) on `s`.  All pointers are device pointers; d_order holds order_small
 // followed by order_big; d_counter holds two counters.
 int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem* d_items, const uint32_t* d_order,
-                const uint8_t* d_in_base, uint8_t* d_out_base, LzbResult* d_results, unsigned int* d_counter) {
+                const uint8_t* d_in_base, uint8_t* d_out_base, LzbResult* d_results, unsigned int* d_counter,
+                bool mirror = false) {
     CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned int), s));
     const uint32_t ns = (uint32_t)p.order_small.size(), nb = (uint32_t)p.order_big.size();
     const LzbKC kc = LZB_KC_INIT;
@@ -161,9 +165,20 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         // per-warp global workspace for the matched-literal columns (L2-resident: 8 KiB per warp at lc+lp = 3)
         const uint64_t mstride = lzb_matched_u16(c.lclp);
         CUDA_TRY(ctx, ctx->d_matchws.ensure((size_t)c.grid * c.warps * mstride * 2));
-        lzb_decode_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, d_in_base, d_out_base, d_results,
-                                                             d_counter, c.lclp, c.warp_bytes,
-                                                             ctx->d_matchws.as<uint16_t>(), mstride, kc);
+        if (mirror) {  // host API with a pinned output buffer: finished pages are streamed to the host by the kernel
+            if (smem > ctx->smem_configured_mirror) {
+                CUDA_TRY(ctx, cudaFuncSetAttribute(lzb_decode_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   ctx->smem_optin));
+                ctx->smem_configured_mirror = ctx->smem_optin;
+            }
+            lzb_decode_mirror_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, d_in_base, d_out_base,
+                                                                        d_results, d_counter, c.lclp, c.warp_bytes,
+                                                                        ctx->d_matchws.as<uint16_t>(), mstride, kc);
+        } else {
+            lzb_decode_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, d_in_base, d_out_base, d_results,
+                                                                 d_counter, c.lclp, c.warp_bytes,
+                                                                 ctx->d_matchws.as<uint16_t>(), mstride, kc);
+        }
         CUDA_TRY(ctx, cudaGetLastError());
     }
     if (nb) {
@@ -194,8 +209,10 @@ int upload_order(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, DevBuf& d_or
 // The one shipped Executor: work items run on the GPU.
 class CudaExecutor : public lzb::Executor {
    public:
-    CudaExecutor(lzb_ctx* ctx, cudaStream_t s, const uint8_t* d_in_base, uint8_t* d_out_base)
-        : ctx_(ctx), s_(s), in_(d_in_base), out_(d_out_base) {}
+    // host_mirror: device-visible address of offset 0 of the caller's pinned host output (nullptr = none)
+    CudaExecutor(lzb_ctx* ctx, cudaStream_t s, const uint8_t* d_in_base, uint8_t* d_out_base, uint8_t* host_mirror = nullptr)
+        : ctx_(ctx), s_(s), in_(d_in_base), out_(d_out_base), hmirror_(host_mirror) {}
+    bool all_mirrored() const { return hmirror_ != nullptr && !unmirrored_; }
 
     int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, LzbResult* results) override {
         int rc = run(items, n, max_lclp, results);
@@ -262,11 +279,23 @@ class CudaExecutor : public lzb::Executor {
         CUDA_TRY(ctx, ctx->d_items.ensure(n * sizeof(LzbItem)));
         CUDA_TRY(ctx, ctx->d_results.ensure(n * sizeof(LzbResult)));
         CUDA_TRY(ctx, ctx->d_counter.ensure(64));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items.p, items, n * sizeof(LzbItem), cudaMemcpyHostToDevice, s_));
+        const LzbItem* up = items;
+        std::vector<LzbItem> patched;
+        if (hmirror_) {  // the mirror copies 16-byte vectors: both copies of a stream's region must be 16-byte aligned
+            patched.assign(items, items + n);
+            for (auto& it : patched) {
+                if ((it.out_off & 15) == 0 && it.kind != LZB_ITEM_PRESET)
+                    it.host_out = (uint64_t)(uintptr_t)(hmirror_ + it.out_off);
+                else if (it.kind != LZB_ITEM_PRESET)
+                    unmirrored_ = true;
+            }
+            up = patched.data();
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items.p, up, n * sizeof(LzbItem), cudaMemcpyHostToDevice, s_));
         int rc = upload_order(ctx, s_, plan, ctx->d_order);
         if (rc != LZB_RC_OK) return rc;
         rc = launch_plan(ctx, s_, plan, ctx->d_items.as<LzbItem>(), ctx->d_order.as<uint32_t>(), in_, out_,
-                         ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>());
+                         ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>(), hmirror_ != nullptr);
         if (rc != LZB_RC_OK) return rc;
         CUDA_TRY(ctx, cudaMemcpyAsync(results, ctx->d_results.p, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s_));
         CUDA_TRY(ctx, cudaStreamSynchronize(s_));
@@ -276,6 +305,8 @@ class CudaExecutor : public lzb::Executor {
     cudaStream_t s_;
     const uint8_t* in_;
     uint8_t* out_;
+    uint8_t* hmirror_;
+    bool unmirrored_ = false;
 };
 
 }  // namespace
@@ -344,11 +375,22 @@ extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, c
     uint8_t* d_out0 = ctx->d_out.as<uint8_t>() + (out_lo & 15);
     if (in_hi > in_lo)
         CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, ctx->stream));
-    CudaExecutor ex(ctx, ctx->stream, d_in0 - in_lo, d_out0 - out_lo);
+    // A pinned (page-locked, device-mapped) output buffer lets K1 stream finished pages straight to the host while it
+    // decodes; a pageable buffer gets one device-to-host copy after the kernel.
+    uint8_t* host_mirror = nullptr;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer &&
+            ((uintptr_t)attr.devicePointer & 15) == 0)
+            host_mirror = (uint8_t*)attr.devicePointer;
+        else
+            cudaGetLastError();  // clear the "not registered" error of a pageable pointer
+    }
+    CudaExecutor ex(ctx, ctx->stream, d_in0 - in_lo, d_out0 - out_lo, host_mirror);
     std::vector<lzb::StreamOut> outs(n);
     int rc = lzb::decode_batch(ex, fmt, opt, in, in_off, n, out_off, outs.data());  // planning reads the host copy
     if (rc != LZB_RC_OK) return rc;
-    if (out_hi > out_lo)
+    if (out_hi > out_lo && !ex.all_mirrored())
         CUDA_TRY(ctx, cudaMemcpyAsync(out + out_lo, d_out0, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (uint32_t i = 0; i < n; i++) {

@@ -19,6 +19,8 @@ struct LzbItem {
     uint32_t hdr_len;   // bytes of container header already consumed before in_off (LZMA: 13 or 5)
     int32_t preset_code;// LZB_ITEM_PRESET: status decided before the decode (header errors)
     uint64_t preset_a0;
+    uint64_t host_out;  // device-visible address of this stream's region in the caller's PINNED host output (0 = none):
+                        // the mirror variant of K1 streams finished 4 KiB pages there while it decodes
 };
 
 enum { LZB_ITEM_LZMA = 0, LZB_ITEM_LZMA2 = 1, LZB_ITEM_PRESET = 2 };

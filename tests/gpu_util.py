@@ -59,3 +59,27 @@ class DeviceBatch:
 
     def display(self, i):
         return "" if self.st[i]["code"] == 0 else _native.format_status(self.lib, self.st[i])
+
+
+def host_decode_pinned(ctx, fmt, streams, capacities, opts=None):
+    """lzb_decode_batch with PINNED host buffers (torch.pin_memory): K1's mirror variant streams finished output pages
+    to the host buffer itself, no device-to-host copy after the kernel.  Returns (list of bytes, out_len, consumed, st)."""
+    import torch
+    lib = _native.load()
+    blob, in_off = _native.pack_streams(streams)
+    n = len(streams)
+    caps = (np.asarray(capacities, dtype=np.uint64) + np.uint64(15)) // np.uint64(16) * np.uint64(16)
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(caps, out=out_off[1:])
+    h_in = torch.from_numpy(blob).pin_memory()
+    h_out = torch.full((int(out_off[-1]) + 16,), 0xEE, dtype=torch.uint8).pin_memory()
+    out_len = np.zeros(n, dtype=np.uint64)
+    consumed = np.zeros(n, dtype=np.uint64)
+    st = np.zeros(n, dtype=_native.STATUS_DTYPE)
+    opt = options_from(opts or {})._native()
+    rc = lib.lzb_decode_batch(ctx.handle, fmt, C.byref(opt), h_in.data_ptr(), in_off.ctypes.data, n, h_out.data_ptr(),
+                              out_off.ctypes.data, out_len.ctypes.data, consumed.ctypes.data, st.ctypes.data)
+    assert rc == 0, (rc, ctx.last_error())
+    hv = h_out.numpy()
+    outs = [hv[int(out_off[i]):int(out_off[i]) + int(out_len[i])].tobytes() for i in range(n)]
+    return outs, out_len, consumed, st

@@ -72,7 +72,7 @@ class HostEmulExecutor : public lzb::Executor {
         const TabPtr tab = {T};
         const TabPtr plain = {BIG ? G : T + T_LIT};
         const TabPtr matched = {BIG ? G + 0x100 : G};
-        decode_item<BIG>(it, in_, out_, T, G, tab, plain, matched, kc, lclp, res, 0);
+        decode_item<BIG, false>(it, in_, out_, T, G, tab, plain, matched, kc, lclp, res, 0);
     }
     const uint8_t* in_;
     uint8_t* out_;

@@ -185,3 +185,29 @@ def test_cpp_host_mirror(ctx, golden, tmp_path):
             assert r.returncode == 3 and r.stderr == v["error"], (name, r.stderr)
         else:
             assert r.returncode == 0, (name, r.stderr)
+
+
+def test_host_api_pinned_output_mirror(ctx):
+    """Pinned host output: the mirror variant of K1 writes finished 4 KiB pages to the host while decoding."""
+    import gpu_util
+    sizes = [0, 1, 15, 16, 17, 4095, 4096, 4097, 8192, 65536, 100_001, 300_000, 1 << 20]
+    plains = [corpus.mixed_text(900 + i, s) for i, s in enumerate(sizes)]
+    comp = [corpus.raw_lzma2(p, dict_size=1 << 20) for p in plains]
+    outs, out_len, consumed, st = gpu_util.host_decode_pinned(ctx, 1, comp, [len(p) for p in plains])
+    assert (st["code"] == 0).all()
+    for o, p, c, k in zip(outs, plains, comp, consumed):
+        assert o == p and int(k) == len(c)
+    # .lzma with errors (partial output = whole dict-size slabs) and .xz files through the same pinned path
+    enc = corpus.LzmaEncoder(3, 0, 2)
+    for i in range(10_000):
+        enc.literal(i & 0xFF)
+    enc.match(4, 9_000)  # beyond the 4 KiB dictionary
+    enc.end_marker()
+    bad = corpus.lzma_header(3, 0, 2, 4096) + enc.finish()
+    ref = oracle.lzma_decompress(bad)
+    outs, out_len, consumed, st = gpu_util.host_decode_pinned(ctx, 0, [bad, corpus.lzma_alone(plains[9])], [20_000, 70_000])
+    assert outs[0] == ref.out and len(ref.out) == 8192 and st[0]["code"] != 0
+    assert outs[1] == plains[9] and st[1]["code"] == 0
+    files = [corpus.xz_file(plains[11], block_size=1 << 16, check=corpus.CHECK_CRC64), corpus.xz_file(plains[12], block_size=100_000)]
+    outs, out_len, consumed, st = gpu_util.host_decode_pinned(ctx, 2, files, [len(plains[11]), len(plains[12])])
+    assert (st["code"] == 0).all() and outs[0] == plains[11] and outs[1] == plains[12]
