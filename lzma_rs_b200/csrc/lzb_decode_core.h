@@ -280,7 +280,7 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
         goto finish;         \
     } while (0)
 
-// Copies out[from, to) (device window) to the same offsets of the host mirror; from is a multiple of 4096 and both
+// Copies out[from, to) (device window) to the same offsets of the host mirror; `from` is a multiple of 16 and both
 // bases are 16-byte aligned (checked by the caller), so the body is 512-byte warp stores over PCIe.
 LZB_DEV void mirror_to_host(const uint8_t* out, uint8_t* hout, uint32_t from, uint32_t to, int lane) {
     LZB_SYNCWARP();  // the window bytes were stored by other lanes
@@ -322,7 +322,10 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
     const uint32_t tab_u16 = LIT_GLOBAL ? (uint32_t)T_LIT : T_LIT + (0x100u << tab_lclp);
     const uint32_t plain_stride = LIT_GLOBAL ? 0x300u : 0x100u, matched_stride = LIT_GLOBAL ? 0x300u : 0x200u;
     uint32_t opos = 0, dict_base = 0;
-    uint32_t mirrored = 0;  // MIRROR: bytes already copied to the host buffer (multiple of 4096)
+    uint32_t mirrored = 0;  // MIRROR: bytes already copied to the host buffer (multiple of 16)
+    // first flush point staggered per stream: equal streams started together would otherwise all flush at the same
+    // instant and serialise on the PCIe link (measured: +4.8 ms per 256 MiB, exactly one bulk copy)
+    uint32_t mirror_next = 4096u + (uint32_t)((itp->out_off >> 4) * 2654435761ull >> 20 & 0xFF0u);
     uint8_t* const hout = MIRROR ? reinterpret_cast<uint8_t*>(itp->host_out) : nullptr;
     uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
     uint32_t lc = 0, lp = 0, pb = 0;
@@ -469,10 +472,11 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
         // process_mode(Finish), lzma.rs:435-455, 496-511
         for (;;) {
-            if (MIRROR && opos - mirrored >= 4096u && hout) {
-                const uint32_t upto = opos & ~4095u;
+            if (MIRROR && opos >= mirror_next && hout) {
+                const uint32_t upto = opos & ~15u;
                 mirror_to_host(out, hout, mirrored, upto, lane);
                 mirrored = upto;
+                mirror_next = upto + 4096u;
             }
             if (opos >= stop_at) break;
             if (!has_target && d.code == 0 && d.p == d.lim) break;  // is_finished_ok, rangecoder.rs:50-52

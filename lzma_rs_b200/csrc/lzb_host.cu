@@ -380,7 +380,8 @@ extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, c
     uint8_t* host_mirror = nullptr;
     {
         cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer &&
+        if (!getenv("LZB_NO_MIRROR") && cudaPointerGetAttributes(&attr, out) == cudaSuccess &&
+            attr.type == cudaMemoryTypeHost && attr.devicePointer &&
             ((uintptr_t)attr.devicePointer & 15) == 0)
             host_mirror = (uint8_t*)attr.devicePointer;
         else
