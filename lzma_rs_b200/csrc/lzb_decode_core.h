@@ -13,7 +13,7 @@
 #ifdef __CUDACC__
 #define LZB_LANES 32
 #define LZB_DEV __device__ __forceinline__
-#define LZB_DEV_NOINLINE __device__ __noinline__
+#define LZB_DEV_NOINLINE __device__ __forceinline__
 #define LZB_MEM __device__ __forceinline__
 #define LZB_SYNCWARP() __syncwarp()
 #define LZB_LDG(p) __ldg(p)
@@ -284,16 +284,19 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
 // bases are 16-byte aligned (checked by the caller), so the body is 512-byte warp stores over PCIe.
 LZB_DEV void mirror_to_host(const uint8_t* out, uint8_t* hout, uint32_t from, uint32_t to, int lane) {
     LZB_SYNCWARP();  // the window bytes were stored by other lanes
-    uint32_t i = from + (uint32_t)lane * 16u;
-    for (; i + 16u <= to; i += 16u * LZB_LANES) {
+    // warp-uniform trip counts with predicated bodies: no lane-dependent loop exits inside the symbol loop
+    const uint32_t to16 = from + ((to - from) & ~15u);
+    for (uint32_t base = from; base < to16; base += 16u * LZB_LANES) {
+        const uint32_t i = base + (uint32_t)lane * 16u;
+        if (i < to16) {
 #ifdef __CUDACC__
-        *reinterpret_cast<uint4*>(hout + i) = *reinterpret_cast<const uint4*>(out + i);
+            *reinterpret_cast<uint4*>(hout + i) = *reinterpret_cast<const uint4*>(out + i);
 #else
-        for (int k = 0; k < 16; k++) hout[i + k] = out[i + k];
+            for (int k = 0; k < 16; k++) hout[i + k] = out[i + k];
 #endif
+        }
     }
-    const uint32_t tail = to - ((to - from) & 15u);  // < 16 trailing bytes
-    for (uint32_t j = tail + (uint32_t)lane; j < to; j += LZB_LANES) hout[j] = out[j];
+    if (to16 + (uint32_t)lane < to) hout[to16 + lane] = out[to16 + lane];  // < 16 trailing bytes
 }
 
 // The literal table (lzma.rs:194, [1 << (lc+lp)][0x300]) is split by column:
