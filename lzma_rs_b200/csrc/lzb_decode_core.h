@@ -205,16 +205,29 @@ LZB_DEV uint32_t rc_bit(Dec& d, const LzbKC& kc, const Tab& t, uint32_t idx) {
     return bit;
 }
 
-// get(count), rangecoder.rs:72-90
+// get(count), rangecoder.rs:72-90.  From a normalised range (>= 2^24, most significant bit h in 24..31) the first
+// h - 24 halvings cannot drop below 2^24 and the next one always does, so the bits are taken in groups of up to
+// h - 23 halvings with the per-bit normalisation test replaced by one test per group (same arithmetic, same order).
 LZB_DEV uint32_t rc_direct(Dec& d, uint32_t count) {
     uint32_t r = 0;
+    while (count) {
+#ifdef __CUDACC__
+        const uint32_t h = 31u - (uint32_t)__clz((int)d.range);
+#else
+        uint32_t h = 31;
+        while (!(d.range >> h)) h--;
+#endif
+        uint32_t j = h - 23u;
+        if (j > count) j = count;
+        count -= j;
 #pragma unroll 1
-    for (uint32_t i = 0; i < count; i++) {
-        d.range >>= 1;
-        const bool b = d.code >= d.range;
-        if (b) d.code -= d.range;
+        for (; j; j--) {
+            d.range >>= 1;
+            const bool b = d.code >= d.range;
+            if (b) d.code -= d.range;
+            r = r + r + (b ? 1u : 0u);
+        }
         rc_normalize(d);
-        r = (r << 1) | (b ? 1u : 0u);
     }
     return r;
 }
@@ -279,6 +292,62 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
         ea1 = (uint64_t)(y); \
         goto finish;         \
     } while (0)
+
+// Warp copy of n bytes src -> dst (arbitrary, independent alignments; regions do not overlap): a few head bytes
+// bring dst to a 4-byte boundary, the body stores aligned 32-bit words assembled from two aligned source words with
+// a funnel shift (128 B per warp instruction instead of 32), the tail goes byte-wise.  SRC_CONST: the source is the
+// read-only input blob (ld.global.nc).
+template <bool SRC_CONST>
+LZB_DEV void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+#ifndef __CUDACC__
+    (void)lane;
+    for (uint32_t k = 0; k < n; k++) dst[k] = src[k];  // 1-lane emulation: plain copy
+    return;
+#endif
+    uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
+    if (head > n) head = n;
+    if ((uint32_t)lane < head) dst[lane] = SRC_CONST ? LZB_LDG(src + lane) : src[lane];
+    const uint32_t words = (n - head) >> 2;
+#ifdef __CUDACC__
+    const uint8_t* s0 = src + head;
+    const uint32_t sh = ((uint32_t)(uintptr_t)s0 & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - ((uintptr_t)s0 & 3u));
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+    for (uint32_t k = lane; k < words; k += LZB_LANES) {
+        const uint32_t lo = SRC_CONST ? __ldg(sw + k) : sw[k];
+        // the second word is only dereferenced when the source is misaligned (it may lie past the last source byte)
+        const uint32_t hi = sh ? (SRC_CONST ? __ldg(sw + k + 1) : sw[k + 1]) : 0u;
+        dw[k] = __funnelshift_r(lo, hi, sh);
+    }
+#else
+    for (uint32_t k = 0; k < words * 4; k++) dst[head + k] = src[head + k];
+#endif
+    const uint32_t done = head + words * 4u;
+    if (done + (uint32_t)lane < n) dst[done + lane] = SRC_CONST ? LZB_LDG(src + done + lane) : src[done + lane];
+}
+
+// Warp fill of n bytes with one byte value (a dist == 1 match: the run-length case, BASELINE config 5).
+LZB_DEV void warp_fill(uint8_t* dst, uint32_t byte, uint32_t n, int lane) {
+#ifndef __CUDACC__
+    (void)lane;
+    for (uint32_t k = 0; k < n; k++) dst[k] = (uint8_t)byte;
+    return;
+#endif
+    uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
+    if (head > n) head = n;
+    if ((uint32_t)lane < head) dst[lane] = (uint8_t)byte;
+    const uint32_t words = (n - head) >> 2;
+    const uint32_t splat = byte * 0x01010101u;
+#ifdef __CUDACC__
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+    for (uint32_t k = lane; k < words; k += LZB_LANES) dw[k] = splat;
+#else
+    (void)splat;
+    for (uint32_t k = 0; k < words * 4; k++) dst[head + k] = (uint8_t)byte;
+#endif
+    const uint32_t done = head + words * 4u;
+    if (done + (uint32_t)lane < n) dst[done + lane] = (uint8_t)byte;
+}
 
 // Copies out[from, to) (device window) to the same offsets of the host mirror; `from` is a multiple of 16 and both
 // bases are 16-byte aligned (checked by the caller), so the body is 512-byte warp stores over PCIe.
@@ -395,20 +464,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                 }
                 if (stream_lim - d.p < n) FAIL(LZB_E_L2_STORED_EOF, n, 0);
                 if (cap - opos < n) FAIL(LZB_E_CAPACITY, (uint64_t)opos + n, 0);
-                {
-                    const uint8_t* s = inb + d.p;
-                    uint8_t* t = out + opos;
-                    uint32_t i = lane;
-                    for (; i + 3 * LZB_LANES < n; i += 4 * LZB_LANES) {
-                        uint8_t v0 = LZB_LDG(s + i), v1 = LZB_LDG(s + i + LZB_LANES), v2 = LZB_LDG(s + i + 2 * LZB_LANES),
-                                v3 = LZB_LDG(s + i + 3 * LZB_LANES);
-                        t[i] = v0;
-                        t[i + LZB_LANES] = v1;
-                        t[i + 2 * LZB_LANES] = v2;
-                        t[i + 3 * LZB_LANES] = v3;
-                    }
-                    for (; i < n; i += LZB_LANES) t[i] = LZB_LDG(s + i);
-                }
+                warp_copy<true>(out + opos, inb + d.p, n, lane);
                 opos += n;
                 d.p += n;
                 prev_byte = inb[d.p - 1];
@@ -545,7 +601,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                 if (lane == 0) out[opos] = (uint8_t)prev_byte;
                 opos += 1;
                 // state after a literal (lzma.rs:299-305): 0,0,0,0,1,2,3,4,5,6,4,5 as packed nibbles
-                state = (uint32_t)(0x546543210000ull >> (state * 4)) & 0xFu;
+                state = ((state < 8 ? 0x43210000u : 0x5465u) >> ((state & 7u) * 4u)) & 7u;
                 mb_valid = false;
                 continue;
             }
@@ -641,13 +697,16 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                 if (dist >= mlen) {
                     for (uint32_t i = lane; i < mlen; i += LZB_LANES) dst[i] = src[i];
                     if (dist == mlen) i_next = 0;
+                    prev_byte = src[i_last];   // last byte written      (uniform load)
+                    match_byte = src[i_next];  // out[new_opos - dist]: the match byte of a following literal
+                } else if (dist == 1) {  // run of one byte: word-wide fill
+                    prev_byte = match_byte = src[0];
+                    warp_fill(dst, prev_byte, mlen, lane);
                 } else {  // overlapping: the window replicates with period dist
                     for (uint32_t i = lane; i < mlen; i += LZB_LANES) dst[i] = src[i % dist];
-                    i_last %= dist;
-                    i_next %= dist;
+                    prev_byte = src[i_last % dist];
+                    match_byte = src[i_next % dist];
                 }
-                prev_byte = src[i_last];   // last byte written      (uniform load)
-                match_byte = src[i_next];  // out[new_opos - dist]: the match byte of a following literal
                 mb_valid = true;
                 opos += mlen;
             }
