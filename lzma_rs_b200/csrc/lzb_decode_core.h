@@ -205,29 +205,17 @@ LZB_DEV uint32_t rc_bit(Dec& d, const LzbKC& kc, const Tab& t, uint32_t idx) {
     return bit;
 }
 
-// get(count), rangecoder.rs:72-90.  From a normalised range (>= 2^24, most significant bit h in 24..31) the first
-// h - 24 halvings cannot drop below 2^24 and the next one always does, so the bits are taken in groups of up to
-// h - 23 halvings with the per-bit normalisation test replaced by one test per group (same arithmetic, same order).
+// get(count), rangecoder.rs:72-90.  (Taking the bits in normalisation-free groups of 31 - clz(range) - 23 halvings
+// was tried: same result, no gain -- the loop is not where the time goes.)
 LZB_DEV uint32_t rc_direct(Dec& d, uint32_t count) {
     uint32_t r = 0;
-    while (count) {
-#ifdef __CUDACC__
-        const uint32_t h = 31u - (uint32_t)__clz((int)d.range);
-#else
-        uint32_t h = 31;
-        while (!(d.range >> h)) h--;
-#endif
-        uint32_t j = h - 23u;
-        if (j > count) j = count;
-        count -= j;
 #pragma unroll 1
-        for (; j; j--) {
-            d.range >>= 1;
-            const bool b = d.code >= d.range;
-            if (b) d.code -= d.range;
-            r = r + r + (b ? 1u : 0u);
-        }
+    for (uint32_t i = 0; i < count; i++) {
+        d.range >>= 1;
+        const bool b = d.code >= d.range;
+        if (b) d.code -= d.range;
         rc_normalize(d);
+        r = (r << 1) | (b ? 1u : 0u);
     }
     return r;
 }
@@ -700,7 +688,10 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     prev_byte = src[i_last];   // last byte written      (uniform load)
                     match_byte = src[i_next];  // out[new_opos - dist]: the match byte of a following literal
                 } else if (dist == 1) {  // run of one byte: word-wide fill
-                    prev_byte = match_byte = src[0];
+                    // (same index expressions as the general overlapping case: written as src[0] the compiler folds
+                    // the load into the lane-dependent fill and loses the warp-uniformity of prev_byte downstream)
+                    prev_byte = src[i_last % dist];
+                    match_byte = src[i_next % dist];
                     warp_fill(dst, prev_byte, mlen, lane);
                 } else {  // overlapping: the window replicates with period dist
                     for (uint32_t i = lane; i < mlen; i += LZB_LANES) dst[i] = src[i % dist];
