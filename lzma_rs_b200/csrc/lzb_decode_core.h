@@ -32,6 +32,7 @@ static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { r
 #endif
 
 #define RC_TOP (1u << 24)
+#define LZB_UNLIKELY(x) __builtin_expect(!!(x), 0)
 
 // Keeps a loop-invariant value in a register instead of letting the compiler rematerialise it every symbol.
 #ifdef __CUDACC__
@@ -70,7 +71,7 @@ LZB_DEV void rc_normalize(Dec& d) {
         d.code = __funnelshift_l(d.cur, d.code, 8);  // (code << 8) | next byte
         d.cur <<= 8;
         d.p += 1;
-        if ((d.p & 3u) == 0) {
+        if (LZB_UNLIKELY((d.p & 3u) == 0)) {
             d.cur = __byte_perm(d.nxt, 0, 0x0123);
             d.nxt = ld_word(d, (d.p >> 2) + 1);
         }
@@ -367,7 +368,10 @@ LZB_DEV void mirror_to_host(const uint8_t* out, uint8_t* hout, uint32_t from, ui
 // MainTab / PlainTab / MatchedTab: handle types of the small tables and the two literal parts.
 // MIRROR: completed 4 KiB pages of the output are copied to the caller's pinned host buffer (itp->host_out) while
 //         the stream is still decoding, so that the host API needs no device-to-host copy after the kernel.
-template <bool LIT_GLOBAL, bool MIRROR, class MainTab, class PlainTab, class MatchedTab>
+// WIDE  : word-wide stored-chunk copies and run fills.  Kept out of the default instantiation because K1 sits at the
+//         edge of the instruction cache: every extra path costs the common case ~1 % even when it never executes
+//         (measured); the host selects the WIDE kernels for batches with stored chunks or extreme expansion ratios.
+template <bool LIT_GLOBAL, bool MIRROR, bool WIDE, class MainTab, class PlainTab, class MatchedTab>
 LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t* __restrict__ in_blob,
                                   uint8_t* out_blob, uint16_t* T, uint16_t* gws, const MainTab tab,
                                   const PlainTab plain, const MatchedTab matched, const LzbKC kc, uint32_t tab_lclp,
@@ -427,7 +431,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
         if (itp->memlimit < (uint64_t)dict_size) mem_stop = (uint32_t)itp->memlimit;  // lzbuffer.rs:209-217
         has_target = itp->unpacked != LZB_UNKNOWN_SIZE;
         target = (uint32_t)LZB_MIN(itp->unpacked, (uint64_t)0xFFFFFFFFu);  // sizes beyond the cap are never reached
-        if (lc + lp > tab_lclp) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
+        if (LZB_UNLIKELY(lc + lp > tab_lclp)) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
     }
     fill_tables(T, tab_u16, lane);
     // global part: the whole literal table (LIT_GLOBAL; .lzma props never change mid-stream) or the matched columns
@@ -435,36 +439,40 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
     for (;;) {  // LZMA2 chunk loop (lzma2.rs:59-78); a .lzma stream is a single pass
         if (is_lzma1) {
-            if (stream_lim - d.p < 5) FAIL(LZB_E_LZMA_STREAM_TOO_SHORT, 0, 0);  // lzma.rs:643-644
+            if (LZB_UNLIKELY(stream_lim - d.p < 5)) FAIL(LZB_E_LZMA_STREAM_TOO_SHORT, 0, 0);  // lzma.rs:643-644
         } else {
-            if (d.p >= stream_lim) FAIL(LZB_E_L2_STATUS_EOF, 0, 0);
+            if (LZB_UNLIKELY(d.p >= stream_lim)) FAIL(LZB_E_L2_STATUS_EOF, 0, 0);
             uint32_t status = inb[d.p];
             d.p += 1;
             chunks++;
             if (status == 0) break;
             if (status == 1 || status == 2) {  // parse_uncompressed, lzma2.rs:195-229
-                if (stream_lim - d.p < 2) FAIL(LZB_E_L2_UNPACKED_EOF, 0, 0);
+                if (LZB_UNLIKELY(stream_lim - d.p < 2)) FAIL(LZB_E_L2_UNPACKED_EOF, 0, 0);
                 uint32_t n = (((uint32_t)inb[d.p] << 8) | inb[d.p + 1]) + 1;
                 d.p += 2;
                 if (status == 1) {  // accum.reset(): everything so far goes to the sink, window restarts
                     dict_base = opos;
                     prev_byte = 0;
                 }
-                if (stream_lim - d.p < n) FAIL(LZB_E_L2_STORED_EOF, n, 0);
-                if (cap - opos < n) FAIL(LZB_E_CAPACITY, (uint64_t)opos + n, 0);
-                warp_copy<true>(out + opos, inb + d.p, n, lane);
+                if (LZB_UNLIKELY(stream_lim - d.p < n)) FAIL(LZB_E_L2_STORED_EOF, n, 0);
+                if (LZB_UNLIKELY(cap - opos < n)) FAIL(LZB_E_CAPACITY, (uint64_t)opos + n, 0);
+                if (WIDE) {
+                    warp_copy<true>(out + opos, inb + d.p, n, lane);
+                } else {
+                    for (uint32_t i = lane; i < n; i += LZB_LANES) out[opos + i] = LZB_LDG(inb + d.p + i);
+                }
                 opos += n;
                 d.p += n;
                 prev_byte = inb[d.p - 1];
                 mb_valid = false;
                 continue;
             }
-            if (status < 0x80) FAIL(LZB_E_L2_INVALID_STATUS, status, 0);  // lzma2.rs:94-99
+            if (LZB_UNLIKELY(status < 0x80)) FAIL(LZB_E_L2_INVALID_STATUS, status, 0);  // lzma2.rs:94-99
             const uint32_t mode = (status >> 5) & 3u;
-            if (stream_lim - d.p < 2) FAIL(LZB_E_L2_UNPACKED_EOF, 0, 0);
+            if (LZB_UNLIKELY(stream_lim - d.p < 2)) FAIL(LZB_E_L2_UNPACKED_EOF, 0, 0);
             const uint32_t unpacked = ((((status & 0x1Fu) << 16) | ((uint32_t)inb[d.p] << 8) | inb[d.p + 1])) + 1;
             d.p += 2;
-            if (stream_lim - d.p < 2) FAIL(LZB_E_L2_PACKED_EOF, 0, 0);
+            if (LZB_UNLIKELY(stream_lim - d.p < 2)) FAIL(LZB_E_L2_PACKED_EOF, 0, 0);
             const uint32_t packed = (((uint32_t)inb[d.p] << 8) | inb[d.p + 1]) + 1;
             d.p += 2;
             if (mode == 3) {  // reset_dict
@@ -473,17 +481,17 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
             }
             if (mode >= 1) {      // reset_state
                 if (mode >= 2) {  // reset_props
-                    if (d.p >= stream_lim) FAIL(LZB_E_L2_PROPS_EOF, 0, 0);
+                    if (LZB_UNLIKELY(d.p >= stream_lim)) FAIL(LZB_E_L2_PROPS_EOF, 0, 0);
                     uint32_t props = inb[d.p];
                     d.p += 1;
-                    if (props >= 225) FAIL(LZB_E_L2_PROPS_RANGE, props, 0);
+                    if (LZB_UNLIKELY(props >= 225)) FAIL(LZB_E_L2_PROPS_RANGE, props, 0);
                     lc = props % 9;
                     props /= 9;
                     lp = props % 5;
                     pb = props / 5;
-                    if (lc + lp > 4) FAIL(LZB_E_L2_PROPS_LCLP, lc, lp);
+                    if (LZB_UNLIKELY(lc + lp > 4)) FAIL(LZB_E_L2_PROPS_LCLP, lc, lp);
                 }
-                if (lc + lp > tab_lclp) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
+                if (LZB_UNLIKELY(lc + lp > tab_lclp)) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
                 if (!tables_fresh) {  // reset_state, lzma.rs:216-249
                     fill_tables(T, tab_u16, lane);
                     fill_tables(gws, 0x200u << tab_lclp, lane);
@@ -494,7 +502,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
             has_target = true;
             target = (opos - dict_base) + unpacked;  // set_unpacked_size(unpacked + accum.len()), lzma2.rs:186-187
             d.lim = LZB_MIN(d.p + packed, stream_lim);   // input.take(packed_size), lzma2.rs:189
-            if (d.lim - d.p < 5) FAIL(LZB_E_L2_INPUT_TOO_SHORT, 0, 0);
+            if (LZB_UNLIKELY(d.lim - d.p < 5)) FAIL(LZB_E_L2_INPUT_TOO_SHORT, 0, 0);
             mb_valid = false;
         }
         tables_fresh = false;
@@ -519,7 +527,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
         // process_mode(Finish), lzma.rs:435-455, 496-511
         for (;;) {
-            if (MIRROR && opos >= mirror_next && hout) {
+            if (MIRROR && LZB_UNLIKELY(opos >= mirror_next) && hout) {
                 const uint32_t upto = opos & ~15u;
                 mirror_to_host(out, hout, mirrored, upto, lane);
                 mirrored = upto;
@@ -547,10 +555,10 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                 // ---- literal, lzma.rs:287-307 + decode_literal 526-561
                 uint32_t sym = 1;
                 if (state >= 7) {
-                    if (!mb_valid) {  // last_n(rep[0] + 1), lzbuffer.rs:98-108 / 240-256
-                        if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
-                        if (rep0 >= dict_size) FAIL(LZB_E_MATCH_DIST_DICT, (uint64_t)rep0 + 1, dict_size);
-                        if (rep0 >= len) FAIL(LZB_E_MATCH_DIST_OUT, (uint64_t)rep0 + 1, len);
+                    if (LZB_UNLIKELY(!mb_valid)) {  // last_n(rep[0] + 1), lzbuffer.rs:98-108 / 240-256
+                        if (LZB_UNLIKELY(d.p > d.lim)) FAIL(LZB_E_IO_EOF, 0, 0);
+                        if (LZB_UNLIKELY(rep0 >= dict_size)) FAIL(LZB_E_MATCH_DIST_DICT, (uint64_t)rep0 + 1, dict_size);
+                        if (LZB_UNLIKELY(rep0 >= len)) FAIL(LZB_E_MATCH_DIST_OUT, (uint64_t)rep0 + 1, len);
                         LZB_SYNCWARP();
                         match_byte = out[opos - rep0 - 1];
                     }
@@ -580,16 +588,16 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     }
                     sym = probs.node_index(kc, node);
                 }
-                if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
-                if (opos >= lit_limit) {
-                    if (opos >= mem_stop) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
+                if (LZB_UNLIKELY(d.p > d.lim)) FAIL(LZB_E_IO_EOF, 0, 0);
+                if (LZB_UNLIKELY(opos >= lit_limit)) {
+                    if (LZB_UNLIKELY(opos >= mem_stop)) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
                     FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);
                 }
                 prev_byte = sym & 0xFFu;
                 if (lane == 0) out[opos] = (uint8_t)prev_byte;
                 opos += 1;
                 // state after a literal (lzma.rs:299-305): 0,0,0,0,1,2,3,4,5,6,4,5 as packed nibbles
-                state = ((state < 8 ? 0x43210000u : 0x5465u) >> ((state & 7u) * 4u)) & 7u;
+                state = (uint32_t)(0x546543210000ull >> (state * 4)) & 0xFu;
                 mb_valid = false;
                 continue;
             }
@@ -658,7 +666,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                             }
                             rep0 = r;
                         }
-                        if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
+                        if (LZB_UNLIKELY(d.p > d.lim)) FAIL(LZB_E_IO_EOF, 0, 0);
                         if (rep0 == 0xFFFFFFFFu) {  // end-of-stream marker, lzma.rs:373-381
                             if (d.code == 0 && d.p == d.lim) goto chunk_done;  // Finished: fall to the size check
                             FAIL(LZB_E_EOS_MORE_BYTES, 0, 0);
@@ -666,17 +674,17 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     }
                     mlen = l + 2;
                 }
-                if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
+                if (LZB_UNLIKELY(d.p > d.lim)) FAIL(LZB_E_IO_EOF, 0, 0);
             }
 
             // ---- append_lz(mlen, rep0 + 1), lzbuffer.rs:125-143 / 272-297
             {
-                if (rep0 >= dict_size) FAIL(LZB_E_LZ_DIST_DICT, (uint64_t)rep0 + 1, dict_size);
-                if (rep0 >= len) FAIL(LZB_E_LZ_DIST_OUT, (uint64_t)rep0 + 1, len);
-                if (mem_stop - opos < mlen && mem_stop != 0xFFFFFFFFu) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
+                if (LZB_UNLIKELY(rep0 >= dict_size)) FAIL(LZB_E_LZ_DIST_DICT, (uint64_t)rep0 + 1, dict_size);
+                if (LZB_UNLIKELY(rep0 >= len)) FAIL(LZB_E_LZ_DIST_OUT, (uint64_t)rep0 + 1, len);
+                if (LZB_UNLIKELY(mem_stop - opos < mlen && mem_stop != 0xFFFFFFFFu)) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
                 if (!is_lzma1 && len + mlen > target)  // the window is never flushed past this point
                     FAIL(LZB_E_UNPACKED_MISMATCH, target, (uint64_t)len + mlen);
-                if (cap - opos < mlen) FAIL(LZB_E_CAPACITY, (uint64_t)opos + mlen, 0);
+                if (LZB_UNLIKELY(cap - opos < mlen)) FAIL(LZB_E_CAPACITY, (uint64_t)opos + mlen, 0);
                 const uint32_t dist = rep0 + 1;
                 const uint8_t* src = out + opos - dist;
                 uint8_t* dst = out + opos;
@@ -687,16 +695,16 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     if (dist == mlen) i_next = 0;
                     prev_byte = src[i_last];   // last byte written      (uniform load)
                     match_byte = src[i_next];  // out[new_opos - dist]: the match byte of a following literal
-                } else if (dist == 1) {  // run of one byte: word-wide fill
-                    // (same index expressions as the general overlapping case: written as src[0] the compiler folds
-                    // the load into the lane-dependent fill and loses the warp-uniformity of prev_byte downstream)
-                    prev_byte = src[i_last % dist];
-                    match_byte = src[i_next % dist];
-                    warp_fill(dst, prev_byte, mlen, lane);
                 } else {  // overlapping: the window replicates with period dist
-                    for (uint32_t i = lane; i < mlen; i += LZB_LANES) dst[i] = src[i % dist];
+                    // (identical index expressions on both sides: written as src[0] the compiler folds the load into the
+                    // lane-dependent fill and loses the warp-uniformity of prev_byte downstream)
                     prev_byte = src[i_last % dist];
                     match_byte = src[i_next % dist];
+                    if (WIDE && dist == 1) {  // run of one byte (BASELINE config 5): word-wide fill
+                        warp_fill(dst, prev_byte, mlen, lane);
+                    } else {
+                        for (uint32_t i = lane; i < mlen; i += LZB_LANES) dst[i] = src[i % dist];
+                    }
                 }
                 mb_valid = true;
                 opos += mlen;

@@ -24,7 +24,7 @@
 // K1 launcher
 // ------------------------------------------------------------------------------------------------
 // Persistent kernels: warps pull stream indices (pre-sorted longest first by the host) from a counter.
-template <bool LIT_GLOBAL, bool MIRROR>
+template <bool LIT_GLOBAL, bool MIRROR, bool WIDE>
 __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order,
                                             uint32_t n_items, const uint8_t* __restrict__ in_blob, uint8_t* out_blob,
                                             LzbResult* results, unsigned int* counter, uint32_t tab_lclp,
@@ -48,11 +48,11 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
         const uint32_t idx = order ? order[slot] : slot;
         if (LIT_GLOBAL) {  // whole literal table in the global workspace (reference layout)
             const TabPtr plain = {gws}, matched = {gws + 0x100};
-            decode_item<true, MIRROR>(items + idx, in_blob, out_blob, T, gws, tab, plain, matched, kc, tab_lclp, results + idx, lane);
+            decode_item<true, MIRROR, WIDE>(items + idx, in_blob, out_blob, T, gws, tab, plain, matched, kc, tab_lclp, results + idx, lane);
         } else {  // plain columns in shared memory, matched columns in the global workspace
             const TabSm plain = {tab.a + (uint32_t)T_LIT * 2u};
             const TabPtr matched = {gws};
-            decode_item<false, MIRROR>(items + idx, in_blob, out_blob, T, gws, tab, plain, matched, kc, tab_lclp, results + idx, lane);
+            decode_item<false, MIRROR, WIDE>(items + idx, in_blob, out_blob, T, gws, tab, plain, matched, kc, tab_lclp, results + idx, lane);
         }
         __syncwarp();
     }
@@ -63,7 +63,7 @@ extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1)
                       const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
                       unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
                       unsigned long long ws_stride_u16, const __grid_constant__ LzbKC kc) {
-    decode_loop<false, false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
+    decode_loop<false, false, false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
                               ws_stride_u16, kc);
 }
 
@@ -73,8 +73,23 @@ extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1)
                              const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
                              unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
                              unsigned long long ws_stride_u16, const __grid_constant__ LzbKC kc) {
-    decode_loop<false, true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
+    decode_loop<false, true, false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
                              ws_stride_u16, kc);
+}
+
+// WIDE variants (word-wide stored-chunk copies and run fills) of the two kernels above.
+#define LZB_KERNEL_ARGS                                                                                              \
+    const LzbItem *__restrict__ items, const uint32_t *__restrict__ order, uint32_t n_items,                         \
+        const uint8_t *__restrict__ in_blob, uint8_t *out_blob, LzbResult *results, unsigned int *counter,           \
+        uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t *ws, unsigned long long ws_stride_u16,                 \
+        const __grid_constant__ LzbKC kc
+extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1) lzb_decode_wide_kernel(LZB_KERNEL_ARGS) {
+    decode_loop<false, false, true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes,
+                                    ws, ws_stride_u16, kc);
+}
+extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1) lzb_decode_wide_mirror_kernel(LZB_KERNEL_ARGS) {
+    decode_loop<false, true, true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes,
+                                   ws, ws_stride_u16, kc);
 }
 
 // .lzma streams with lc+lp > 4: literal table in a per-warp global workspace (ws + warp_id * ws_stride_u16).
@@ -83,7 +98,7 @@ extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1)
                              const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
                              unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
                              unsigned long long ws_stride_u16, const __grid_constant__ LzbKC kc) {
-    decode_loop<true, true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
+    decode_loop<true, true, true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
                             ws_stride_u16, kc);
 }
 
@@ -165,10 +180,11 @@ extern "C" __global__ void lzb_scan_kernel(int fmt, lzb_options opt, const uint8
             if (q >= len) break;
             uint32_t status = p[q++];
             if (status == 0) {
-                sc.flags = 1;
+                sc.flags |= 1;
                 break;
             }
             if (status == 1 || status == 2) {
+                sc.flags |= 2;  // has a stored chunk
                 if (len - q < 2) break;
                 uint64_t nb = (((uint32_t)p[q] << 8) | p[q + 1]) + 1;
                 q += 2;

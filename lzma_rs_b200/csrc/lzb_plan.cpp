@@ -68,6 +68,7 @@ Lzma2Scan scan_lzma2(const uint8_t* p, uint64_t len) {
             break;
         }
         if (status == 1 || status == 2) {
+            s.has_stored = true;
             if (len - q < 2) break;
             uint64_t nb = (((uint32_t)p[q] << 8) | p[q + 1]) + 1;
             q += 2;
@@ -158,7 +159,7 @@ void plan_lzma2(const uint8_t* p, uint64_t len, uint64_t base_off, LzbItem* it, 
     Lzma2Scan s = scan_lzma2(p, len);
     memset(sc, 0, sizeof *sc);
     sc->unpacked = s.unpacked;
-    sc->flags = s.well_formed ? 1u : 0u;
+    sc->flags = (s.well_formed ? 1u : 0u) | (s.has_stored ? 2u : 0u);
     sc->max_lclp = (uint8_t)s.max_lclp;
     if (len > 0xFFFFE000ull) preset(it, LZB_E_UNSUPPORTED);
 }
@@ -393,7 +394,7 @@ static uint64_t check_len(int check) {
     return check == CHECK_CRC32 ? 4 : check == CHECK_CRC64 ? 8 : check == CHECK_SHA256 ? 32 : 0;
 }
 
-static void plan_file(XzFile& f, std::vector<LzbItem>& items, uint32_t* max_lclp) {
+static void plan_file(XzFile& f, std::vector<LzbItem>& items, uint32_t* max_lclp, uint32_t* hints) {
     uint64_t pos = f.pos, out_rel = f.out_pos;
     f.plan.clear();
     f.terminal = T_NONE;
@@ -417,6 +418,7 @@ static void plan_file(XzFile& f, std::vector<LzbItem>& items, uint32_t* max_lclp
         }
         Lzma2Scan sc = scan_lzma2(f.p + bp.bh.payload, f.len - bp.bh.payload);
         *max_lclp = std::max(*max_lclp, sc.max_lclp);
+        if (sc.has_stored) *hints |= LZB_HINT_STORED;
         bp.pred_packed = sc.packed;
         bp.pred_unpacked = sc.unpacked;
         bp.out_rel = out_rel;
@@ -519,17 +521,17 @@ int decode_xz_batch(Executor& ex, const uint8_t* in, const uint64_t* in_off, uin
     std::vector<uint64_t> c64;
     for (;;) {
         items.clear();
-        uint32_t max_lclp = 0;
+        uint32_t max_lclp = 0, hints = 0;
         bool any = false;
         for (auto& f : files) {
             if (f.done) continue;
             any = true;
-            plan_file(f, items, &max_lclp);
+            plan_file(f, items, &max_lclp, &hints);
         }
         if (!any) break;
         results.assign(items.size(), LzbResult{});
         if (!items.empty()) {
-            int rc = ex.decode(items.data(), (uint32_t)items.size(), max_lclp, results.data());
+            int rc = ex.decode(items.data(), (uint32_t)items.size(), max_lclp, hints, results.data());
             if (rc != LZB_RC_OK) return rc;
         }
         ranges.clear();
@@ -560,7 +562,7 @@ int decode_batch(Executor& ex, int fmt, const lzb_options* opt, const uint8_t* i
     if (fmt == LZB_FMT_XZ) return decode_xz_batch(ex, in, in_off, n, out_off, outs);
     std::vector<LzbItem> items(n);
     std::vector<LzbResult> results(n);
-    uint32_t max_lclp = 0;
+    uint32_t max_lclp = 0, hints = 0;
     for (uint32_t i = 0; i < n; i++) {
         LzbScan sc;
         const uint8_t* p = in + in_off[i];
@@ -572,9 +574,10 @@ int decode_batch(Executor& ex, int fmt, const lzb_options* opt, const uint8_t* i
         items[i].out_off = out_off[i];
         items[i].out_cap = out_off[i + 1] - out_off[i];
         if (items[i].kind != LZB_ITEM_PRESET) max_lclp = std::max<uint32_t>(max_lclp, sc.max_lclp);
+        if (sc.flags & 2) hints |= LZB_HINT_STORED;
     }
     if (n) {
-        int rc = ex.decode(items.data(), n, max_lclp, results.data());
+        int rc = ex.decode(items.data(), n, max_lclp, hints, results.data());
         if (rc != LZB_RC_OK) return rc;
     }
     for (uint32_t i = 0; i < n; i++) {

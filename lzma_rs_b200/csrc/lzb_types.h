@@ -39,7 +39,7 @@ struct LzbResult {
 // Per-stream scan summary (K2).
 struct LzbScan {
     uint64_t unpacked; // exact for well-formed LZMA2 / known-size LZMA; heuristic otherwise
-    uint32_t flags;    // bit0: walk ended at a 0x00 control byte (well-formed framing)
+    uint32_t flags;    // bit0: walk ended at a 0x00 control byte (well-formed framing); bit1: has a stored chunk
     uint8_t max_lclp;  // largest lc+lp any chunk (or the .lzma header) asks for
     uint8_t pad[3];
 };

@@ -14,7 +14,7 @@ namespace {
 class HostEmulExecutor : public lzb::Executor {
    public:
     HostEmulExecutor(const uint8_t* in, uint8_t* out) : in_(in), out_(out) {}
-    int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, LzbResult* results) override {
+    int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint32_t /*hints*/, LzbResult* results) override {
         const uint32_t small_lclp = max_lclp > 4 ? 4 : max_lclp;
         std::vector<uint16_t> T(lzb_table_u16(small_lclp) + 8), M(lzb_matched_u16(small_lclp) + 8), T4, M4, G;
         for (uint32_t i = 0; i < n; i++) {
@@ -72,7 +72,7 @@ class HostEmulExecutor : public lzb::Executor {
         const TabPtr tab = {T};
         const TabPtr plain = {BIG ? G : T + T_LIT};
         const TabPtr matched = {BIG ? G + 0x100 : G};
-        decode_item<BIG, false>(it, in_, out_, T, G, tab, plain, matched, kc, lclp, res, 0);
+        decode_item<BIG, false, true>(it, in_, out_, T, G, tab, plain, matched, kc, lclp, res, 0);
     }
     const uint8_t* in_;
     uint8_t* out_;
