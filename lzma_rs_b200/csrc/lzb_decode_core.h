@@ -577,7 +577,12 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                 } else {  // plain 8-level walk (root fetched above, while is_match was being decoded)
                     const uint32_t x0 = probs.x0(kc), x1 = probs.x1(kc);
                     uint32_t node = probs.root(kc), pv = lit_pv;
-#pragma unroll
+#ifndef LZB_LIT_UNROLL
+#define LZB_LIT_UNROLL 8
+#endif
+#define LZB_PRAGMA_(x) _Pragma(#x)
+#define LZB_PRAGMA(x) LZB_PRAGMA_(x)
+                    LZB_PRAGMA(unroll LZB_LIT_UNROLL)
                     for (int i = 0; i < 8; i++) {
                         uint32_t np;
                         const uint32_t child = rc_step_tree(d, kc, pv, np, node, x0, x1);

@@ -211,3 +211,47 @@ def test_host_api_pinned_output_mirror(ctx):
     files = [corpus.xz_file(plains[11], block_size=1 << 16, check=corpus.CHECK_CRC64), corpus.xz_file(plains[12], block_size=100_000)]
     outs, out_len, consumed, st = gpu_util.host_decode_pinned(ctx, 2, files, [len(plains[11]), len(plains[12])])
     assert (st["code"] == 0).all() and outs[0] == plains[11] and outs[1] == plains[12]
+
+
+def test_fuzz_differential(ctx):
+    """Differential fuzzing in the style of the reference's fuzz targets (fuzz/fuzz_targets/compare_xz.rs:28-37:
+    both fail or both equal): thousands of mutated streams per format in ONE batch call each, against the oracle."""
+    import random
+    rnd = random.Random(20260925)
+    seeds = {
+        0: [corpus.lzma_alone(corpus.mixed_text(3000 + i, n), dict_size=d) for i, (n, d) in
+            enumerate([(500, 4096), (6000, 4096), (20_000, 1 << 16)])] +
+           [corpus.lzma_alone_known_size(corpus.mixed_text(3010, 3000), dict_size=4096)],
+        1: [corpus.raw_lzma2(corpus.mixed_text(3100 + i, n), dict_size=d, lc=lc, lp=lp, pb=pb) for i, (n, d, lc, lp, pb) in
+            enumerate([(700, 4096, 3, 0, 2), (9000, 1 << 16, 0, 2, 0), (150_000, 1 << 16, 4, 0, 4)])] +
+           [corpus.stored_lzma2(corpus.mixed_text(3110, 2000))],
+        2: [corpus.xz_file(corpus.mixed_text(3200, 5000), block_size=1500, check=corpus.CHECK_CRC32),
+            corpus.xz_file(corpus.mixed_text(3201, 40_000), block_size=1 << 14, check=corpus.CHECK_CRC64, with_sizes=True)],
+    }
+
+    def mutate(b):
+        b = bytearray(b)
+        k = rnd.random()
+        if k < 0.55:
+            for _ in range(rnd.choice([1, 1, 1, 2, 4])):
+                b[rnd.randrange(len(b))] = rnd.randrange(256)
+        elif k < 0.7:
+            b = b[:rnd.randrange(len(b))]
+        elif k < 0.8:
+            i = rnd.randrange(len(b))
+            b[i:i] = bytes(rnd.randrange(256) for _ in range(rnd.choice([1, 2, 7])))
+        elif k < 0.9:
+            i = rnd.randrange(len(b))
+            del b[i:i + rnd.choice([1, 2, 5])]
+        else:
+            i = rnd.randrange(min(len(b), 24))
+            b[i] ^= 1 << rnd.randrange(8)
+        return bytes(b)
+
+    total = 0
+    for fmt, srcs in seeds.items():
+        named = [(f"fuzz-{fmt}-{i}", mutate(srcs[i % len(srcs)])) for i in range(1200)]
+        bad = parity.check_group(_host(ctx), fmt, {}, named)
+        assert not bad, f"fmt {fmt}: {len(bad)} mismatches:\n" + "\n".join(bad[:20])
+        total += len(named)
+    assert total == 3600
