@@ -591,7 +591,10 @@ int decode_batch(Executor& ex, int fmt, const lzb_options* opt, const uint8_t* i
 // Output capacity a stream needs (lzb_scan): exact for well-formed LZMA2 / XZ / known-size .lzma (+ slack for the
 // <= 272 bytes a final match may overshoot before the size check fires, lzma.rs:513-521).
 uint64_t scan_capacity(int fmt, const lzb_options* opt, const uint8_t* p, uint64_t len) {
-    if (fmt == LZB_FMT_XZ) return scan_xz_capacity(p, len);
+    // sizes claimed by (possibly corrupt) headers are trusted up to a generous expansion bound; a stream that really
+    // expands more reports LZB_E_CAPACITY with the bytes it needs and is retried (lzb_decompress_alloc)
+    const uint64_t bound = len * 16384 + (1u << 20);
+    if (fmt == LZB_FMT_XZ) return std::min(scan_xz_capacity(p, len), bound);
     LzbItem it;
     LzbScan sc;
     if (fmt == LZB_FMT_LZMA) {
@@ -599,11 +602,11 @@ uint64_t scan_capacity(int fmt, const lzb_options* opt, const uint8_t* p, uint64
         if (it.kind == LZB_ITEM_PRESET) return 0;
         // a declared size is trusted up to a generous expansion bound; beyond it (garbage headers) start from a
         // heuristic and let LZB_E_CAPACITY drive the retry (lzb_decompress_alloc)
-        if ((sc.flags & 1) && sc.unpacked <= len * 16384 + (1u << 20)) return sc.unpacked + 288;
+        if ((sc.flags & 1) && sc.unpacked <= bound) return sc.unpacked + 288;
         return len * 8 + 65536;
     }
     plan_lzma2(p, len, 0, &it, &sc);
-    return sc.unpacked;
+    return std::min<uint64_t>(sc.unpacked, bound);
 }
 
 uint64_t scan_xz_capacity(const uint8_t* p, uint64_t len) {
@@ -615,7 +618,8 @@ uint64_t scan_xz_capacity(const uint8_t* p, uint64_t len) {
         BlockHeader bh;
         if (parse_block_header(p, len, pos, &bh).code) break;
         Lzma2Scan sc = scan_lzma2(p + bh.payload, len - bh.payload);
-        total += std::max<uint64_t>(sc.unpacked, bh.has_unpacked ? bh.unpacked : 0);
+        const uint64_t cap_bound = len * 16384 + (1u << 20);  // ignore absurd sizes in corrupt block headers
+        total += std::min(std::max<uint64_t>(sc.unpacked, bh.has_unpacked ? bh.unpacked : 0), cap_bound);
         if (!sc.well_formed) break;
         const uint64_t end = bh.payload + sc.packed;
         const uint64_t count = end - pos;
