@@ -147,8 +147,21 @@ class Context:
             raise RuntimeError(f"lzb_scan failed rc={rc}: {self.last_error()}")
         return cap
 
-    def decode_batch(self, fmt, streams, options=None, capacities=None):
-        """streams: list of bytes-like.  Returns a list of StreamResult (same order)."""
+    def decode_batch(self, fmt, streams, options=None, capacities=None, retry=True):
+        """streams: list of bytes-like.  Returns a list of StreamResult (same order).
+        retry: streams whose size cannot be known up front (end-marker .lzma, malformed framing) and that report
+        LZB_E_CAPACITY are decoded again with a larger buffer, like lzb_decompress_alloc does."""
+        res = self._decode_batch_once(fmt, streams, options, capacities)
+        if retry:
+            for i, r in enumerate(res):
+                cap = None
+                while int(r.status["code"]) == _native.E_CAPACITY and (cap or 0) < 0xF0000000:
+                    cap = max(int(r.status["a0"]) * 2, 1 << 16) if cap is None else cap * 2
+                    r = self._decode_batch_once(fmt, [streams[i]], options, [cap])[0]
+                res[i] = r
+        return res
+
+    def _decode_batch_once(self, fmt, streams, options=None, capacities=None):
         blob, in_off = _native.pack_streams(streams)
         n = len(streams)
         opt = (options or decompress.Options())._native()

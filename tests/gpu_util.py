@@ -13,16 +13,8 @@ def options_from(opts):
 
 
 def host_decode(ctx, fmt, streams, opts):
-    """lzb_decode_batch (host buffers) with the LZB_E_CAPACITY retry lzb_decompress_alloc performs."""
-    o = options_from(opts)
-    res = ctx.decode_batch(fmt, streams, o)
-    for i, r in enumerate(res):
-        cap = None
-        while int(r.status["code"]) == _native.E_CAPACITY:
-            cap = max(int(r.status["a0"]) * 2, 1 << 16) if cap is None else cap * 2
-            r = ctx.decode_batch(fmt, [streams[i]], o, capacities=[cap])[0]
-        res[i] = r
-    return res
+    """lzb_decode_batch (host buffers), with the LZB_E_CAPACITY retry of Context.decode_batch."""
+    return ctx.decode_batch(fmt, streams, options_from(opts))
 
 
 class DeviceBatch:
