@@ -255,3 +255,23 @@ def test_fuzz_differential(ctx):
         assert not bad, f"fmt {fmt}: {len(bad)} mismatches:\n" + "\n".join(bad[:20])
         total += len(named)
     assert total == 3600
+
+
+def test_batch_shape_extremes(ctx):
+    """Many tiny streams next to a few long ones (scheduler imbalance), and a long .lzma whose 4 KiB ring wraps often."""
+    import gpu_util
+    tiny_plain = [corpus.mixed_text(7000 + i, 40 + (i % 200)) for i in range(512)]
+    tiny = [corpus.raw_lzma2(p) for p in tiny_plain]
+    big_plain = [corpus.mixed_text(7777, 6 << 20), b"\0" * (3 << 20) + corpus.mixed_text(7778, 1 << 20)]
+    big = [corpus.raw_lzma2(p, dict_size=1 << 22) for p in big_plain]
+    n_tiny = 20_000
+    streams = [tiny[i % 512] for i in range(n_tiny)] + big
+    plains = [tiny_plain[i % 512] for i in range(n_tiny)] + big_plain
+    b = gpu_util.DeviceBatch(ctx, 1, streams, [len(p) for p in plains]).decode()
+    assert (b.st["code"] == 0).all()
+    for i in list(range(0, n_tiny, 997)) + [n_tiny, n_tiny + 1]:
+        assert b.output(i) == plains[i], i
+    assert int(b.out_len.sum()) == sum(len(p) for p in plains)
+    wrap_plain = corpus.mixed_text(7900, 2 << 20)
+    r = ctx.decode_batch(0, [corpus.lzma_alone(wrap_plain, dict_size=4096), corpus.lzma_alone_known_size(wrap_plain, dict_size=1 << 16)])
+    assert all(x.ok and x.data == wrap_plain for x in r)
