@@ -15,6 +15,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _ensure_native_built():
+    """Build liblzma_b200.so / the oracle in-tree when they are missing or older than their sources (a fresh
+    checkout: built artefacts are git-ignored).  nvcc cross-compiles sm_100a without a GPU."""
+    import subprocess
+    csrc = os.path.join(ROOT, "lzma_rs_b200", "csrc")
+    lib = os.path.join(ROOT, "lzma_rs_b200", "liblzma_b200.so")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(ROOT, "include", "lzma_b200.h")]
+    if (not os.path.exists(lib)) or any(os.path.getmtime(f) > os.path.getmtime(lib) for f in srcs):
+        subprocess.check_call(["make", "-C", csrc, "-s"])
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+
+
+_ensure_native_built()
+
+
 class Golden:
     """The reference's own golden vectors, committed under tests/golden/ (see make_golden.py)."""
 
