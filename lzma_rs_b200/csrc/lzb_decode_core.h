@@ -534,7 +534,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                 mirror_next = upto + 4096u;
             }
             if (opos >= stop_at) break;
-            if (!has_target && d.code == 0 && d.p == d.lim) break;  // is_finished_ok, rangecoder.rs:50-52
+            if (LZB_UNLIKELY(d.code == 0) && !has_target && d.p == d.lim) break;  // is_finished_ok, rangecoder.rs:50-52
             const uint32_t len = opos - dict_base;
             const uint32_t pos_state = len & pb_mask;
 
