@@ -379,7 +379,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
     Dec d;
     const bool is_lzma1 = itp->kind == LZB_ITEM_LZMA;
     const uint32_t p0 = (uint32_t)(itp->in_off & 3ull);
-    const uint8_t* __restrict__ inb = in_blob + (itp->in_off - p0);
+    const uint8_t* __restrict__ inb =
+        ((itp->flags & LZB_ITEM_F_IN_FROM_OUT) ? (const uint8_t*)out_blob : in_blob) + (itp->in_off - p0);
     const uint32_t stream_lim = p0 + (uint32_t)itp->in_len;
     uint8_t* out = out_blob + itp->out_off;
     const uint32_t cap = (uint32_t)LZB_MIN(itp->out_cap, (uint64_t)0xFFFFF000u);

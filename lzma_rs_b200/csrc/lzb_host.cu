@@ -281,6 +281,24 @@ class CudaExecutor : public lzb::Executor {
         return LZB_RC_OK;
     }
 
+    int scratch(uint64_t bytes, uint64_t* off) override {
+        lzb_ctx* ctx = ctx_;
+        void* p = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&p, bytes + 64));
+        scratch_.push_back(p);
+        *off = (uint64_t)((uint8_t*)p - out_);  // output-blob coordinates (pointer difference modulo 2^64)
+        return LZB_RC_OK;
+    }
+    int read_out(uint64_t off, uint64_t len, uint8_t* dst) override {
+        lzb_ctx* ctx = ctx_;
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, out_ + off, len, cudaMemcpyDeviceToHost, s_));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s_));
+        return LZB_RC_OK;
+    }
+    ~CudaExecutor() override {
+        for (void* p : scratch_) cudaFree(p);
+    }
+
    private:
     int run(const LzbItem* items, uint32_t n, uint32_t lclp_hint, uint32_t hints, LzbResult* results) {
         lzb_ctx* ctx = ctx_;
@@ -294,6 +312,7 @@ class CudaExecutor : public lzb::Executor {
         if (hmirror_) {  // the mirror copies 16-byte vectors: both copies of a stream's region must be 16-byte aligned
             patched.assign(items, items + n);
             for (auto& it : patched) {
+                if (it.flags & LZB_ITEM_F_OUT_SCRATCH) continue;  // intermediate result of a filter chain
                 if ((it.out_off & 15) == 0 && it.kind != LZB_ITEM_PRESET)
                     it.host_out = (uint64_t)(uintptr_t)(hmirror_ + it.out_off);
                 else if (it.kind != LZB_ITEM_PRESET)
@@ -317,6 +336,7 @@ class CudaExecutor : public lzb::Executor {
     uint8_t* out_;
     uint8_t* hmirror_;
     bool unmirrored_ = false;
+    std::vector<void*> scratch_;
 };
 
 }  // namespace

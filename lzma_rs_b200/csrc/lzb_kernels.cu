@@ -126,6 +126,7 @@ extern "C" __global__ void lzb_scan_kernel(int fmt, lzb_options opt, const uint8
     it.hdr_len = 0;
     it.preset_code = 0;
     it.preset_a0 = 0;
+    it.flags = 0;
     it.host_out = 0;
     sc.unpacked = 0;
     sc.flags = 0;

@@ -229,6 +229,7 @@ struct BlockHeader {
     bool has_packed = false, has_unpacked = false;
     uint64_t packed = 0, unpacked = 0;
     uint32_t nfilters = 0;
+    uint32_t bad_props_from = 0;  // first filter index >= 1 whose properties are not 1 byte (0 = none)
 };
 
 // read_block (header part, xz.rs:206-224) + read_block_header (356-446) + the filter-props check of
@@ -276,7 +277,8 @@ static lzb_status parse_block_header(const uint8_t* p, uint64_t len, uint64_t po
     const uint32_t digest = crc ^ 0xFFFFFFFFu;
     if (crc_read != digest) return mk(LZB_E_XZ_HEADER_CRC, crc_read, digest);
     if (props_len[0] != 1) return mk(LZB_E_XZ_FILTER_PROPS);
-    if (bh->nfilters > 1) return mk(LZB_E_UNSUPPORTED);  // chained LZMA2->LZMA2 filters: not on the GPU path yet
+    for (uint32_t i = 1; i < bh->nfilters; i++)  // decode_filter checks each filter's props when it runs (xz.rs:343-348);
+        if (props_len[i] != 1) bh->bad_props_from = bh->bad_props_from ? bh->bad_props_from : i;  // later ones fail later
     bh->payload = f.pos;
     return mk(LZB_OK);
 }
@@ -367,6 +369,8 @@ struct BlockPlan {
     bool cap_is_prediction = false;
     uint32_t item = 0;
     int32_t crc_idx = -1;
+    bool chain_stage = false;  // this item is one stage of a chained-filter block (not the whole block)
+    bool chain_last = false;   // ... and it is the last filter (its output is the block's output)
 };
 enum Terminal { T_NONE, T_INDEX, T_ERROR };
 struct XzFile {
@@ -381,11 +385,18 @@ struct XzFile {
     lzb_status terminal_status{};
     uint64_t index_pos = 0;
     StreamOut* out = nullptr;
-    void finish(const lzb_status& s) {
+    // chained filters (xz.rs:240-249): the block at `pos` is decoded one filter per round
+    uint32_t chain_next = 0;      // next filter to run (0 = not inside a chain)
+    uint64_t chain_in_off = 0, chain_in_len = 0;  // previous filter's output (output-blob coordinates)
+    uint64_t chain_packed = 0;    // bytes filter 0 consumed from the file
+    std::vector<uint8_t> chain_host;  // host copy of the previous filter's output (framing scan only)
+    uint64_t chain_scratch_hint = 0;  // scratch size to try after a stage overflowed its scratch
+    int finish(const lzb_status& s) {
         out->st = s;
         out->out_len = out_pos;
         out->consumed = s.code == LZB_OK ? len : pos;
         done = true;
+        return LZB_RC_OK;
     }
 };
 }  // namespace
@@ -394,7 +405,51 @@ static uint64_t check_len(int check) {
     return check == CHECK_CRC32 ? 4 : check == CHECK_CRC64 ? 8 : check == CHECK_SHA256 ? 32 : 0;
 }
 
-static void plan_file(XzFile& f, std::vector<LzbItem>& items, uint32_t* max_lclp, uint32_t* hints) {
+// One stage of a chained-filter block (xz.rs:240-249): filter j decodes the previous filter's output.  Stage 0 reads
+// the file payload; every stage but the last writes to device scratch; the last writes to the file's output region.
+static int plan_chain_stage(Executor& ex, XzFile& f, const BlockPlan& proto, std::vector<LzbItem>& items,
+                            uint32_t* max_lclp, uint32_t* hints) {
+    BlockPlan bp = proto;
+    const uint32_t j = f.chain_next;
+    const bool last = j + 1 == bp.bh.nfilters;
+    if (bp.bh.bad_props_from && j >= bp.bh.bad_props_from) {  // decode_filter(j): props.len() != 1, xz.rs:343-348
+        f.terminal = T_ERROR;
+        f.terminal_status = mk(LZB_E_XZ_FILTER_PROPS);
+        return LZB_RC_OK;
+    }
+    const uint8_t* src = j == 0 ? f.p + bp.bh.payload : f.chain_host.data();
+    const uint64_t src_len = j == 0 ? f.len - bp.bh.payload : f.chain_in_len;
+    Lzma2Scan sc = scan_lzma2(src, src_len);
+    *max_lclp = std::max(*max_lclp, sc.max_lclp);
+    if (sc.has_stored) *hints |= LZB_HINT_STORED;
+    LzbItem it;
+    if (j == 0) {
+        item_defaults(&it, f.in_base + bp.bh.payload, src_len);
+    } else {
+        item_defaults(&it, f.chain_in_off, src_len);
+        it.flags = LZB_ITEM_F_IN_FROM_OUT;
+    }
+    bp.out_rel = f.out_pos;
+    if (last) {
+        bp.cap = f.out_cap - std::min(f.out_cap, f.out_pos);
+        it.out_off = f.out_base + f.out_pos;
+    } else {
+        bp.cap = std::max<uint64_t>(std::max<uint64_t>(sc.unpacked, f.chain_scratch_hint), 4096) + 64;
+        int rc = ex.scratch(bp.cap, &it.out_off);
+        if (rc != LZB_RC_OK) return rc;
+        it.flags |= LZB_ITEM_F_OUT_SCRATCH;
+    }
+    it.out_cap = bp.cap;
+    if (it.in_len > 0xFFFFE000ull) preset(&it, LZB_E_UNSUPPORTED);
+    bp.chain_stage = true;
+    bp.chain_last = last;
+    bp.item = (uint32_t)items.size();
+    items.push_back(it);
+    f.plan.push_back(bp);
+    return LZB_RC_OK;
+}
+
+static int plan_file(Executor& ex, XzFile& f, std::vector<LzbItem>& items, uint32_t* max_lclp, uint32_t* hints) {
     uint64_t pos = f.pos, out_rel = f.out_pos;
     f.plan.clear();
     f.terminal = T_NONE;
@@ -415,6 +470,10 @@ static void plan_file(XzFile& f, std::vector<LzbItem>& items, uint32_t* max_lclp
             f.terminal = T_ERROR;
             f.terminal_status = s;
             break;
+        }
+        if (bp.bh.nfilters > 1) {  // chained filters: the block runs alone, one filter per round
+            if (!f.plan.empty()) break;
+            return plan_chain_stage(ex, f, bp, items, max_lclp, hints);
         }
         Lzma2Scan sc = scan_lzma2(f.p + bp.bh.payload, f.len - bp.bh.payload);
         *max_lclp = std::max(*max_lclp, sc.max_lclp);
@@ -443,24 +502,50 @@ static void plan_file(XzFile& f, std::vector<LzbItem>& items, uint32_t* max_lclp
         pos = end + (((count ^ 3) + 1) & 3) + check_len(f.check);
         out_rel += sc.unpacked;
     }
+    return LZB_RC_OK;
 }
 
 // Validates the planned blocks of one file in order (xz.rs:232-287); returns true when the file is finished.
-static void validate_file(XzFile& f, const std::vector<LzbResult>& results, const std::vector<uint32_t>& crc32,
-                          const std::vector<uint64_t>& crc64) {
+static int validate_file(Executor& ex, XzFile& f, const std::vector<LzbItem>& items, const std::vector<LzbResult>& results,
+                         const std::vector<uint32_t>& crc32, const std::vector<uint64_t>& crc64) {
     for (size_t k = 0; k < f.plan.size(); k++) {
         const BlockPlan& bp = f.plan[k];
         const LzbResult& r = results[bp.item];
         const uint64_t remaining = f.out_cap - std::min(f.out_cap, bp.out_rel);
+        if (bp.chain_stage && !bp.chain_last) {  // an inner filter of a chain: its output feeds the next round
+            if (r.code == LZB_E_CAPACITY) {  // scratch too small (framing scan mispredicted): retry this stage bigger
+                f.chain_scratch_hint = std::max<uint64_t>(r.a0 * 2, f.chain_scratch_hint * 2);
+                if (f.chain_scratch_hint > 0xF0000000ull) return f.finish(mk(LZB_E_UNSUPPORTED)), LZB_RC_OK;
+                return LZB_RC_OK;
+            }
+            if (r.code != LZB_OK) return f.finish(mk(r.code, r.a0, r.a1)), LZB_RC_OK;
+            if (f.chain_next == 0) {
+                f.chain_packed = r.consumed;
+                if (bp.bh.has_packed && r.consumed != bp.bh.packed)  // checked right after filter 0, xz.rs:232-238
+                    return f.finish(mk(LZB_E_XZ_PACKED_SIZE, bp.bh.packed, r.consumed)), LZB_RC_OK;
+            }
+            f.chain_in_off = items[bp.item].out_off;
+            f.chain_in_len = r.out_len;
+            f.chain_host.resize(r.out_len + 16);
+            if (r.out_len) {
+                int rc = ex.read_out(f.chain_in_off, r.out_len, f.chain_host.data());
+                if (rc != LZB_RC_OK) return rc;
+            }
+            f.chain_next += 1;
+            f.chain_scratch_hint = 0;
+            return LZB_RC_OK;
+        }
         if (r.code == LZB_E_CAPACITY || r.code == LZB_E_UNSUPPORTED) {
             if (r.code == LZB_E_CAPACITY && bp.cap_is_prediction && bp.cap < remaining) {
                 f.lookahead = false;  // the framing scan mispredicted: redo from this block without look-ahead
-                return;
+                return LZB_RC_OK;
             }
             return f.finish(mk(r.code, r.code == LZB_E_CAPACITY ? bp.out_rel + r.a0 : r.a0, r.a1));
         }
         if (r.code != LZB_OK) return f.finish(mk(r.code, r.a0, r.a1));  // `?` on Lzma2Decoder::decompress, xz.rs:350
-        const uint64_t packed = r.consumed, unpacked = r.out_len;
+        // (a chain's last filter: the bytes consumed from the FILE are those of filter 0)
+        const uint64_t packed = (bp.chain_stage && f.chain_next > 0) ? f.chain_packed : r.consumed, unpacked = r.out_len;
+        if (bp.chain_stage) f.chain_next = 0;
         if (bp.bh.has_packed && packed != bp.bh.packed) return f.finish(mk(LZB_E_XZ_PACKED_SIZE, bp.bh.packed, packed));
         if (bp.bh.has_unpacked && unpacked != bp.bh.unpacked)
             return f.finish(mk(LZB_E_XZ_UNPACKED_SIZE, bp.bh.unpacked, unpacked));
@@ -489,12 +574,13 @@ static void validate_file(XzFile& f, const std::vector<LzbResult>& results, cons
         f.pos = c.pos;
         if ((packed != bp.pred_packed || unpacked != bp.pred_unpacked) && k + 1 < f.plan.size()) {
             f.lookahead = false;  // later blocks were planned at the wrong offsets
-            return;
+            return LZB_RC_OK;
         }
     }
     if (f.terminal == T_ERROR) return f.finish(f.terminal_status);
     if (f.terminal == T_INDEX) return f.finish(check_index_and_footer(f.p, f.len, f.index_pos, f.records, f.check));
     // T_NONE: planning stopped for lack of look-ahead; continue next round from f.pos
+    return LZB_RC_OK;
 }
 
 int decode_xz_batch(Executor& ex, const uint8_t* in, const uint64_t* in_off, uint32_t n, const uint64_t* out_off,
@@ -526,7 +612,8 @@ int decode_xz_batch(Executor& ex, const uint8_t* in, const uint64_t* in_off, uin
         for (auto& f : files) {
             if (f.done) continue;
             any = true;
-            plan_file(f, items, &max_lclp, &hints);
+            int prc = plan_file(ex, f, items, &max_lclp, &hints);
+            if (prc != LZB_RC_OK) return prc;
         }
         if (!any) break;
         results.assign(items.size(), LzbResult{});
@@ -540,6 +627,7 @@ int decode_xz_batch(Executor& ex, const uint8_t* in, const uint64_t* in_off, uin
             for (auto& bp : f.plan) {
                 const LzbResult& r = results[bp.item];
                 if (r.code != LZB_OK) break;
+                if (bp.chain_stage && !bp.chain_last) break;  // intermediate result of a filter chain: no check
                 bp.crc_idx = (int32_t)ranges.size();
                 ranges.push_back(CrcRange{f.out_base + bp.out_rel, r.out_len});
             }
@@ -550,8 +638,11 @@ int decode_xz_batch(Executor& ex, const uint8_t* in, const uint64_t* in_off, uin
             int rc = ex.crc(ranges.data(), (uint32_t)ranges.size(), c32.data(), c64.data());
             if (rc != LZB_RC_OK) return rc;
         }
-        for (auto& f : files)
-            if (!f.done) validate_file(f, results, c32, c64);
+        for (auto& f : files) {
+            if (f.done) continue;
+            int vrc = validate_file(ex, f, items, results, c32, c64);
+            if (vrc != LZB_RC_OK) return vrc;
+        }
     }
     return LZB_RC_OK;
 }

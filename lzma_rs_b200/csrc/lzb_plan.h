@@ -26,6 +26,11 @@ class Executor {
     virtual int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint32_t hints, LzbResult* results) = 0;
     // CRC-32 and CRC-64 of output-blob ranges.
     virtual int crc(const CrcRange* ranges, uint32_t n, uint32_t* crc32, uint64_t* crc64) = 0;
+    // Device scratch of `bytes` bytes, returned as an offset in output-blob coordinates (valid until the executor dies):
+    // intermediate results of chained .xz filters.  Returns LZB_RC_*.
+    virtual int scratch(uint64_t bytes, uint64_t* out_off) = 0;
+    // Copies output-blob bytes [off, off+len) to host memory (the framing scan of an intermediate result).
+    virtual int read_out(uint64_t off, uint64_t len, uint8_t* dst) = 0;
 };
 
 // ---- scans (host copies of what K2 does on the device) ----

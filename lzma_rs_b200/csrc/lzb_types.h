@@ -18,12 +18,16 @@ struct LzbItem {
     uint8_t lc, lp, pb; // LZMA properties (LZMA2 reads its own from chunk headers)
     uint32_t hdr_len;   // bytes of container header already consumed before in_off (LZMA: 13 or 5)
     int32_t preset_code;// LZB_ITEM_PRESET: status decided before the decode (header errors)
+    uint32_t flags;     // LZB_ITEM_F_*
     uint64_t preset_a0;
     uint64_t host_out;  // device-visible address of this stream's region in the caller's PINNED host output (0 = none):
                         // the mirror variant of K1 streams finished 4 KiB pages there while it decodes
 };
 
 enum { LZB_ITEM_LZMA = 0, LZB_ITEM_LZMA2 = 1, LZB_ITEM_PRESET = 2 };
+// in_off addresses the OUTPUT blob: the stream is the output of an earlier launch (chained .xz filters, xz.rs:240-249)
+// out_off addresses device scratch outside the caller's output region (never mirrored to the host)
+enum { LZB_ITEM_F_IN_FROM_OUT = 1, LZB_ITEM_F_OUT_SCRATCH = 2 };
 #define LZB_UNKNOWN_SIZE 0xFFFFFFFFFFFFFFFFull
 
 // Per-stream result written by the decode kernel.

@@ -401,23 +401,64 @@ def xz_cases():
     return out
 
 
-def unsupported_cases():
-    """Inputs the reference accepts but the GPU path reports as LZB_E_UNSUPPORTED (documented gaps):
-    chained LZMA2->LZMA2 filters in one .xz block (xz.rs:240-249; never produced by xz itself)."""
-    plain = c.mixed_text(60, 2000)
-    inner = c.raw_lzma2(plain)
-    outer = c.raw_lzma2(inner)
-    blk, unp = c.xz_block(outer, plain, c.CHECK_CRC32, nfilters=2)
-    flags = bytes([0, c.CHECK_CRC32])
-    o = bytearray(b"\xfd7zXZ\0" + flags + struct.pack("<I", zlib.crc32(flags))) + blk
-    idx = bytearray(b"\0" + c._multibyte(1) + c._multibyte(unp) + c._multibyte(len(plain)))
+def _xz_wrap(blocks_bytes, records, check):
+    flags = bytes([0, check])
+    o = bytearray(b"\xfd7zXZ\0" + flags + struct.pack("<I", zlib.crc32(flags))) + blocks_bytes
+    idx = bytearray(b"\0" + c._multibyte(len(records)))
+    for u, p in records:
+        idx += c._multibyte(u) + c._multibyte(p)
     idx += b"\0" * ((4 - len(idx) % 4) % 4)
     idx += struct.pack("<I", zlib.crc32(bytes(idx)))
     fb = struct.pack("<I", len(idx) // 4 - 1) + flags
-    o += idx + struct.pack("<I", zlib.crc32(fb)) + fb + b"YZ"
-    return [("xz-two-filters", XZ, bytes(o), {}, plain)]
+    return bytes(o + idx + struct.pack("<I", zlib.crc32(fb)) + fb + b"YZ")
+
+
+def xz_chain_cases():
+    """Blocks with 2-4 chained LZMA2 filters (the reference decodes filter i+1 from filter i's output, xz.rs:240-249;
+    xz itself never writes such files)."""
+    out = []
+    plain = c.mixed_text(60, 30_000)
+    lvl = [plain]
+    for k in range(4):
+        lvl.append(c.raw_lzma2(lvl[-1], dict_size=1 << 16))
+    for nf in (2, 3, 4):
+        for check in (c.CHECK_CRC32, c.CHECK_CRC64, c.CHECK_NONE):
+            blk, unp = c.xz_block(lvl[nf], plain, check, nfilters=nf)
+            out.append((f"xz-chain-{nf}-{check}", XZ, _xz_wrap(blk, [(unp, len(plain))], check), {}))
+    # a normal block, then a chained one, then a normal one (look-ahead must stop and resume around the chain)
+    p2 = c.mixed_text(61, 5000)
+    b1, u1 = c.xz_block(c.raw_lzma2(p2), p2, c.CHECK_CRC32)
+    b2, u2 = c.xz_block(lvl[2], plain, c.CHECK_CRC32, nfilters=2)
+    out.append(("xz-chain-mixed", XZ, _xz_wrap(b1 + b2 + b1, [(u1, len(p2)), (u2, len(plain)), (u1, len(p2))], c.CHECK_CRC32), {}))
+    # sizes in the header: packed = filter 0's input, unpacked = the last filter's output
+    blk, unp = c.xz_block(lvl[2], plain, c.CHECK_CRC32, with_sizes=True, nfilters=2)
+    out.append(("xz-chain-sizes", XZ, _xz_wrap(blk, [(unp, len(plain))], c.CHECK_CRC32), {}))
+    # inner stream corrupt / truncated / with trailing bytes after its end marker (ignored by the reference)
+    bad_inner = c.raw_lzma2(lvl[1][:-1] + b"\x7f", dict_size=1 << 16)
+    blk, unp = c.xz_block(bad_inner, plain, c.CHECK_CRC32, nfilters=2)
+    out.append(("xz-chain-inner-bad-status", XZ, _xz_wrap(blk, [(unp, len(plain))], c.CHECK_CRC32), {}))
+    trunc_inner = c.raw_lzma2(lvl[1][:len(lvl[1]) // 2], dict_size=1 << 16)
+    blk, unp = c.xz_block(trunc_inner, plain, c.CHECK_CRC32, nfilters=2)
+    out.append(("xz-chain-inner-truncated", XZ, _xz_wrap(blk, [(unp, len(plain))], c.CHECK_CRC32), {}))
+    trail_inner = c.raw_lzma2(lvl[1] + b"trailing garbage", dict_size=1 << 16)
+    blk, unp = c.xz_block(trail_inner, plain, c.CHECK_CRC32, nfilters=2)
+    out.append(("xz-chain-inner-trailing", XZ, _xz_wrap(blk, [(unp, len(plain))], c.CHECK_CRC32), {}))
+    # wrong check over the final output; second filter with 2-byte properties (fails when that filter is reached)
+    blk, unp = c.xz_block(lvl[2], plain[:-1] + b"!", c.CHECK_CRC32, nfilters=2)
+    out.append(("xz-chain-bad-crc", XZ, _xz_wrap(blk, [(unp, len(plain))], c.CHECK_CRC32), {}))
+    body = bytes([0x01, 0x21, 0x01, 0x16, 0x21, 0x02, 0x16, 0x00])
+    total = 1 + len(body) + 4
+    tp = (total + 3) & ~3
+    body += b"\0" * (tp - total)
+    hdr = bytes([tp // 4 - 1]) + body
+    hdr += struct.pack("<I", zlib.crc32(hdr))
+    blk = hdr + lvl[2]
+    unp = len(blk) + 4
+    blk += b"\0" * ((4 - len(blk) % 4) % 4) + struct.pack("<I", zlib.crc32(plain))
+    out.append(("xz-chain-second-props-len2", XZ, _xz_wrap(blk, [(unp, len(plain))], c.CHECK_CRC32), {}))
+    return out
 
 
 def all_cases():
     return (valid_lzma2_cases() + valid_lzma_cases() + hand_encoded_cases() + truncation_and_corruption_cases() +
-            xz_cases())
+            xz_cases() + xz_chain_cases())

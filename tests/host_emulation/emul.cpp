@@ -65,6 +65,16 @@ class HostEmulExecutor : public lzb::Executor {
         return LZB_RC_OK;
     }
 
+    int scratch(uint64_t bytes, uint64_t* off) override {
+        scratch_.emplace_back(bytes + 64);
+        *off = (uint64_t)(scratch_.back().data() - out_);  // output-blob coordinates
+        return LZB_RC_OK;
+    }
+    int read_out(uint64_t off, uint64_t len, uint8_t* dst) override {
+        memcpy(dst, out_ + off, len);
+        return LZB_RC_OK;
+    }
+
    private:
     template <bool BIG>
     void run(const LzbItem* it, uint16_t* T, uint16_t* G, uint32_t lclp, LzbResult* res) {
@@ -76,6 +86,7 @@ class HostEmulExecutor : public lzb::Executor {
     }
     const uint8_t* in_;
     uint8_t* out_;
+    std::vector<std::vector<uint8_t>> scratch_;
 };
 }  // namespace
 

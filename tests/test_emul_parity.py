@@ -23,7 +23,7 @@ def _decode(fmt, streams, opts):
 
 
 @pytest.mark.parametrize("family", ["valid_lzma2_cases", "valid_lzma_cases", "hand_encoded_cases",
-                                    "truncation_and_corruption_cases", "xz_cases"])
+                                    "truncation_and_corruption_cases", "xz_cases", "xz_chain_cases"])
 def test_emulated_kernel_matches_oracle(family):
     bad = []
     n = 0
@@ -31,12 +31,3 @@ def test_emulated_kernel_matches_oracle(family):
         bad += parity.check_group(_decode, fmt, dict(okey), named)
         n += len(named)
     assert not bad, f"{len(bad)}/{n} mismatches:\n" + "\n".join(bad[:40])
-
-
-def test_documented_unsupported_inputs():
-    import oracle_py
-    for name, fmt, stream, opts, plain in cases.unsupported_cases():
-        ref = oracle_py.xz_decompress(stream)
-        assert ref.ok and ref.out == plain, name  # the reference accepts it ...
-        r = _decode(fmt, [stream], opts)[0]
-        assert int(r.status["code"]) == _native.E_UNSUPPORTED and r.data == b"", name  # ... the GPU path says so loudly

@@ -30,7 +30,7 @@ def _host(ctx):
 
 
 @pytest.mark.parametrize("family", ["valid_lzma2_cases", "valid_lzma_cases", "hand_encoded_cases",
-                                    "truncation_and_corruption_cases", "xz_cases"])
+                                    "truncation_and_corruption_cases", "xz_cases", "xz_chain_cases"])
 def test_cuda_path_matches_oracle(ctx, family):
     bad, n = [], 0
     for (fmt, okey), named in parity.group_cases(getattr(cases, family)()).items():
