@@ -44,6 +44,9 @@ CONFIGS = {
                name="C3 shard: {n} independent raw LZMA2 streams x 262144 B (dict 1 MiB, 3 chunks each) per GPU"),
     "c5": dict(index=5, stream_bytes=262144, dict_size=1 << 20, streams=8192, kind="rep0",
                name="C5: {n} raw LZMA2 streams x 262144 B of all-overlapping rep0 matches (dist=1, len=273) per GPU"),
+    "ns": dict(index=6, stream_bytes=0, dict_size=1 << 20, streams=8192, kind="mixed",
+               name="NS shard: {n} independent raw LZMA2 streams, sizes log-uniform in [64 KiB, 1 MiB], dict 1 MiB, per GPU "
+                    "(north-star sweep: 65 536 streams over 8 GPUs)"),
     "c4": dict(index=4, stream_bytes=1 << 20, dict_size=1 << 20, streams=1024, kind="xz",
                name="C4: {n} .xz files x 1 MiB (4 blocks of 256 KiB each, LZMA2 filter, CRC32 block check) per GPU, "
                     "host API only (container walk on the host, K1 decode + K3 CRC on the GPU)"),
@@ -54,6 +57,8 @@ CFG = CONFIGS["c2"]
 def _one_stream(args):
     import corpus
     seed, size, dict_size, kind = args
+    if size == 0:  # north-star sweep: size log-uniform in [64 KiB, 1 MiB], a function of the seed
+        size = int(65536 * 16 ** np.random.default_rng(seed ^ 0x5EED).random())
     if kind == "xz":
         plain = corpus.mixed_text(seed, size)
         return corpus.xz_file(plain, block_size=1 << 18, check=corpus.CHECK_CRC32, dict_size=dict_size), plain
