@@ -47,6 +47,9 @@ CONFIGS = {
     "ns": dict(index=6, stream_bytes=0, dict_size=1 << 20, streams=8192, kind="mixed",
                name="NS shard: {n} independent raw LZMA2 streams, sizes log-uniform in [64 KiB, 1 MiB], dict 1 MiB, per GPU "
                     "(north-star sweep: 65 536 streams over 8 GPUs)"),
+    "c6": dict(index=7, stream_bytes=1 << 20, dict_size=1 << 20, streams=2048, kind="stored",
+               name="C6: {n} raw LZMA2 streams x 1 MiB of stored chunks only (16 x `01 FF FF` + 64 KiB, the only LZMA2 the "
+                    "reference's own encoder writes, src/encode/lzma2.rs:4-26) per GPU -- the byte-bound end of the path"),
     "c4": dict(index=4, stream_bytes=1 << 20, dict_size=1 << 20, streams=1024, kind="xz",
                name="C4: {n} .xz files x 1 MiB (4 blocks of 256 KiB each, LZMA2 filter, CRC32 block check) per GPU, "
                     "host API only (container walk on the host, K1 decode + K3 CRC on the GPU)"),
@@ -62,6 +65,9 @@ def _one_stream(args):
     if kind == "xz":
         plain = corpus.mixed_text(seed, size)
         return corpus.xz_file(plain, block_size=1 << 18, check=corpus.CHECK_CRC32, dict_size=dict_size), plain
+    if kind == "stored":
+        plain = np.random.default_rng(seed).bytes(size)
+        return corpus.stored_lzma2(plain), plain
     if kind == "rep0":
         plain = bytes([seed & 0xFF]) * size
         return corpus.rep0_stress_lzma2(size, byte=seed & 0xFF), plain
@@ -270,7 +276,7 @@ def main():
     workers = max(1, min(32, ncpu // max(1, world)))
     distinct = a.distinct or (min(a.streams, 4096 if CFG["kind"] == "mixed" and CFG["stream_bytes"] <= 65536 else 1024)
                               if ncpu >= 16 else min(a.streams, 1024))
-    if CFG["kind"] == "rep0":
+    if CFG["kind"] in ("rep0", "stored"):
         distinct = min(distinct, 256)
 
     workload = CFG["name"].format(n=a.streams)
@@ -443,7 +449,8 @@ def main():
                     "api": "lzb_decode_batch (C ABI) with pinned host buffers"},
             "gpu_launches": kernels_per_step * a.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "lzb_decode_kernel", "peak_source": peak_src,
+                         "traffic": traffic,
+                         "kernel": "lzb_decode_wide_kernel" if CFG["kind"] in ("rep0", "stored") else "lzb_decode_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": in_bytes + out_bytes, "kernel_ms": kernel_ms},
             "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": effective_cores(cpu_used, ncap, quota), "kind": "port",
                              "sample": f"{cpu_k} of {n} streams ({cpu_total} B out), one stream per task, best of thread "

@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblzma_b200.so")
+# LZMA_B200_LIB: another build of the same library (kernel experiments: tools/variants.py); default = the in-tree build
+LIB_PATH = os.environ.get("LZMA_B200_LIB") or os.path.join(_HERE, "liblzma_b200.so")
 
 FMT_LZMA, FMT_LZMA2, FMT_XZ = 0, 1, 2
 RC_OK, RC_BAD_ARG, RC_NO_DEVICE, RC_CUDA, RC_OOM = 0, -1, -2, -3, -4
@@ -49,7 +50,13 @@ def load():
         raise NativeLibraryMissing(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(lzma_rs_b200 has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    _lib = bind(LIB_PATH)
+    return _lib
+
+
+def bind(path):
+    """dlopen one build of the library and declare the C ABI's argument types (tools/kbench.py binds several)."""
+    lib = C.CDLL(path)
     vp, u64p = C.c_void_p, C.c_void_p
     lib.lzb_create.argtypes = [C.POINTER(vp), C.c_int]
     lib.lzb_destroy.argtypes = [vp]
@@ -70,7 +77,6 @@ def load():
     lib.lzb_crc_device.argtypes = [vp, vp, u64p, u64p, C.c_uint32, vp, vp, vp]
     lib.lzb_format_error.argtypes = [C.POINTER(Status), C.c_char_p, C.c_size_t]
     lib.lzb_format_error.restype = C.c_size_t
-    _lib = lib
     return lib
 
 

@@ -293,26 +293,44 @@ LZB_DEV void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
     for (uint32_t k = 0; k < n; k++) dst[k] = src[k];  // 1-lane emulation: plain copy
     return;
 #endif
-    uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
+#ifdef __CUDACC__
+    // dst is brought to a 16-byte boundary; the body stores aligned 16-byte vectors (512 B per warp instruction),
+    // each assembled from five aligned source words with funnel shifts.  Four vectors per lane are loaded before the
+    // first is stored (SRC_CONST loads are non-coherent, so nothing orders them behind the stores): 80 B per lane,
+    // 2.5 KB per warp, ~70 KB per SM in flight -- what a copy needs to cover HBM latency at 28 warps per SM.
+    uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
     if (head > n) head = n;
     if ((uint32_t)lane < head) dst[lane] = SRC_CONST ? LZB_LDG(src + lane) : src[lane];
-    const uint32_t words = (n - head) >> 2;
-#ifdef __CUDACC__
+    const uint32_t vecs = (n - head) >> 4;
     const uint8_t* s0 = src + head;
     const uint32_t sh = ((uint32_t)(uintptr_t)s0 & 3u) * 8u;
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - ((uintptr_t)s0 & 3u));
-    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-    for (uint32_t k = lane; k < words; k += LZB_LANES) {
-        const uint32_t lo = SRC_CONST ? __ldg(sw + k) : sw[k];
-        // the second word is only dereferenced when the source is misaligned (it may lie past the last source byte)
-        const uint32_t hi = sh ? (SRC_CONST ? __ldg(sw + k + 1) : sw[k + 1]) : 0u;
-        dw[k] = __funnelshift_r(lo, hi, sh);
+    uint4* dv = reinterpret_cast<uint4*>(dst + head);
+    constexpr int U = 4;
+    for (uint32_t base = 0; base < vecs; base += U * LZB_LANES) {
+        uint32_t w[U][5];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t k = base + u * LZB_LANES + lane;
+            if (k < vecs) {
+                const uint32_t* q = sw + 4u * k;
+#pragma unroll
+                for (int j = 0; j < 4; j++) w[u][j] = SRC_CONST ? __ldg(q + j) : q[j];
+                // the fifth word is only dereferenced when the source is misaligned (it may lie past the last byte)
+                w[u][4] = sh ? (SRC_CONST ? __ldg(q + 4) : q[4]) : 0u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t k = base + u * LZB_LANES + lane;
+            if (k < vecs)
+                dv[k] = make_uint4(__funnelshift_r(w[u][0], w[u][1], sh), __funnelshift_r(w[u][1], w[u][2], sh),
+                                   __funnelshift_r(w[u][2], w[u][3], sh), __funnelshift_r(w[u][3], w[u][4], sh));
+        }
     }
-#else
-    for (uint32_t k = 0; k < words * 4; k++) dst[head + k] = src[head + k];
-#endif
-    const uint32_t done = head + words * 4u;
+    const uint32_t done = head + vecs * 16u;
     if (done + (uint32_t)lane < n) dst[done + lane] = SRC_CONST ? LZB_LDG(src + done + lane) : src[done + lane];
+#endif
 }
 
 // Warp fill of n bytes with one byte value (a dist == 1 match: the run-length case, BASELINE config 5).
