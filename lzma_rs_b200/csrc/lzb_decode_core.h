@@ -31,6 +31,8 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t, uint32_t) { return __bu
 static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { return (hi << s) | (lo >> (32 - s)); }
 #endif
 
+#define LZB_PRAGMA_(x) _Pragma(#x)
+#define LZB_PRAGMA(x) LZB_PRAGMA_(x)
 #define RC_TOP (1u << 24)
 #define LZB_UNLIKELY(x) __builtin_expect(!!(x), 0)
 
@@ -265,9 +267,25 @@ LZB_DEV uint32_t rev_bits(uint32_t v, uint32_t nb) {  // the low nb bits of v, r
 #endif
 }
 
+// Every probability = 0x400 (lzma.rs:188-214).  T is 16-byte aligned and n_u16 a multiple of 8 (all table sizes are).
+// One rolled loop of 16-byte stores: this runs once per stream / state reset, and K1's code must stay inside the
+// 32 KB instruction cache (an unrolled fill at four call sites cost 178 instructions).
 LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
+#if defined(__CUDACC__) && defined(LZB_FILL_OLD)
     uint32_t* T32 = reinterpret_cast<uint32_t*>(T);
-    for (uint32_t i = lane; i < n_u16 / 2; i += LZB_LANES) T32[i] = 0x04000400u;  // every prob = 0x400 (lzma.rs:188-214)
+    for (uint32_t i = lane; i < n_u16 / 2; i += LZB_LANES) T32[i] = 0x04000400u;
+#elif defined(__CUDACC__)
+    uint4* T4 = reinterpret_cast<uint4*>(T);
+    const uint4 v = make_uint4(0x04000400u, 0x04000400u, 0x04000400u, 0x04000400u);
+#ifndef LZB_FILL_UNROLL
+#define LZB_FILL_UNROLL 2
+#endif
+    LZB_PRAGMA(unroll LZB_FILL_UNROLL)
+    for (uint32_t i = lane; i < n_u16 / 8; i += LZB_LANES) T4[i] = v;
+#else
+    (void)lane;
+    for (uint32_t i = 0; i < n_u16; i++) T[i] = 0x400;
+#endif
     LZB_SYNCWARP();
 }
 
@@ -286,8 +304,16 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
 // bring dst to a 4-byte boundary, the body stores aligned 32-bit words assembled from two aligned source words with
 // a funnel shift (128 B per warp instruction instead of 32), the tail goes byte-wise.  SRC_CONST: the source is the
 // read-only input blob (ld.global.nc).
+// Deliberately NOT inlined: its 20 live registers, inlined into decode_item, push ptxas into allocating the decode
+// state in uniform registers, and the whole bit loop then runs on the (slow, single) uniform datapath -- measured 44 %
+// slower (tools/check_sass.py guards the build against that flip).  The call happens once per stored chunk.
 template <bool SRC_CONST>
-LZB_DEV void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+#if defined(__CUDACC__) && defined(LZB_COPY_NOINLINE)
+__device__ __noinline__ void warp_copy(
+#else
+LZB_DEV void warp_copy(
+#endif
+uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
 #ifndef __CUDACC__
     (void)lane;
     for (uint32_t k = 0; k < n; k++) dst[k] = src[k];  // 1-lane emulation: plain copy
@@ -306,7 +332,10 @@ LZB_DEV void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
     const uint32_t sh = ((uint32_t)(uintptr_t)s0 & 3u) * 8u;
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - ((uintptr_t)s0 & 3u));
     uint4* dv = reinterpret_cast<uint4*>(dst + head);
-    constexpr int U = 4;
+#ifndef LZB_COPY_U
+#define LZB_COPY_U 2
+#endif
+    constexpr int U = LZB_COPY_U;
     for (uint32_t base = 0; base < vecs; base += U * LZB_LANES) {
         uint32_t w[U][5];
 #pragma unroll
@@ -386,10 +415,10 @@ LZB_DEV void mirror_to_host(const uint8_t* out, uint8_t* hout, uint32_t from, ui
 // MainTab / PlainTab / MatchedTab: handle types of the small tables and the two literal parts.
 // MIRROR: completed 4 KiB pages of the output are copied to the caller's pinned host buffer (itp->host_out) while
 //         the stream is still decoding, so that the host API needs no device-to-host copy after the kernel.
-// WIDE  : word-wide stored-chunk copies and run fills.  Kept out of the default instantiation because K1 sits at the
-//         edge of the instruction cache: every extra path costs the common case ~1 % even when it never executes
-//         (measured); the host selects the WIDE kernels for batches with stored chunks or extreme expansion ratios.
-template <bool LIT_GLOBAL, bool MIRROR, bool WIDE, class MainTab, class PlainTab, class MatchedTab>
+// WIDE  : 1 = word-wide run fills, 2 = 16-byte vector stored-chunk copies.  Kept out of the default instantiation (0)
+//         because K1 sits at the edge of the instruction cache: every extra path costs the common case 1-6 % even when
+//         it never executes (measured); the host selects the variant per batch from the framing scan.
+template <bool LIT_GLOBAL, bool MIRROR, int WIDE, class MainTab, class PlainTab, class MatchedTab>
 LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t* __restrict__ in_blob,
                                   uint8_t* out_blob, uint16_t* T, uint16_t* gws, const MainTab tab,
                                   const PlainTab plain, const MatchedTab matched, const LzbKC kc, uint32_t tab_lclp,
@@ -475,7 +504,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                 }
                 if (LZB_UNLIKELY(stream_lim - d.p < n)) FAIL(LZB_E_L2_STORED_EOF, n, 0);
                 if (LZB_UNLIKELY(cap - opos < n)) FAIL(LZB_E_CAPACITY, (uint64_t)opos + n, 0);
-                if (WIDE) {
+                if (WIDE == 2) {
                     warp_copy<true>(out + opos, inb + d.p, n, lane);
                 } else {
                     for (uint32_t i = lane; i < n; i += LZB_LANES) out[opos + i] = LZB_LDG(inb + d.p + i);
@@ -599,8 +628,6 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 #ifndef LZB_LIT_UNROLL
 #define LZB_LIT_UNROLL 8
 #endif
-#define LZB_PRAGMA_(x) _Pragma(#x)
-#define LZB_PRAGMA(x) LZB_PRAGMA_(x)
                     LZB_PRAGMA(unroll LZB_LIT_UNROLL)
                     for (int i = 0; i < 8; i++) {
                         uint32_t np;
@@ -724,7 +751,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     // lane-dependent fill and loses the warp-uniformity of prev_byte downstream)
                     prev_byte = src[i_last % dist];
                     match_byte = src[i_next % dist];
-                    if (WIDE && dist == 1) {  // run of one byte (BASELINE config 5): word-wide fill
+                    if (WIDE == 1 && dist == 1) {  // run of one byte (BASELINE config 5): word-wide fill
                         warp_fill(dst, prev_byte, mlen, lane);
                     } else {
                         for (uint32_t i = lane; i < mlen; i += LZB_LANES) dst[i] = src[i % dist];

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "lzb_plan.h"
+#include "lzb_sched.h"
 #include "lzb_types.h"
 
 struct LzbCrcRange {
@@ -18,21 +19,23 @@ struct LzbCrcRange {
 };
 #define CRC_SEG 4096u
 
-extern "C" __global__ void lzb_decode_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
-                                             LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long,
-                                             const LzbKC);
-extern "C" __global__ void lzb_decode_mirror_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
-                                                    LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*,
-                                                    unsigned long long, const LzbKC);
-extern "C" __global__ void lzb_decode_wide_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
-                                                  LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*,
-                                                  unsigned long long, const LzbKC);
-extern "C" __global__ void lzb_decode_wide_mirror_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*,
-                                                         uint8_t*, LzbResult*, unsigned int*, uint32_t, uint32_t,
-                                                         uint16_t*, unsigned long long, const LzbKC);
-extern "C" __global__ void lzb_decode_biglit_kernel(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*,
-                                                    LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*,
-                                                    unsigned long long, const LzbKC);
+#define LZB_K1_PROTO(NAME)                                                                                       \
+    extern "C" __global__ void NAME(const LzbItem*, const uint32_t*, uint32_t, uint32_t, const uint8_t*, uint8_t*, \
+                                    LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long, \
+                                    const LzbKC)
+LZB_K1_PROTO(lzb_decode_kernel);
+LZB_K1_PROTO(lzb_decode_mirror_kernel);
+LZB_K1_PROTO(lzb_decode_fill_kernel);
+LZB_K1_PROTO(lzb_decode_fill_mirror_kernel);
+LZB_K1_PROTO(lzb_decode_copy_kernel);
+LZB_K1_PROTO(lzb_decode_copy_mirror_kernel);
+LZB_K1_PROTO(lzb_decode_sched_kernel);
+LZB_K1_PROTO(lzb_decode_sched_mirror_kernel);
+LZB_K1_PROTO(lzb_decode_sched_fill_kernel);
+LZB_K1_PROTO(lzb_decode_sched_fill_mirror_kernel);
+LZB_K1_PROTO(lzb_decode_sched_copy_kernel);
+LZB_K1_PROTO(lzb_decode_sched_copy_mirror_kernel);
+LZB_K1_PROTO(lzb_decode_biglit_kernel);
 extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, const uint64_t*, const uint64_t*, uint32_t,
                                            LzbItem*, LzbScan*);
 extern "C" __global__ void lzb_crc_partial_kernel(const uint8_t*, const LzbCrcRange*, const uint32_t*, uint64_t,
@@ -73,7 +76,7 @@ struct lzb_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     int smem_optin = 0;
-    int smem_configured[4] = {-1, -1, -1, -1}, smem_configured_big = -1;
+    int smem_configured[12] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1}, smem_configured_big = -1;
     char err[320] = {0};
     std::mutex mu;
     DevBuf d_in, d_out, d_items, d_results, d_order, d_counter, d_scan, d_off, d_crc_ranges, d_crc_segmap, d_crc_part32,
@@ -118,21 +121,26 @@ LaunchCfg decode_config(const lzb_ctx* ctx, uint32_t n, uint32_t lclp) {
 struct DecodePlan {
     std::vector<uint32_t> order_small, order_big;  // item indices, longest compressed stream first
     LaunchCfg cfg_small{}, cfg_big{};
+    uint32_t n_small = 0;         // streams of the first launch (order_small may also hold LZB_ORDER_PARK entries)
+    uint32_t n_static = 0;        // leading order_small entries that are pre-assigned first items (lzb_sched.h)
+    uint32_t parked = 0;          // warps the placement keeps out of the launch
     uint64_t big_stride_u16 = 0;  // workspace u16 per warp
-    bool wide = false;            // use the WIDE kernels (word-wide stored-chunk copies / run fills)
+    int wide = 0;                 // K1 variant: 0 lean, 1 word-wide run fills, 2 vector stored-chunk copies
 };
 
-void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lzma2_lclp_hint, uint32_t hints,
+void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lzma2_lclp_hint, uint64_t stored_bytes,
                DecodePlan* p) {
     uint32_t lclp_small = 0, lclp_big = 0;
-    // WIDE kernels when the scan saw stored chunks, or when the batch expands so much (> 16x) that it must be long
-    // runs; the default kernels are ~3 % faster on everything else (instruction-cache footprint)
+    // K1 variants beside the lean default (which is 3-6 % faster on everything else: instruction-cache footprint):
+    // vector stored-chunk copies when stored chunks carry >= 80 % of the batch's output (break-even measured at ~5x the
+    // range-coded bytes: C3 with 3 stored chunks in 8 192 streams lost 6 % to the copy code it never needed), word-wide
+    // run fills when the batch expands so much (> 16x) that it must be long runs
     uint64_t in_sum = 0, cap_sum = 0;
     for (uint32_t i = 0; i < n; i++) {
         in_sum += items[i].in_len;
         cap_sum += items[i].out_cap;
     }
-    p->wide = (hints & lzb::LZB_HINT_STORED) || cap_sum > 16 * in_sum;
+    p->wide = stored_bytes * 5 >= cap_sum * 4 && stored_bytes ? 2 : cap_sum > 16 * in_sum ? 1 : 0;
     p->order_small.clear();
     p->order_big.clear();
     for (uint32_t i = 0; i < n; i++) {
@@ -149,7 +157,21 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
     auto by_len = [&](uint32_t a, uint32_t b) { return items[a].in_len > items[b].in_len; };
     std::stable_sort(p->order_small.begin(), p->order_small.end(), by_len);
     std::stable_sort(p->order_big.begin(), p->order_big.end(), by_len);
-    p->cfg_small = decode_config(ctx, (uint32_t)p->order_small.size(), lclp_small);
+    p->n_small = (uint32_t)p->order_small.size();
+    p->cfg_small = decode_config(ctx, p->n_small, lclp_small);
+    p->n_static = p->parked = 0;
+    if (p->n_small > (uint32_t)ctx->sm_count * p->cfg_small.warps) {
+        // several rounds: streams that would still be running when the queue is empty get less crowded SMs
+        std::vector<double> work(n);
+        for (uint32_t i = 0; i < n; i++) work[i] = (double)items[i].in_len;
+        lzb_sched::Plan sp = lzb_sched::plan(p->order_small, work, (uint32_t)ctx->sm_count, p->cfg_small.warps);
+        if (sp.throttled) {
+            p->order_small.swap(sp.order);
+            p->n_static = sp.n_static;
+            p->parked = sp.parked;
+            p->cfg_small.grid = sp.grid;
+        }
+    }
     if (!p->order_big.empty()) {
         LaunchCfg& c = p->cfg_big;
         c.lclp = lclp_big;
@@ -177,18 +199,22 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         // per-warp global workspace for the matched-literal columns (L2-resident: 8 KiB per warp at lc+lp = 3)
         const uint64_t mstride = lzb_matched_u16(c.lclp);
         CUDA_TRY(ctx, ctx->d_matchws.ensure((size_t)c.grid * c.warps * mstride * 2));
-        // variants: [mirror][wide]; mirror = host API with a pinned output buffer (finished pages streamed to the host)
-        typedef void (*kern_t)(const LzbItem*, const uint32_t*, uint32_t, const uint8_t*, uint8_t*, LzbResult*,
+        // variants: [sched][mirror][lean | fill | copy]; mirror = host API with a pinned output buffer (finished pages
+        // streamed to the host); sched = the launch carries a placement plan (lzb_sched.h)
+        typedef void (*kern_t)(const LzbItem*, const uint32_t*, uint32_t, uint32_t, const uint8_t*, uint8_t*, LzbResult*,
                                unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long, const LzbKC);
-        static const kern_t kernels[4] = {lzb_decode_kernel, lzb_decode_wide_kernel, lzb_decode_mirror_kernel,
-                                          lzb_decode_wide_mirror_kernel};
-        const int v = (mirror ? 2 : 0) + (p.wide ? 1 : 0);
+        static const kern_t kernels[12] = {
+            lzb_decode_kernel,              lzb_decode_fill_kernel,              lzb_decode_copy_kernel,
+            lzb_decode_mirror_kernel,       lzb_decode_fill_mirror_kernel,       lzb_decode_copy_mirror_kernel,
+            lzb_decode_sched_kernel,        lzb_decode_sched_fill_kernel,        lzb_decode_sched_copy_kernel,
+            lzb_decode_sched_mirror_kernel, lzb_decode_sched_fill_mirror_kernel, lzb_decode_sched_copy_mirror_kernel};
+        const int v = (p.n_static ? 6 : 0) + (mirror ? 3 : 0) + p.wide;
         if (smem > ctx->smem_configured[v]) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[v], cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
             ctx->smem_configured[v] = ctx->smem_optin;
         }
-        kernels[v]<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, d_in_base, d_out_base, d_results, d_counter,
-                                                      c.lclp, c.warp_bytes, ctx->d_matchws.as<uint16_t>(), mstride, kc);
+        kernels[v]<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, p.n_static, d_in_base, d_out_base, d_results,
+                                                      d_counter, c.lclp, c.warp_bytes, ctx->d_matchws.as<uint16_t>(), mstride, kc);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     if (nb) {
@@ -200,7 +226,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
             ctx->smem_configured_big = ctx->smem_optin;
         }
         CUDA_TRY(ctx, ctx->d_litws.ensure((size_t)c.grid * c.warps * p.big_stride_u16 * 2));
-        lzb_decode_biglit_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order + ns, nb, d_in_base, d_out_base,
+        lzb_decode_biglit_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order + ns, nb, 0u, d_in_base, d_out_base,
                                                                     d_results, d_counter + 1, c.lclp, c.warp_bytes,
                                                                     ctx->d_litws.as<uint16_t>(), p.big_stride_u16, kc);
         CUDA_TRY(ctx, cudaGetLastError());
@@ -224,8 +250,8 @@ class CudaExecutor : public lzb::Executor {
         : ctx_(ctx), s_(s), in_(d_in_base), out_(d_out_base), hmirror_(host_mirror) {}
     bool all_mirrored() const { return hmirror_ != nullptr && !unmirrored_; }
 
-    int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint32_t hints, LzbResult* results) override {
-        int rc = run(items, n, max_lclp, hints, results);
+    int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint64_t stored_bytes, LzbResult* results) override {
+        int rc = run(items, n, max_lclp, stored_bytes, results);
         if (rc != LZB_RC_OK) return rc;
         // the framing scan can under-estimate lc+lp on malformed LZMA2 streams: rerun just those with the maximum
         std::vector<uint32_t> redo;
@@ -237,7 +263,7 @@ class CudaExecutor : public lzb::Executor {
             std::vector<LzbItem> sub(redo.size());
             std::vector<LzbResult> subres(redo.size());
             for (size_t k = 0; k < redo.size(); k++) sub[k] = items[redo[k]];
-            rc = run(sub.data(), (uint32_t)sub.size(), 4, hints, subres.data());
+            rc = run(sub.data(), (uint32_t)sub.size(), 4, stored_bytes, subres.data());
             if (rc != LZB_RC_OK) return rc;
             for (size_t k = 0; k < redo.size(); k++) results[redo[k]] = subres[k];
         }
@@ -300,10 +326,10 @@ class CudaExecutor : public lzb::Executor {
     }
 
    private:
-    int run(const LzbItem* items, uint32_t n, uint32_t lclp_hint, uint32_t hints, LzbResult* results) {
+    int run(const LzbItem* items, uint32_t n, uint32_t lclp_hint, uint64_t stored_bytes, LzbResult* results) {
         lzb_ctx* ctx = ctx_;
         DecodePlan plan;
-        make_plan(ctx, items, n, lclp_hint, hints, &plan);
+        make_plan(ctx, items, n, lclp_hint, stored_bytes, &plan);
         CUDA_TRY(ctx, ctx->d_items.ensure(n * sizeof(LzbItem)));
         CUDA_TRY(ctx, ctx->d_results.ensure(n * sizeof(LzbResult)));
         CUDA_TRY(ctx, ctx->d_counter.ensure(64));
@@ -489,12 +515,13 @@ extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, 
     B_TRY(cudaMemcpyAsync(scan.data(), b->d_scan.p, n * sizeof(LzbScan), cudaMemcpyDeviceToHost, s));
     B_TRY(cudaMemcpyAsync(b->items.data(), b->d_items.p, n * sizeof(LzbItem), cudaMemcpyDeviceToHost, s));
     B_TRY(cudaStreamSynchronize(s));
-    uint32_t lclp = 0, hints = 0;
+    uint32_t lclp = 0;
+    uint64_t stored_bytes = 0;
     for (uint32_t i = 0; i < n; i++) {
         if (b->items[i].kind == LZB_ITEM_LZMA2) lclp = std::max<uint32_t>(lclp, scan[i].max_lclp);
-        if (scan[i].flags & 2) hints |= lzb::LZB_HINT_STORED;
+        stored_bytes += scan[i].stored;
     }
-    make_plan(ctx, b->items.data(), n, lclp, hints, &b->plan);
+    make_plan(ctx, b->items.data(), n, lclp, stored_bytes, &b->plan);
     if (upload_order(ctx, s, b->plan, b->d_order) != LZB_RC_OK) return fail(LZB_RC_CUDA);
     B_TRY(cudaStreamSynchronize(s));
     *out = b;

@@ -24,10 +24,14 @@
 // K1 launcher
 // ------------------------------------------------------------------------------------------------
 // Persistent kernels: warps pull stream indices (pre-sorted longest first by the host) from a counter.
-template <bool LIT_GLOBAL, bool MIRROR, bool WIDE>
+// SCHED: the launch carries a placement plan (lzb_sched.h): order[0 .. n_static) holds the first item of every warp
+// (n_static = gridDim.x * warps), LZB_ORDER_PARK there = this warp stays out of the launch; order[n_static ..) is the
+// dynamic queue.  A separate instantiation because K1's hot loop is sensitive to code layout: the same loop head in
+// the default kernels costs batches that need no plan 0.5-3 % (measured, tools/kbench.py).
+template <bool LIT_GLOBAL, bool MIRROR, int WIDE, bool SCHED>
 __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order,
-                                            uint32_t n_items, const uint8_t* __restrict__ in_blob, uint8_t* out_blob,
-                                            LzbResult* results, unsigned int* counter, uint32_t tab_lclp,
+                                            uint32_t n_items, uint32_t n_static, const uint8_t* __restrict__ in_blob,
+                                            uint8_t* out_blob, LzbResult* results, unsigned int* counter, uint32_t tab_lclp,
                                             uint32_t warp_smem_bytes, uint16_t* ws, unsigned long long ws_stride_u16,
                                             const LzbKC& kc) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -40,12 +44,19 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
     const TabSm tab = {(uint32_t)__cvta_generic_to_shared(T)};
     // this warp's slice of the global workspace -- indexed with the broadcast (provably uniform) warp index as well
     uint16_t* gws = ws + ((unsigned long long)blockIdx.x * (blockDim.x >> 5) + (unsigned)warp) * ws_stride_u16;
+    bool first = SCHED;
     for (;;) {
         unsigned int slot = 0;
-        if (lane == 0) slot = atomicAdd(counter, 1u);
-        slot = __shfl_sync(FULL_MASK, slot, 0);
+        if (SCHED && first) {
+            slot = blockIdx.x * (blockDim.x >> 5) + (unsigned)warp;
+            first = false;
+        } else {
+            if (lane == 0) slot = (SCHED ? n_static : 0u) + atomicAdd(counter, 1u);
+            slot = __shfl_sync(FULL_MASK, slot, 0);
+        }
         if (slot >= n_items) break;
-        const uint32_t idx = order ? order[slot] : slot;
+        const uint32_t idx = order[slot];
+        if (SCHED && idx == LZB_ORDER_PARK) break;
         if (LIT_GLOBAL) {  // whole literal table in the global workspace (reference layout)
             const TabPtr plain = {gws}, matched = {gws + 0x100};
             decode_item<true, MIRROR, WIDE>(items + idx, in_blob, out_blob, T, gws, tab, plain, matched, kc, tab_lclp, results + idx, lane);
@@ -58,49 +69,35 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
     }
 }
 
-extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1)
-    lzb_decode_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
-                      const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
-                      unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
-                      unsigned long long ws_stride_u16, const __grid_constant__ LzbKC kc) {
-    decode_loop<false, false, false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
-                              ws_stride_u16, kc);
-}
-
-// Host-API variant: identical decode, plus the mirror of finished output pages into the caller's pinned host buffer.
-extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1)
-    lzb_decode_mirror_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
-                             const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
-                             unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
-                             unsigned long long ws_stride_u16, const __grid_constant__ LzbKC kc) {
-    decode_loop<false, true, false>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
-                             ws_stride_u16, kc);
-}
-
-// WIDE variants (word-wide stored-chunk copies and run fills) of the two kernels above.
 #define LZB_KERNEL_ARGS                                                                                              \
-    const LzbItem *__restrict__ items, const uint32_t *__restrict__ order, uint32_t n_items,                         \
+    const LzbItem *__restrict__ items, const uint32_t *__restrict__ order, uint32_t n_items, uint32_t n_static,      \
         const uint8_t *__restrict__ in_blob, uint8_t *out_blob, LzbResult *results, unsigned int *counter,           \
         uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t *ws, unsigned long long ws_stride_u16,                 \
         const __grid_constant__ LzbKC kc
-extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1) lzb_decode_wide_kernel(LZB_KERNEL_ARGS) {
-    decode_loop<false, false, true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes,
-                                    ws, ws_stride_u16, kc);
-}
-extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1) lzb_decode_wide_mirror_kernel(LZB_KERNEL_ARGS) {
-    decode_loop<false, true, true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes,
-                                   ws, ws_stride_u16, kc);
-}
+#define LZB_KERNEL_PASS items, order, n_items, n_static, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws, ws_stride_u16, kc
+#define LZB_DEFINE_K1(NAME, LIT_GLOBAL, MIRROR, WIDE, SCHED)                                               \
+    extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1) NAME(LZB_KERNEL_ARGS) {          \
+        decode_loop<LIT_GLOBAL, MIRROR, WIDE, SCHED>(LZB_KERNEL_PASS);                                    \
+    }
 
+// MIRROR: host-API variant, finished output pages are mirrored into the caller's pinned host buffer.
+// WIDE  : 0 lean; 1 ("fill") word-wide run fills for batches that expand > 16x; 2 ("copy") 16-byte vector copies of
+//         stored chunks for batches that are mostly stored chunks.  Selected by the host from the framing scan.
+// SCHED : launch with a placement plan (above).
+LZB_DEFINE_K1(lzb_decode_kernel, false, false, 0, false)
+LZB_DEFINE_K1(lzb_decode_mirror_kernel, false, true, 0, false)
+LZB_DEFINE_K1(lzb_decode_fill_kernel, false, false, 1, false)
+LZB_DEFINE_K1(lzb_decode_fill_mirror_kernel, false, true, 1, false)
+LZB_DEFINE_K1(lzb_decode_copy_kernel, false, false, 2, false)
+LZB_DEFINE_K1(lzb_decode_copy_mirror_kernel, false, true, 2, false)
+LZB_DEFINE_K1(lzb_decode_sched_kernel, false, false, 0, true)
+LZB_DEFINE_K1(lzb_decode_sched_mirror_kernel, false, true, 0, true)
+LZB_DEFINE_K1(lzb_decode_sched_fill_kernel, false, false, 1, true)
+LZB_DEFINE_K1(lzb_decode_sched_fill_mirror_kernel, false, true, 1, true)
+LZB_DEFINE_K1(lzb_decode_sched_copy_kernel, false, false, 2, true)
+LZB_DEFINE_K1(lzb_decode_sched_copy_mirror_kernel, false, true, 2, true)
 // .lzma streams with lc+lp > 4: literal table in a per-warp global workspace (ws + warp_id * ws_stride_u16).
-extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1)
-    lzb_decode_biglit_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order, uint32_t n_items,
-                             const uint8_t* __restrict__ in_blob, uint8_t* out_blob, LzbResult* results,
-                             unsigned int* counter, uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t* ws,
-                             unsigned long long ws_stride_u16, const __grid_constant__ LzbKC kc) {
-    decode_loop<true, true, true>(items, order, n_items, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws,
-                            ws_stride_u16, kc);
-}
+LZB_DEFINE_K1(lzb_decode_biglit_kernel, true, true, 1, false)
 
 // ------------------------------------------------------------------------------------------------
 // K2: per-stream scan -> work items (+ size summary).  One thread per stream.
@@ -132,6 +129,7 @@ extern "C" __global__ void lzb_scan_kernel(int fmt, lzb_options opt, const uint8
     sc.flags = 0;
     sc.max_lclp = 0;
     sc.pad[0] = sc.pad[1] = sc.pad[2] = 0;
+    sc.stored = 0;
 
     if (fmt == LZB_FMT_LZMA) {  // LzmaParams::read_header, lzma.rs:96-161
         const uint32_t hdr = opt.unpacked_mode == LZB_UNPACKED_USE_PROVIDED ? 5u : 13u;
@@ -192,6 +190,7 @@ extern "C" __global__ void lzb_scan_kernel(int fmt, lzb_options opt, const uint8
                 if (len - q < nb) break;
                 q += nb;
                 total += nb;
+                sc.stored += nb;
                 continue;
             }
             if (status < 0x80) break;

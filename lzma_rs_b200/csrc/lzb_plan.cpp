@@ -68,13 +68,13 @@ Lzma2Scan scan_lzma2(const uint8_t* p, uint64_t len) {
             break;
         }
         if (status == 1 || status == 2) {
-            s.has_stored = true;
             if (len - q < 2) break;
             uint64_t nb = (((uint32_t)p[q] << 8) | p[q + 1]) + 1;
             q += 2;
             if (len - q < nb) break;
             q += nb;
             s.unpacked += nb;
+            s.stored += nb;
             continue;
         }
         if (status < 0x80) break;
@@ -159,7 +159,8 @@ void plan_lzma2(const uint8_t* p, uint64_t len, uint64_t base_off, LzbItem* it, 
     Lzma2Scan s = scan_lzma2(p, len);
     memset(sc, 0, sizeof *sc);
     sc->unpacked = s.unpacked;
-    sc->flags = (s.well_formed ? 1u : 0u) | (s.has_stored ? 2u : 0u);
+    sc->flags = (s.well_formed ? 1u : 0u) | (s.stored ? 2u : 0u);
+    sc->stored = s.stored;
     sc->max_lclp = (uint8_t)s.max_lclp;
     if (len > 0xFFFFE000ull) preset(it, LZB_E_UNSUPPORTED);
 }
@@ -408,7 +409,7 @@ static uint64_t check_len(int check) {
 // One stage of a chained-filter block (xz.rs:240-249): filter j decodes the previous filter's output.  Stage 0 reads
 // the file payload; every stage but the last writes to device scratch; the last writes to the file's output region.
 static int plan_chain_stage(Executor& ex, XzFile& f, const BlockPlan& proto, std::vector<LzbItem>& items,
-                            uint32_t* max_lclp, uint32_t* hints) {
+                            uint32_t* max_lclp, uint64_t* stored) {
     BlockPlan bp = proto;
     const uint32_t j = f.chain_next;
     const bool last = j + 1 == bp.bh.nfilters;
@@ -421,7 +422,7 @@ static int plan_chain_stage(Executor& ex, XzFile& f, const BlockPlan& proto, std
     const uint64_t src_len = j == 0 ? f.len - bp.bh.payload : f.chain_in_len;
     Lzma2Scan sc = scan_lzma2(src, src_len);
     *max_lclp = std::max(*max_lclp, sc.max_lclp);
-    if (sc.has_stored) *hints |= LZB_HINT_STORED;
+    *stored += sc.stored;
     LzbItem it;
     if (j == 0) {
         item_defaults(&it, f.in_base + bp.bh.payload, src_len);
@@ -449,7 +450,7 @@ static int plan_chain_stage(Executor& ex, XzFile& f, const BlockPlan& proto, std
     return LZB_RC_OK;
 }
 
-static int plan_file(Executor& ex, XzFile& f, std::vector<LzbItem>& items, uint32_t* max_lclp, uint32_t* hints) {
+static int plan_file(Executor& ex, XzFile& f, std::vector<LzbItem>& items, uint32_t* max_lclp, uint64_t* stored) {
     uint64_t pos = f.pos, out_rel = f.out_pos;
     f.plan.clear();
     f.terminal = T_NONE;
@@ -473,11 +474,11 @@ static int plan_file(Executor& ex, XzFile& f, std::vector<LzbItem>& items, uint3
         }
         if (bp.bh.nfilters > 1) {  // chained filters: the block runs alone, one filter per round
             if (!f.plan.empty()) break;
-            return plan_chain_stage(ex, f, bp, items, max_lclp, hints);
+            return plan_chain_stage(ex, f, bp, items, max_lclp, stored);
         }
         Lzma2Scan sc = scan_lzma2(f.p + bp.bh.payload, f.len - bp.bh.payload);
         *max_lclp = std::max(*max_lclp, sc.max_lclp);
-        if (sc.has_stored) *hints |= LZB_HINT_STORED;
+        *stored += sc.stored;
         bp.pred_packed = sc.packed;
         bp.pred_unpacked = sc.unpacked;
         bp.out_rel = out_rel;
@@ -607,18 +608,19 @@ int decode_xz_batch(Executor& ex, const uint8_t* in, const uint64_t* in_off, uin
     std::vector<uint64_t> c64;
     for (;;) {
         items.clear();
-        uint32_t max_lclp = 0, hints = 0;
+        uint32_t max_lclp = 0;
+        uint64_t stored = 0;
         bool any = false;
         for (auto& f : files) {
             if (f.done) continue;
             any = true;
-            int prc = plan_file(ex, f, items, &max_lclp, &hints);
+            int prc = plan_file(ex, f, items, &max_lclp, &stored);
             if (prc != LZB_RC_OK) return prc;
         }
         if (!any) break;
         results.assign(items.size(), LzbResult{});
         if (!items.empty()) {
-            int rc = ex.decode(items.data(), (uint32_t)items.size(), max_lclp, hints, results.data());
+            int rc = ex.decode(items.data(), (uint32_t)items.size(), max_lclp, stored, results.data());
             if (rc != LZB_RC_OK) return rc;
         }
         ranges.clear();
@@ -653,7 +655,8 @@ int decode_batch(Executor& ex, int fmt, const lzb_options* opt, const uint8_t* i
     if (fmt == LZB_FMT_XZ) return decode_xz_batch(ex, in, in_off, n, out_off, outs);
     std::vector<LzbItem> items(n);
     std::vector<LzbResult> results(n);
-    uint32_t max_lclp = 0, hints = 0;
+    uint32_t max_lclp = 0;
+        uint64_t stored = 0;
     for (uint32_t i = 0; i < n; i++) {
         LzbScan sc;
         const uint8_t* p = in + in_off[i];
@@ -665,10 +668,10 @@ int decode_batch(Executor& ex, int fmt, const lzb_options* opt, const uint8_t* i
         items[i].out_off = out_off[i];
         items[i].out_cap = out_off[i + 1] - out_off[i];
         if (items[i].kind != LZB_ITEM_PRESET) max_lclp = std::max<uint32_t>(max_lclp, sc.max_lclp);
-        if (sc.flags & 2) hints |= LZB_HINT_STORED;
+        stored += sc.stored;
     }
     if (n) {
-        int rc = ex.decode(items.data(), n, max_lclp, hints, results.data());
+        int rc = ex.decode(items.data(), n, max_lclp, stored, results.data());
         if (rc != LZB_RC_OK) return rc;
     }
     for (uint32_t i = 0; i < n; i++) {

@@ -10,8 +10,6 @@
 
 namespace lzb {
 
-enum { LZB_HINT_STORED = 1 };  // some stream has stored (uncompressed) LZMA2 chunks
-
 struct CrcRange {
     uint64_t off, len;  // into the output blob
 };
@@ -22,8 +20,9 @@ class Executor {
    public:
     virtual ~Executor() {}
     // Decode items[0..n) (offsets relative to the bound input / output blobs).  Returns LZB_RC_*.
-    // hints: LZB_HINT_* (what the framing scan saw; selects kernel variants, never changes results)
-    virtual int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint32_t hints, LzbResult* results) = 0;
+    // stored_bytes: output bytes the framing scan saw in stored (uncompressed) LZMA2 chunks; selects kernel variants,
+    // never changes results
+    virtual int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint64_t stored_bytes, LzbResult* results) = 0;
     // CRC-32 and CRC-64 of output-blob ranges.
     virtual int crc(const CrcRange* ranges, uint32_t n, uint32_t* crc32, uint64_t* crc64) = 0;
     // Device scratch of `bytes` bytes, returned as an offset in output-blob coordinates (valid until the executor dies):
@@ -39,7 +38,7 @@ struct Lzma2Scan {
     uint64_t packed = 0;    // bytes up to and including the 0x00 control byte
     uint32_t max_lclp = 0;
     bool well_formed = false;  // walk ended at a 0x00 control byte with valid framing
-    bool has_stored = false;   // at least one stored (uncompressed) chunk
+    uint64_t stored = 0;       // bytes of `unpacked` that sit in stored (uncompressed) chunks
 };
 Lzma2Scan scan_lzma2(const uint8_t* p, uint64_t len);
 

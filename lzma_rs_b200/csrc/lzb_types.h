@@ -29,6 +29,8 @@ enum { LZB_ITEM_LZMA = 0, LZB_ITEM_LZMA2 = 1, LZB_ITEM_PRESET = 2 };
 // out_off addresses device scratch outside the caller's output region (never mirrored to the host)
 enum { LZB_ITEM_F_IN_FROM_OUT = 1, LZB_ITEM_F_OUT_SCRATCH = 2 };
 #define LZB_UNKNOWN_SIZE 0xFFFFFFFFFFFFFFFFull
+// K1's order array: a warp whose pre-assigned first entry is this value takes no part in the launch (lzb_sched.h)
+#define LZB_ORDER_PARK 0xFFFFFFFFu
 
 // Per-stream result written by the decode kernel.
 struct LzbResult {
@@ -46,6 +48,7 @@ struct LzbScan {
     uint32_t flags;    // bit0: walk ended at a 0x00 control byte (well-formed framing); bit1: has a stored chunk
     uint8_t max_lclp;  // largest lc+lp any chunk (or the .lzma header) asks for
     uint8_t pad[3];
+    uint64_t stored;   // bytes of `unpacked` in stored chunks
 };
 
 // Probability-table layout in shared memory (u16 indices); see DESIGN.md "K1".

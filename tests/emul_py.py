@@ -14,7 +14,7 @@ _DIR = os.path.join(_HERE, "host_emulation")
 _SO = os.path.join(_DIR, "liblzb_emul.so")
 _SRCS = [os.path.join(_DIR, "emul.cpp"), os.path.join(_ROOT, "lzma_rs_b200", "csrc", "lzb_plan.cpp")]
 _DEPS = _SRCS + [os.path.join(_ROOT, "lzma_rs_b200", "csrc", f) for f in
-                 ("lzb_decode_core.h", "lzb_plan.h", "lzb_types.h")] + [os.path.join(_ROOT, "include", "lzma_b200.h")]
+                 ("lzb_decode_core.h", "lzb_plan.h", "lzb_types.h", "lzb_sched.h")] + [os.path.join(_ROOT, "include", "lzma_b200.h")]
 
 _lib = None
 
@@ -31,6 +31,10 @@ def lib():
         _lib.emul_decode_batch.argtypes = [C.c_int, C.POINTER(_native.Options), vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
         _lib.emul_scan_capacity.argtypes = [C.c_int, C.POINTER(_native.Options), vp, C.c_uint64]
         _lib.emul_scan_capacity.restype = C.c_uint64
+        _lib.emul_sched_plan.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
+        _lib.emul_sched_plan.restype = C.c_uint32
+        _lib.emul_sched_simulate.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_uint32]
+        _lib.emul_sched_simulate.restype = C.c_double
         _lib.lzb_format_error.argtypes = [C.POINTER(_native.Status), C.c_char_p, C.c_size_t]
         _lib.lzb_format_error.restype = C.c_size_t
     return _lib
@@ -70,3 +74,24 @@ def decode_batch(fmt, streams, opt=None, capacities=None):
         disp = "" if st[i]["code"] == 0 else _native.format_status(L, st[i])
         res.append(Result(out[o:o + int(out_len[i])].tobytes(), int(consumed[i]), st[i].copy(), disp))
     return res
+
+
+def sched_plan(work, sms=148, warps=28):
+    """lzb_sched::plan on a queue of per-stream work (longest first).  Returns (order, info dict)."""
+    L = lib()
+    w = np.ascontiguousarray(work, dtype=np.float64)
+    order = np.zeros(len(w) + sms * warps, dtype=np.uint32)
+    info = np.zeros(4, dtype=np.uint32)
+    model = np.zeros(2, dtype=np.float64)
+    k = L.emul_sched_plan(w.ctypes.data, len(w), sms, warps, order.ctypes.data, info.ctypes.data, model.ctypes.data)
+    return order[:k].copy(), dict(throttled=bool(info[0]), n_static=int(info[1]), grid=int(info[2]), parked=int(info[3]),
+                                  plain=float(model[0]), predicted=float(model[1]))
+
+
+def sched_simulate(work, counts=None, sms=148, warps=28):
+    L = lib()
+    w = np.ascontiguousarray(work, dtype=np.float64)
+    if counts is None:
+        return L.emul_sched_simulate(w.ctypes.data, len(w), None, 0, sms, warps)
+    c = np.ascontiguousarray(counts, dtype=np.uint32)
+    return L.emul_sched_simulate(w.ctypes.data, len(w), c.ctypes.data, len(c), sms, warps)

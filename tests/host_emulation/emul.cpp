@@ -14,7 +14,7 @@ namespace {
 class HostEmulExecutor : public lzb::Executor {
    public:
     HostEmulExecutor(const uint8_t* in, uint8_t* out) : in_(in), out_(out) {}
-    int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint32_t /*hints*/, LzbResult* results) override {
+    int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint64_t /*stored_bytes*/, LzbResult* results) override {
         const uint32_t small_lclp = max_lclp > 4 ? 4 : max_lclp;
         std::vector<uint16_t> T(lzb_table_u16(small_lclp) + 8), M(lzb_matched_u16(small_lclp) + 8), T4, M4, G;
         for (uint32_t i = 0; i < n; i++) {
@@ -82,7 +82,7 @@ class HostEmulExecutor : public lzb::Executor {
         const TabPtr tab = {T};
         const TabPtr plain = {BIG ? G : T + T_LIT};
         const TabPtr matched = {BIG ? G + 0x100 : G};
-        decode_item<BIG, false, true>(it, in_, out_, T, G, tab, plain, matched, kc, lclp, res, 0);
+        decode_item<BIG, false, 1>(it, in_, out_, T, G, tab, plain, matched, kc, lclp, res, 0);
     }
     const uint8_t* in_;
     uint8_t* out_;
@@ -106,4 +106,33 @@ extern "C" int emul_decode_batch(int fmt, const lzb_options* opt, const uint8_t*
 
 extern "C" uint64_t emul_scan_capacity(int fmt, const lzb_options* opt, const uint8_t* p, uint64_t len) {
     return lzb::scan_capacity(fmt, opt, p, len);
+}
+
+// ---- placement planner (lzb_sched.h, host-only C++): exposed so the CPU tier can check it against its Python twin ----
+#include "../../lzma_rs_b200/csrc/lzb_sched.h"
+
+// work[n] in queue order (longest first).  Writes the order array (capacity n + sms * warps) and returns its length;
+// info = {throttled, n_static, grid, parked}; model = {plain makespan, predicted makespan}.
+extern "C" uint32_t emul_sched_plan(const double* work, uint32_t n, uint32_t sms, uint32_t warps, uint32_t* order_out,
+                                    uint32_t* info, double* model) {
+    std::vector<uint32_t> sorted(n);
+    std::vector<double> w(work, work + n);
+    for (uint32_t i = 0; i < n; i++) sorted[i] = i;
+    lzb_sched::Plan p = lzb_sched::plan(sorted, w, sms, warps);
+    for (size_t k = 0; k < p.order.size(); k++) order_out[k] = p.order[k];
+    info[0] = p.throttled;
+    info[1] = p.n_static;
+    info[2] = p.grid;
+    info[3] = p.parked;
+    model[0] = p.plain;
+    model[1] = p.predicted;
+    return (uint32_t)p.order.size();
+}
+
+extern "C" double emul_sched_simulate(const double* work, uint32_t n, const uint32_t* counts, uint32_t n_counts, uint32_t sms,
+                                      uint32_t warps) {
+    std::vector<double> w(work, work + n);
+    if (!counts) return lzb_sched::simulate(w, nullptr, sms, warps);
+    std::vector<uint32_t> c(counts, counts + n_counts);
+    return lzb_sched::simulate(w, &c, sms, warps);
 }

@@ -275,3 +275,27 @@ def test_batch_shape_extremes(ctx):
     wrap_plain = corpus.mixed_text(7900, 2 << 20)
     r = ctx.decode_batch(0, [corpus.lzma_alone(wrap_plain, dict_size=4096), corpus.lzma_alone_known_size(wrap_plain, dict_size=1 << 16)])
     assert all(x.ok and x.data == wrap_plain for x in r)
+
+
+def test_size_mix_placement(ctx):
+    """North-star shaped batch (sizes log-uniform over a 64x range, more streams than resident warps): the placement
+    planner (lzb_sched.h) pre-assigns first items and parks warps next to the longest streams; every stream must still
+    be decoded exactly once and bit-exact."""
+    import emul_py
+    import gpu_util
+    rng = np.random.default_rng(99)
+    base_plain = [corpus.mixed_text(8100 + i, int(2048 * 64 ** rng.random())) for i in range(600)]
+    base = [corpus.raw_lzma2(p, dict_size=1 << 20) for p in base_plain]
+    n = 6000
+    streams = [base[i % 600] for i in range(n)]
+    plains = [base_plain[i % 600] for i in range(n)]
+    work = np.sort(np.array([len(s) for s in streams], dtype=np.float64))[::-1]
+    _, info = emul_py.sched_plan(work)  # the same planner code, compiled for the CPU tier
+    assert info["throttled"] and info["parked"] > 0, info
+    b = gpu_util.DeviceBatch(ctx, 1, streams, [len(p) for p in plains]).decode()
+    assert (b.st["code"] == 0).all()
+    assert (b.consumed == np.array([len(s) for s in streams], dtype=np.uint64)).all()
+    host = b.d_out.cpu().numpy()
+    for i in range(n):
+        o = int(b.out_off[i])
+        assert host[o:o + int(b.out_len[i])].tobytes() == plains[i], i
