@@ -92,6 +92,101 @@ class decompress:  # namespace mirroring lzma_rs::decompress (src/decode/options
         def _native(self):
             return _native.make_options(self.unpacked_size.mode, self.unpacked_size.value, self.memlimit)
 
+    class raw:  # namespace mirroring lzma_rs::decompress::raw (feature `raw_decoder`, src/lib.rs:29-35)
+        """Reusable raw decoders over the batch path.  The reference keeps a decoder's probability state between two
+        `decompress` calls unless `reset` is called in between; the GPU path decodes every stream from a fresh state,
+        so a second `decompress` without `reset()` raises instead of silently decoding something else."""
+
+        class LzmaProperties:
+            """LzmaProperties { lc, lp, pb } (src/decode/lzma.rs:41-66)."""
+
+            def __init__(self, lc, lp, pb):
+                self.lc, self.lp, self.pb = int(lc), int(lp), int(pb)
+
+            def validate(self):
+                assert self.lc <= 8 and self.lp <= 4 and self.pb <= 4  # lzma.rs:62-66 (the reference panics)
+
+        class LzmaParams:
+            """LzmaParams::new(properties, dict_size, unpacked_size) (src/decode/lzma.rs:68-93)."""
+
+            def __init__(self, properties, dict_size, unpacked_size=None):
+                self.properties, self.dict_size, self.unpacked_size = properties, int(dict_size), unpacked_size
+
+            @classmethod
+            def read_header(cls, input, options=None):
+                """LzmaParams::read_header (lzma.rs:96-161): consumes the 13-byte (5-byte with UseProvided) header."""
+                options = options or decompress.Options()
+                us = options.unpacked_size
+                head = input.read(1)
+                if len(head) < 1:
+                    raise error.HeaderTooShort("header too short: failed to fill whole buffer")
+                props = head[0]
+                if props >= 225:
+                    raise error.LzmaError(f"lzma error: LZMA header invalid properties: {props} must be < 225")
+                lc, lp, pb = props % 9, (props // 9) % 5, props // 45
+                d = input.read(4)
+                if len(d) < 4:
+                    raise error.HeaderTooShort("header too short: failed to fill whole buffer")
+                dict_size = max(int.from_bytes(d, "little"), 0x1000)
+                if us.mode == decompress.UnpackedSizeMode.UseProvided:
+                    size = us.value
+                else:
+                    h = input.read(8)
+                    if len(h) < 8:
+                        raise error.HeaderTooShort("header too short: failed to fill whole buffer")
+                    hv = int.from_bytes(h, "little")
+                    if us.mode == decompress.UnpackedSizeMode.ReadHeaderButUseProvided:
+                        size = us.value
+                    else:
+                        size = None if hv == 0xFFFFFFFFFFFFFFFF else hv
+                return cls(decompress.raw.LzmaProperties(lc, lp, pb), dict_size, size)
+
+        class LzmaDecoder:
+            """raw::LzmaDecoder (src/decode/lzma.rs:597-648): `input` is a headerless LZMA stream."""
+
+            def __init__(self, params, memlimit=None, ctx=None):
+                params.properties.validate()
+                if params.dict_size < 0x1000:
+                    # LzmaParams::new does not clamp (only read_header does, lzma.rs:122-126); the GPU path's work item
+                    # is built from a header, which does
+                    raise error.InternalError("raw LzmaDecoder: dict_size < 4096 is not supported on the GPU path")
+                self.params, self.memlimit, self._ctx, self._used = params, memlimit, ctx, False
+                self._unpacked = params.unpacked_size
+
+            def reset(self, unpacked_size=...):
+                """reset(None) keeps the size; reset(Some(x)) replaces it (lzma.rs:620-627): pass nothing or x."""
+                if unpacked_size is not ...:
+                    self._unpacked = unpacked_size
+                self._used = False
+
+            def decompress(self, input, output=None):
+                if self._used:
+                    raise error.InternalError("raw LzmaDecoder: call reset() before decoding another stream")
+                self._used = True
+                pr = self.params.properties
+                head = bytes([(pr.pb * 5 + pr.lp) * 9 + pr.lc]) + self.params.dict_size.to_bytes(4, "little")
+                opts = decompress.Options(decompress.UnpackedSize.UseProvided(self._unpacked), self.memlimit)
+                data, reader = _read_all(input)
+                r = (self._ctx or _ctx()).decompress_one(_native.FMT_LZMA, head + data, opts)
+                return _deliver(r, len(data) + 5, 5, reader, output)
+
+        class Lzma2Decoder:
+            """raw::Lzma2Decoder (src/decode/lzma2.rs:11-82)."""
+
+            def __init__(self, ctx=None):
+                self._ctx, self._used = ctx, False
+
+            def reset(self):
+                self._used = False
+
+            def decompress(self, input, output=None):
+                if self._used:
+                    raise error.InternalError("raw Lzma2Decoder: call reset() before decoding another stream")
+                self._used = True
+                data, reader = _read_all(input)
+                r = (self._ctx or _ctx()).decompress_one(_native.FMT_LZMA2, data, None)
+                return _deliver(r, len(data), 0, reader, output)
+
 
 class StreamResult:
     """Outcome of one stream of a batch call."""
@@ -222,15 +317,20 @@ def _read_all(inp):
     return inp.read(), inp
 
 
-def _one(fmt, inp, output, options):
-    data, reader = _read_all(inp)
-    r = _ctx().decompress_one(fmt, data, options)
+def _deliver(r, given, prefix, reader, output):
+    """Writes the result to `output`, leaves unread trailing bytes in `reader`, raises the reference's error.
+    given = bytes handed to the decoder, of which the first `prefix` were synthesised by the caller."""
     if output is not None and r.data:
         output.write(r.data)  # on error this is the reference's partial output
-    if reader is not None and r.ok and hasattr(reader, "seek") and r.consumed != len(data):
-        reader.seek(r.consumed - len(data), 1)  # leave unread trailing bytes in the reader, like BufRead::consume
+    if reader is not None and r.ok and hasattr(reader, "seek") and r.consumed != given:
+        reader.seek(max(r.consumed, prefix) - given, 1)  # like BufRead::consume
     r.raise_for_status()
     return r.data
+
+
+def _one(fmt, inp, output, options):
+    data, reader = _read_all(inp)
+    return _deliver(_ctx().decompress_one(fmt, data, options), len(data), 0, reader, output)
 
 
 def lzma_decompress(input, output=None):

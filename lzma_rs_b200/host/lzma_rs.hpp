@@ -14,6 +14,7 @@
 #include <iterator>
 #include <optional>
 #include <ostream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -82,6 +83,71 @@ inline void lzma_decompress_with_options(std::istream& in, std::ostream& out, co
     detail::run(LZB_FMT_LZMA, &n, in, out);
 }
 inline void lzma_decompress(std::istream& in, std::ostream& out) { lzma_decompress_with_options(in, out, {}); }
+
+// lzma_rs::decompress::raw (feature `raw_decoder`, src/lib.rs:29-35).  The reference keeps a decoder's probability
+// state between two decompress() calls unless reset() is called; the GPU path always starts from a fresh state, so a
+// second decompress() without reset() throws instead of decoding something else.
+namespace decompress {
+namespace raw {
+struct LzmaProperties {  // lzma.rs:41-66
+    uint32_t lc, lp, pb;
+    void validate() const {
+        if (lc > 8 || lp > 4 || pb > 4) throw std::invalid_argument("LzmaProperties: lc <= 8, lp <= 4, pb <= 4");
+    }
+};
+struct LzmaParams {  // LzmaParams::new, lzma.rs:68-93
+    LzmaProperties properties;
+    uint32_t dict_size;
+    std::optional<uint64_t> unpacked_size;
+};
+class LzmaDecoder {  // lzma.rs:597-648: `in` is a headerless LZMA stream
+   public:
+    LzmaDecoder(const LzmaParams& p, std::optional<size_t> memlimit) : p_(p), memlimit_(memlimit), size_(p.unpacked_size) {
+        p.properties.validate();
+        if (p.dict_size < 0x1000) throw std::invalid_argument("raw LzmaDecoder: dict_size < 4096 is not supported on the GPU path");
+    }
+    void reset() { used_ = false; }
+    void reset(std::optional<uint64_t> unpacked_size) { size_ = unpacked_size, used_ = false; }
+    void decompress(std::istream& in, std::ostream& out) {
+        if (used_) throw std::logic_error("raw LzmaDecoder: call reset() before decoding another stream");
+        used_ = true;
+        // the work item is built from a 5-byte header (props, dict size) with UnpackedSize::UseProvided
+        std::string head(5, '\0');
+        head[0] = (char)((p_.properties.pb * 5 + p_.properties.lp) * 9 + p_.properties.lc);
+        for (int k = 0; k < 4; k++) head[1 + k] = (char)(p_.dict_size >> (8 * k));
+        std::string body((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        std::istringstream whole(head + body);
+        lzb_options n{};
+        n.unpacked_mode = 2;
+        n.has_provided = size_.has_value();
+        n.provided = size_.value_or(0);
+        n.has_memlimit = memlimit_.has_value();
+        n.memlimit = memlimit_.value_or(0);
+        detail::run(LZB_FMT_LZMA, &n, whole, out);
+        in.clear();
+        in.seekg((std::streamoff)whole.tellg() - 5 - (std::streamoff)body.size(), std::ios::cur);
+    }
+
+   private:
+    LzmaParams p_;
+    std::optional<size_t> memlimit_;
+    std::optional<uint64_t> size_;
+    bool used_ = false;
+};
+class Lzma2Decoder {  // lzma2.rs:11-82
+   public:
+    void reset() { used_ = false; }
+    void decompress(std::istream& in, std::ostream& out) {
+        if (used_) throw std::logic_error("raw Lzma2Decoder: call reset() before decoding another stream");
+        used_ = true;
+        detail::run(LZB_FMT_LZMA2, nullptr, in, out);
+    }
+
+   private:
+    bool used_ = false;
+};
+}  // namespace raw
+}  // namespace decompress
 inline void lzma2_decompress(std::istream& in, std::ostream& out) { detail::run(LZB_FMT_LZMA2, nullptr, in, out); }
 inline void xz_decompress(std::istream& in, std::ostream& out) { detail::run(LZB_FMT_XZ, nullptr, in, out); }
 

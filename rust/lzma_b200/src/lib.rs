@@ -183,6 +183,67 @@ pub fn lzma_decompress_with_options<R: io::BufRead, W: io::Write>(
 ) -> error::Result<()> {
     run(FMT_LZMA, &options(opts), input, output)
 }
+/// `lzma_rs::decompress::raw` (feature `raw_decoder`, src/lib.rs:29-35) over the batch path.  The reference keeps a
+/// decoder's probability state between two `decompress` calls unless `reset` is called; the GPU path always starts
+/// from a fresh state, so a second `decompress` without `reset` is an error instead of a different decode.
+pub mod raw {
+    use super::*;
+    /// src/decode/lzma.rs:41-66
+    #[derive(Debug, Copy, Clone)]
+    pub struct LzmaProperties { pub lc: u32, pub lp: u32, pub pb: u32 }
+    /// src/decode/lzma.rs:68-93
+    #[derive(Debug, Copy, Clone)]
+    pub struct LzmaParams { properties: LzmaProperties, dict_size: u32, unpacked_size: Option<u64> }
+    impl LzmaParams {
+        pub fn new(properties: LzmaProperties, dict_size: u32, unpacked_size: Option<u64>) -> LzmaParams {
+            LzmaParams { properties, dict_size, unpacked_size }
+        }
+    }
+    fn stale() -> error::Error {
+        error::Error::IoError(io::Error::new(io::ErrorKind::Other, "raw decoder: call reset() before decoding another stream"))
+    }
+    /// src/decode/lzma.rs:597-648
+    pub struct LzmaDecoder { params: LzmaParams, memlimit: Option<usize>, used: bool }
+    impl LzmaDecoder {
+        pub fn new(params: LzmaParams, memlimit: Option<usize>) -> error::Result<LzmaDecoder> {
+            let p = params.properties;
+            assert!(p.lc <= 8 && p.lp <= 4 && p.pb <= 4);
+            if params.dict_size < 0x1000 {
+                return Err(error::Error::IoError(io::Error::new(io::ErrorKind::Other, "dict_size < 4096 is not supported on the GPU path")));
+            }
+            Ok(LzmaDecoder { params, memlimit, used: false })
+        }
+        pub fn reset(&mut self, unpacked_size: Option<Option<u64>>) {
+            if let Some(u) = unpacked_size { self.params.unpacked_size = u; }
+            self.used = false;
+        }
+        pub fn decompress<W: io::Write, R: io::BufRead>(&mut self, input: &mut R, output: &mut W) -> error::Result<()> {
+            if self.used { return Err(stale()); }
+            self.used = true;
+            let p = self.params.properties;
+            let mut head = vec![((p.pb * 5 + p.lp) * 9 + p.lc) as u8];
+            head.extend_from_slice(&self.params.dict_size.to_le_bytes());
+            let opts = decompress::Options {
+                unpacked_size: decompress::UnpackedSize::UseProvided(self.params.unpacked_size),
+                memlimit: self.memlimit, allow_incomplete: false,
+            };
+            run(FMT_LZMA, &options(&opts), &mut io::Read::chain(&head[..], input), output)
+        }
+    }
+    /// src/decode/lzma2.rs:11-82
+    #[derive(Default)]
+    pub struct Lzma2Decoder { used: bool }
+    impl Lzma2Decoder {
+        pub fn new() -> Lzma2Decoder { Lzma2Decoder { used: false } }
+        pub fn reset(&mut self) { self.used = false; }
+        pub fn decompress<W: io::Write, R: io::BufRead>(&mut self, input: &mut R, output: &mut W) -> error::Result<()> {
+            if self.used { return Err(stale()); }
+            self.used = true;
+            run(FMT_LZMA2, &LzbOptions::default(), input, output)
+        }
+    }
+}
+
 /// `lzma_rs::lzma2_decompress` (src/lib.rs:83-88)
 pub fn lzma2_decompress<R: io::BufRead, W: io::Write>(input: &mut R, output: &mut W) -> error::Result<()> {
     run(FMT_LZMA2, &LzbOptions::default(), input, output)

@@ -175,7 +175,8 @@ def test_cpp_host_mirror(ctx, golden, tmp_path):
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + root, "-I" + os.path.join(root, "include"),
                            os.path.join(root, "tests", "cpp", "host_check.cpp"), "-L" + os.path.join(root, "lzma_rs_b200"),
                            "-llzma_b200", "-Wl,-rpath," + os.path.join(root, "lzma_rs_b200"), "-o", str(exe)])
-    for name, fmt in [("foo.txt.lzma", "lzma"), ("good-1-lzma2-4.xz", "xz"), ("corrupt-footer.xz", "xz")]:
+    for name, fmt in [("foo.txt.lzma", "lzma"), ("good-1-lzma2-4.xz", "xz"), ("corrupt-footer.xz", "xz"),
+                      ("foo.txt.lzma", "rawlzma"), ("range-coder-edge-case.lzma", "rawlzma")]:
         v = next(x for x in golden.vectors() if x["name"] == name)
         src, dst = tmp_path / "in.bin", tmp_path / "out.bin"
         src.write_bytes(golden.compressed(v))
@@ -299,3 +300,43 @@ def test_size_mix_placement(ctx):
     for i in range(n):
         o = int(b.out_off[i])
         assert host[o:o + int(b.out_len[i])].tobytes() == plains[i], i
+
+
+def test_raw_decoders(ctx):
+    """decompress::raw::{LzmaParams, LzmaDecoder, Lzma2Decoder} (feature raw_decoder, src/lib.rs:29-35) over the batch
+    path: header split off by read_header, headerless payload decoded with the parsed parameters, reset() semantics."""
+    import lzma_rs_b200 as L
+    raw = L.decompress.raw
+    data = corpus.mixed_text(4242, 150_000)
+    for blob, size in ((corpus.lzma_alone(data, dict_size=1 << 20), None),
+                       (corpus.lzma_alone_known_size(data, dict_size=1 << 16), len(data))):
+        rd = io.BytesIO(blob + b"TRAILER")
+        params = raw.LzmaParams.read_header(rd)
+        assert params.unpacked_size == size and (params.properties.lc, params.properties.lp, params.properties.pb) == (3, 0, 2)
+        dec = raw.LzmaDecoder(params, None, ctx)
+        out = io.BytesIO()
+        if size is None:  # end marker followed by more bytes: lzma.rs:374-381
+            with pytest.raises(L.error.LzmaError, match="end-of-stream marker but more bytes"):
+                dec.decompress(rd, out)
+        else:
+            dec.decompress(rd, out)
+            # known size: the decoder stops at the last byte it needs; liblzma's end marker stays unread (lzma.rs:442-445)
+            assert out.getvalue() == data and rd.read() == (blob + b"TRAILER")[oracle.lzma_decompress(blob + b"TRAILER").consumed:]
+        with pytest.raises(L.error.InternalError, match="reset"):
+            dec.decompress(io.BytesIO(blob[13:]))
+        dec.reset()
+        assert dec.decompress(blob[13:]) == data
+    # same payload decoded against the oracle with an explicit size (UseProvided) and a wrong size
+    blob = corpus.lzma_alone_known_size(data, dict_size=1 << 16)
+    p = raw.LzmaParams(raw.LzmaProperties(3, 0, 2), 1 << 16, len(data) - 10)
+    want = oracle.lzma_decompress(blob[:5] + blob[13:], unpacked_mode=2, provided=len(data) - 10)
+    with pytest.raises(L.error.LzmaError) as ei:
+        raw.LzmaDecoder(p, None, ctx).decompress(blob[13:])
+    assert str(ei.value) == want.display
+    with pytest.raises(AssertionError):
+        raw.LzmaDecoder(raw.LzmaParams(raw.LzmaProperties(9, 0, 0), 1 << 16), None, ctx)
+    d2 = raw.Lzma2Decoder(ctx)
+    rd = io.BytesIO(corpus.raw_lzma2(data) + b"xyz")
+    assert d2.decompress(rd) == data and rd.read() == b"xyz"
+    d2.reset()
+    assert d2.decompress(corpus.raw_lzma2(data[:1000])) == data[:1000]
