@@ -113,7 +113,8 @@ enum {
     LZB_E_XZ_TRAILING_DATA = 56,    /* xz.rs:88-92 */
     /* not reference errors (kind = LZB_KIND_INTERNAL) */
     LZB_E_CAPACITY = -1,    /* caller's output capacity too small; a0 = bytes needed (lower bound if the size is unknown) */
-    LZB_E_UNSUPPORTED = -2  /* outside the GPU path's limits (stream or output >= 4 GiB - 4 KiB) */
+    LZB_E_UNSUPPORTED = -2, /* outside the GPU path's limits (stream or output >= 4 GiB - 4 KiB) */
+    LZB_E_INPUT_TIMEOUT = -3 /* host API: the stream's input never reached the device (lost upload); nothing decoded */
 };
 
 typedef struct lzb_status {

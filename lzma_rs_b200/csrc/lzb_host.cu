@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <mutex>
 #include <numeric>
+#include <chrono>
+#include <functional>
 #include <vector>
 
 #include "lzb_plan.h"
@@ -22,7 +24,7 @@ struct LzbCrcRange {
 #define LZB_K1_PROTO(NAME)                                                                                       \
     extern "C" __global__ void NAME(const LzbItem*, const uint32_t*, uint32_t, uint32_t, const uint8_t*, uint8_t*, \
                                     LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long, \
-                                    const LzbKC)
+                                    const LzbKC, const unsigned long long*)
 LZB_K1_PROTO(lzb_decode_kernel);
 LZB_K1_PROTO(lzb_decode_mirror_kernel);
 LZB_K1_PROTO(lzb_decode_fill_kernel);
@@ -74,14 +76,21 @@ struct DevBuf {
 struct lzb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // host API input gate (lzb_decode_batch): the input blob is uploaded in chunks on `copy_stream` while K1 already runs
+    // on `stream`; after each chunk the offset reached is copied from h_marks to d_gate[0] (see input_arrived())
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t gate_ready = nullptr;
+    unsigned long long* h_marks = nullptr;  // pinned: [0..2] initial gate words, [8..] one watermark per chunk
     int sm_count = 0;
     int smem_optin = 0;
     int smem_configured[12] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1}, smem_configured_big = -1;
     char err[320] = {0};
     std::mutex mu;
     DevBuf d_in, d_out, d_items, d_results, d_order, d_counter, d_scan, d_off, d_crc_ranges, d_crc_segmap, d_crc_part32,
-        d_crc_part64, d_crc_out32, d_crc_out64, d_litws, d_matchws;
+        d_crc_part64, d_crc_out32, d_crc_out64, d_litws, d_matchws, d_gate;
 };
+#define LZB_GATE_CHUNK (8ull << 20)  // upload granularity of the gated host path
+#define LZB_GATE_MAX_CHUNKS 56
 
 #define CUDA_TRY(ctx, call)                                                                         \
     do {                                                                                            \
@@ -94,6 +103,15 @@ struct lzb_ctx {
     } while (0)
 
 namespace {
+
+// LZB_TRACE=1: one line per host-API decode on stderr with the host-side timeline (ms since the call started) and the
+// in-situ duration of the K1 launch (CUDA events) -- how the end-to-end time of lzb_decode_batch splits up.
+struct Trace {
+    bool on = getenv("LZB_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double plan = 0, launched = 0, uploaded = 0, synced = 0, kernel_ms = 0;
+    double now() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 struct LaunchCfg {
     uint32_t lclp, warp_bytes, warps, grid;
@@ -189,7 +207,7 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
 // followed by order_big; d_counter holds two counters.
 int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem* d_items, const uint32_t* d_order,
                 const uint8_t* d_in_base, uint8_t* d_out_base, LzbResult* d_results, unsigned int* d_counter,
-                bool mirror = false) {
+                bool mirror = false, const unsigned long long* d_gate = nullptr) {
     CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned int), s));
     const uint32_t ns = (uint32_t)p.order_small.size(), nb = (uint32_t)p.order_big.size();
     const LzbKC kc = LZB_KC_INIT;
@@ -202,7 +220,8 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         // variants: [sched][mirror][lean | fill | copy]; mirror = host API with a pinned output buffer (finished pages
         // streamed to the host); sched = the launch carries a placement plan (lzb_sched.h)
         typedef void (*kern_t)(const LzbItem*, const uint32_t*, uint32_t, uint32_t, const uint8_t*, uint8_t*, LzbResult*,
-                               unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long, const LzbKC);
+                               unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long, const LzbKC,
+                               const unsigned long long*);
         static const kern_t kernels[12] = {
             lzb_decode_kernel,              lzb_decode_fill_kernel,              lzb_decode_copy_kernel,
             lzb_decode_mirror_kernel,       lzb_decode_fill_mirror_kernel,       lzb_decode_copy_mirror_kernel,
@@ -214,7 +233,8 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
             ctx->smem_configured[v] = ctx->smem_optin;
         }
         kernels[v]<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, p.n_static, d_in_base, d_out_base, d_results,
-                                                      d_counter, c.lclp, c.warp_bytes, ctx->d_matchws.as<uint16_t>(), mstride, kc);
+                                                      d_counter, c.lclp, c.warp_bytes, ctx->d_matchws.as<uint16_t>(), mstride, kc,
+                                                      mirror ? d_gate : nullptr);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     if (nb) {
@@ -228,7 +248,8 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         CUDA_TRY(ctx, ctx->d_litws.ensure((size_t)c.grid * c.warps * p.big_stride_u16 * 2));
         lzb_decode_biglit_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order + ns, nb, 0u, d_in_base, d_out_base,
                                                                     d_results, d_counter + 1, c.lclp, c.warp_bytes,
-                                                                    ctx->d_litws.as<uint16_t>(), p.big_stride_u16, kc);
+                                                                    ctx->d_litws.as<uint16_t>(), p.big_stride_u16, kc,
+                                                                    mirror ? d_gate : nullptr);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     return LZB_RC_OK;
@@ -246,8 +267,14 @@ int upload_order(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, DevBuf& d_or
 class CudaExecutor : public lzb::Executor {
    public:
     // host_mirror: device-visible address of offset 0 of the caller's pinned host output (nullptr = none)
-    CudaExecutor(lzb_ctx* ctx, cudaStream_t s, const uint8_t* d_in_base, uint8_t* d_out_base, uint8_t* host_mirror = nullptr)
-        : ctx_(ctx), s_(s), in_(d_in_base), out_(d_out_base), hmirror_(host_mirror) {}
+    // d_gate: input gate words of a chunked upload still in flight (nullptr = the input is already on the device)
+    CudaExecutor(lzb_ctx* ctx, cudaStream_t s, const uint8_t* d_in_base, uint8_t* d_out_base, uint8_t* host_mirror = nullptr,
+                 const unsigned long long* d_gate = nullptr)
+        : ctx_(ctx), s_(s), in_(d_in_base), out_(d_out_base), hmirror_(host_mirror), gate_(d_gate) {}
+    // Runs once, right after the first K1 launch has been enqueued: the gated upload of the input blob.  Issued after the
+    // launch so that the (small) uploads of the plan are not queued behind it on the copy engine.
+    std::function<int()> after_first_launch;
+    Trace* trace = nullptr;
     bool all_mirrored() const { return hmirror_ != nullptr && !unmirrored_; }
 
     int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint64_t stored_bytes, LzbResult* results) override {
@@ -349,11 +376,37 @@ class CudaExecutor : public lzb::Executor {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items.p, up, n * sizeof(LzbItem), cudaMemcpyHostToDevice, s_));
         int rc = upload_order(ctx, s_, plan, ctx->d_order);
         if (rc != LZB_RC_OK) return rc;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        const bool tr = trace && trace->on && trace->launched == 0;
+        if (tr) {
+            trace->plan = trace->now();
+            cudaEventCreate(&ev0);
+            cudaEventCreate(&ev1);
+            cudaEventRecord(ev0, s_);
+        }
         rc = launch_plan(ctx, s_, plan, ctx->d_items.as<LzbItem>(), ctx->d_order.as<uint32_t>(), in_, out_,
-                         ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>(), hmirror_ != nullptr);
+                         ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>(), hmirror_ != nullptr, gate_);
         if (rc != LZB_RC_OK) return rc;
+        if (tr) {
+            cudaEventRecord(ev1, s_);
+            trace->launched = trace->now();
+        }
+        if (after_first_launch) {
+            rc = after_first_launch();
+            after_first_launch = nullptr;
+            if (rc != LZB_RC_OK) return rc;
+        }
+        if (tr) trace->uploaded = trace->now();
         CUDA_TRY(ctx, cudaMemcpyAsync(results, ctx->d_results.p, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s_));
         CUDA_TRY(ctx, cudaStreamSynchronize(s_));
+        if (tr) {
+            trace->synced = trace->now();
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev0, ev1);
+            trace->kernel_ms = ms;
+            cudaEventDestroy(ev0);
+            cudaEventDestroy(ev1);
+        }
         return LZB_RC_OK;
     }
     lzb_ctx* ctx_;
@@ -361,6 +414,7 @@ class CudaExecutor : public lzb::Executor {
     const uint8_t* in_;
     uint8_t* out_;
     uint8_t* hmirror_;
+    const unsigned long long* gate_;
     bool unmirrored_ = false;
     std::vector<void*> scratch_;
 };
@@ -384,8 +438,12 @@ extern "C" int lzb_create(lzb_ctx** out, int device) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        delete ctx;
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->gate_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->h_marks, (8 + LZB_GATE_MAX_CHUNKS) * sizeof(unsigned long long), cudaHostAllocDefault) !=
+            cudaSuccess) {
+        lzb_destroy(ctx);
         return LZB_RC_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
@@ -397,12 +455,16 @@ extern "C" int lzb_create(lzb_ctx** out, int device) {
 extern "C" void lzb_destroy(lzb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_items, &ctx->d_results, &ctx->d_order, &ctx->d_counter, &ctx->d_scan,
                       &ctx->d_off, &ctx->d_crc_ranges, &ctx->d_crc_segmap, &ctx->d_crc_part32, &ctx->d_crc_part64,
-                      &ctx->d_crc_out32, &ctx->d_crc_out64, &ctx->d_litws, &ctx->d_matchws};
+                      &ctx->d_crc_out32, &ctx->d_crc_out64, &ctx->d_litws, &ctx->d_matchws, &ctx->d_gate};
     for (DevBuf* b : bufs) b->release();
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->gate_ready) cudaEventDestroy(ctx->gate_ready);
+    if (ctx->h_marks) cudaFreeHost(ctx->h_marks);
     delete ctx;
 }
 
@@ -422,6 +484,7 @@ extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, c
     if (n == 0) return LZB_RC_OK;
     if (!in || !out) return LZB_RC_BAD_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    Trace trace;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const uint64_t in_lo = in_off[0], in_hi = in_off[n], out_lo = out_off[0], out_hi = out_off[n];
     // device copies keep the low 4 address bits of the host offsets so that (base + offset) stays 16-byte congruent
@@ -429,8 +492,6 @@ extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, c
     CUDA_TRY(ctx, ctx->d_out.ensure((out_hi - out_lo) + 64));
     uint8_t* d_in0 = ctx->d_in.as<uint8_t>() + (in_lo & 15);
     uint8_t* d_out0 = ctx->d_out.as<uint8_t>() + (out_lo & 15);
-    if (in_hi > in_lo)
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, ctx->stream));
     // A pinned (page-locked, device-mapped) output buffer lets K1 stream finished pages straight to the host while it
     // decodes; a pageable buffer gets one device-to-host copy after the kernel.
     uint8_t* host_mirror = nullptr;
@@ -443,7 +504,50 @@ extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, c
         else
             cudaGetLastError();  // clear the "not registered" error of a pageable pointer
     }
-    CudaExecutor ex(ctx, ctx->stream, d_in0 - in_lo, d_out0 - out_lo, host_mirror);
+    // Input upload.  With a pinned output (mirror kernels) and a blob worth splitting, K1 is launched first and the blob
+    // follows in chunks on the copy stream: every warp waits only for its own stream's bytes (input_arrived() in
+    // lzb_kernels.cu), so the upload overlaps the decode.  Otherwise: one copy, in stream order before the kernel.
+    const unsigned long long* d_gate = nullptr;
+    std::function<int()> upload;
+    struct CopyJoin {  // no exit path may leave copies in flight into ctx->d_in
+        cudaStream_t s;
+        ~CopyJoin() {
+            if (s) cudaStreamSynchronize(s);
+        }
+    } join{nullptr};
+    const uint64_t in_bytes = in_hi - in_lo, lead = in_lo & 15;
+    if (host_mirror && in_bytes >= 2 * LZB_GATE_CHUNK && !getenv("LZB_NO_GATE")) {
+        uint64_t chunk = LZB_GATE_CHUNK;
+        while ((lead + in_bytes + chunk - 1) / chunk > LZB_GATE_MAX_CHUNKS) chunk *= 2;
+        CUDA_TRY(ctx, ctx->d_gate.ensure(64));
+        unsigned long long* hm = ctx->h_marks;
+        hm[0] = 0;                                        // watermark: device offset reached so far
+        hm[1] = (unsigned long long)(lead - in_lo);       // device offset = blob offset + this (mod 2^64)
+        hm[2] = (unsigned long long)(lead + in_bytes);    // device offset of the end of the blob
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, hm, 24, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->gate_ready, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gate_ready, 0));
+        join.s = ctx->copy_stream;
+        upload = [=]() -> int {
+            uint32_t k = 0;
+            for (uint64_t lo = lead; lo < lead + in_bytes; k++) {  // chunk boundaries at device offsets k * chunk
+                const uint64_t hi = std::min<uint64_t>((lo / chunk + 1) * chunk, lead + in_bytes);
+                CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + lo, in + in_lo + (lo - lead), hi - lo,
+                                              cudaMemcpyHostToDevice, ctx->copy_stream));
+                hm[8 + k] = hi;
+                CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, &hm[8 + k], 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+                lo = hi;
+            }
+            return LZB_RC_OK;
+        };
+        d_gate = ctx->d_gate.as<unsigned long long>();
+    } else if (in_bytes) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, in + in_lo, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CudaExecutor ex(ctx, ctx->stream, d_in0 - in_lo, d_out0 - out_lo, host_mirror, d_gate);
+    ex.after_first_launch = upload;
+    ex.trace = &trace;
+    const double t_enq = trace.now();
     std::vector<lzb::StreamOut> outs(n);
     int rc = lzb::decode_batch(ex, fmt, opt, in, in_off, n, out_off, outs.data());  // planning reads the host copy
     if (rc != LZB_RC_OK) return rc;
@@ -455,6 +559,10 @@ extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, c
         consumed[i] = outs[i].consumed;
         st[i] = outs[i].st;
     }
+    if (trace.on)
+        fprintf(stderr, "lzb_trace n=%u in=%llu gated=%d setup=%.3f planned=%.3f launched=%.3f uploaded=%.3f synced=%.3f "
+                        "end=%.3f kernel_in_situ=%.3f ms\n", n, (unsigned long long)in_bytes, d_gate != nullptr, t_enq,
+                trace.plan, trace.launched, trace.uploaded, trace.synced, trace.now(), trace.kernel_ms);
     return LZB_RC_OK;
 }
 

@@ -28,12 +28,37 @@
 // (n_static = gridDim.x * warps), LZB_ORDER_PARK there = this warp stays out of the launch; order[n_static ..) is the
 // dynamic queue.  A separate instantiation because K1's hot loop is sensitive to code layout: the same loop head in
 // the default kernels costs batches that need no plan 0.5-3 % (measured, tools/kbench.py).
+// Input gate of the host API (lzb_decode_batch with a pinned output buffer): the kernel is launched while the input
+// blob is still travelling to the device in chunks on a second stream; after every chunk the copy engine writes the
+// device offset reached so far to gate[0].  A warp starts a stream once every 128-byte line the stream touches has
+// arrived (whole lines: K1 reads the blob through the non-coherent path, so a line must never be fetched before all of
+// it is there).  gate[1] = device offset minus blob offset, gate[2] = device offset of the end of the blob.
+// Returns false if the bytes did not arrive within 5 s (reported as LZB_E_INPUT_TIMEOUT; never seen in practice, it
+// keeps a lost copy from hanging the GPU).
+__device__ __noinline__ bool input_arrived(const LzbItem* it, const unsigned long long* gate) {
+    if (it->kind == LZB_ITEM_PRESET || (it->flags & LZB_ITEM_F_IN_FROM_OUT)) return true;
+    unsigned long long need = (it->in_off + it->in_len + gate[1] + 127ull) & ~127ull;
+    if (need > gate[2]) need = gate[2];
+    const volatile unsigned long long* wm = gate;
+    if (*wm < need) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            __nanosleep(400);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 5000000000ull) return false;
+        } while (*wm < need);
+    }
+    __threadfence_system();  // the stream's bytes are read after the watermark
+    return true;
+}
+
 template <bool LIT_GLOBAL, bool MIRROR, int WIDE, bool SCHED>
 __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order,
                                             uint32_t n_items, uint32_t n_static, const uint8_t* __restrict__ in_blob,
                                             uint8_t* out_blob, LzbResult* results, unsigned int* counter, uint32_t tab_lclp,
                                             uint32_t warp_smem_bytes, uint16_t* ws, unsigned long long ws_stride_u16,
-                                            const LzbKC& kc) {
+                                            const LzbKC& kc, const unsigned long long* gate) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     // broadcast from lane 0 so that the compiler's divergence analysis sees the warp index (and with it every
@@ -57,6 +82,14 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
         if (slot >= n_items) break;
         const uint32_t idx = order[slot];
         if (SCHED && idx == LZB_ORDER_PARK) break;
+        if (MIRROR && gate && !input_arrived(items + idx, gate)) {  // host API: the input blob is still being uploaded
+            if (lane == 0) {
+                LzbResult r = {};
+                r.code = LZB_E_INPUT_TIMEOUT;
+                results[idx] = r;
+            }
+            continue;
+        }
         if (LIT_GLOBAL) {  // whole literal table in the global workspace (reference layout)
             const TabPtr plain = {gws}, matched = {gws + 0x100};
             decode_item<true, MIRROR, WIDE>(items + idx, in_blob, out_blob, T, gws, tab, plain, matched, kc, tab_lclp, results + idx, lane);
@@ -73,8 +106,8 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
     const LzbItem *__restrict__ items, const uint32_t *__restrict__ order, uint32_t n_items, uint32_t n_static,      \
         const uint8_t *__restrict__ in_blob, uint8_t *out_blob, LzbResult *results, unsigned int *counter,           \
         uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t *ws, unsigned long long ws_stride_u16,                 \
-        const __grid_constant__ LzbKC kc
-#define LZB_KERNEL_PASS items, order, n_items, n_static, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws, ws_stride_u16, kc
+        const __grid_constant__ LzbKC kc, const unsigned long long *gate
+#define LZB_KERNEL_PASS items, order, n_items, n_static, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws, ws_stride_u16, kc, gate
 #define LZB_DEFINE_K1(NAME, LIT_GLOBAL, MIRROR, WIDE, SCHED)                                               \
     extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1) NAME(LZB_KERNEL_ARGS) {          \
         decode_loop<LIT_GLOBAL, MIRROR, WIDE, SCHED>(LZB_KERNEL_PASS);                                    \

@@ -536,7 +536,7 @@ static int validate_file(Executor& ex, XzFile& f, const std::vector<LzbItem>& it
             f.chain_scratch_hint = 0;
             return LZB_RC_OK;
         }
-        if (r.code == LZB_E_CAPACITY || r.code == LZB_E_UNSUPPORTED) {
+        if (r.code < 0) {  // LZB_KIND_INTERNAL
             if (r.code == LZB_E_CAPACITY && bp.cap_is_prediction && bp.cap < remaining) {
                 f.lookahead = false;  // the framing scan mispredicted: redo from this block without look-ahead
                 return LZB_RC_OK;
@@ -799,6 +799,7 @@ extern "C" size_t lzb_format_error(const lzb_status* st, char* buf, size_t buf_l
     case LZB_E_XZ_TRAILING_DATA: snprintf(m, sizeof m, "Unexpected data after last XZ block"); break;
     case LZB_E_CAPACITY: snprintf(m, sizeof m, "output capacity too small, need at least %llu bytes", a0); break;
     case LZB_E_UNSUPPORTED: snprintf(m, sizeof m, "stream outside the GPU path's limits"); break;
+    case LZB_E_INPUT_TIMEOUT: snprintf(m, sizeof m, "input upload did not reach the device"); break;
     default: snprintf(m, sizeof m, "unknown status %d", st->code); break;
     }
     int n = snprintf(buf, buf_len, "%s%s", pfx, m);

@@ -53,17 +53,20 @@ class DeviceBatch:
         return "" if self.st[i]["code"] == 0 else _native.format_status(self.lib, self.st[i])
 
 
-def host_decode_pinned(ctx, fmt, streams, capacities, opts=None):
+def host_decode_pinned(ctx, fmt, streams, capacities, opts=None, pin_input=True, blob_shift=0):
     """lzb_decode_batch with PINNED host buffers (torch.pin_memory): K1's mirror variant streams finished output pages
     to the host buffer itself, no device-to-host copy after the kernel.  Returns (list of bytes, out_len, consumed, st)."""
     import torch
     lib = _native.load()
     blob, in_off = _native.pack_streams(streams)
+    if blob_shift:  # the batch starts at an odd offset of the caller's buffer (in_off[0] != 0)
+        blob = np.concatenate([np.zeros(blob_shift, dtype=np.uint8), blob])
+        in_off = in_off + np.uint64(blob_shift)
     n = len(streams)
     caps = (np.asarray(capacities, dtype=np.uint64) + np.uint64(15)) // np.uint64(16) * np.uint64(16)
     out_off = np.zeros(n + 1, dtype=np.uint64)
     np.cumsum(caps, out=out_off[1:])
-    h_in = torch.from_numpy(blob).pin_memory()
+    h_in = torch.from_numpy(blob).pin_memory() if pin_input else torch.from_numpy(blob)
     h_out = torch.full((int(out_off[-1]) + 16,), 0xEE, dtype=torch.uint8).pin_memory()
     out_len = np.zeros(n, dtype=np.uint64)
     consumed = np.zeros(n, dtype=np.uint64)

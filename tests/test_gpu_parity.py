@@ -328,11 +328,18 @@ def test_raw_decoders(ctx):
         assert dec.decompress(blob[13:]) == data
     # same payload decoded against the oracle with an explicit size (UseProvided) and a wrong size
     blob = corpus.lzma_alone_known_size(data, dict_size=1 << 16)
-    p = raw.LzmaParams(raw.LzmaProperties(3, 0, 2), 1 << 16, len(data) - 10)
-    want = oracle.lzma_decompress(blob[:5] + blob[13:], unpacked_mode=2, provided=len(data) - 10)
-    with pytest.raises(L.error.LzmaError) as ei:
-        raw.LzmaDecoder(p, None, ctx).decompress(blob[13:])
-    assert str(ei.value) == want.display
+    for short in range(1, 3000):  # find a size the last match overshoots (lzma.rs:513-521); others just stop early
+        p = raw.LzmaParams(raw.LzmaProperties(3, 0, 2), 1 << 16, len(data) - short)
+        want = oracle.lzma_decompress(blob[:5] + blob[13:], unpacked_mode=2, provided=len(data) - short)
+        if want.ok:
+            assert raw.LzmaDecoder(p, None, ctx).decompress(blob[13:]) == want.out == data[:len(data) - short]
+        else:
+            with pytest.raises(L.error.LzmaError) as ei:
+                raw.LzmaDecoder(p, None, ctx).decompress(blob[13:])
+            assert str(ei.value) == want.display and "Expected unpacked size" in want.display
+            break
+    else:
+        raise AssertionError("no overshooting size found")
     with pytest.raises(AssertionError):
         raw.LzmaDecoder(raw.LzmaParams(raw.LzmaProperties(9, 0, 0), 1 << 16), None, ctx)
     d2 = raw.Lzma2Decoder(ctx)
@@ -340,3 +347,36 @@ def test_raw_decoders(ctx):
     assert d2.decompress(rd) == data and rd.read() == b"xyz"
     d2.reset()
     assert d2.decompress(corpus.raw_lzma2(data[:1000])) == data[:1000]
+
+
+def test_host_api_gated_upload(ctx):
+    """lzb_decode_batch with a pinned output and > 16 MiB of input: K1 is launched before the input blob has arrived
+    and every warp waits for its own stream's bytes (input gate).  Pinned and pageable input, blob starting at an odd
+    offset, streams that end in errors and preset (header) errors mixed in; compared with the ungated path."""
+    import os
+    import gpu_util
+    rng = np.random.default_rng(11)
+    base_plain = [corpus.mixed_text(8800 + i, int(rng.integers(20_000, 200_000))) for i in range(96)]
+    base = [corpus.raw_lzma2(p, dict_size=1 << 20) for p in base_plain]
+    n = 1200
+    streams = [base[i % 96] for i in range(n)]
+    plains = [base_plain[i % 96] for i in range(n)]
+    streams[7] = streams[7][:len(streams[7]) // 2]        # truncated: UnexpectedEof
+    streams[600] = b"\x55" + streams[600][1:]             # invalid LZMA2 status byte
+    assert sum(len(s) for s in streams) > 40 << 20
+    caps = [len(p) for p in plains]
+    want = [oracle.lzma2_decompress(streams[i]) for i in (7, 600)]
+    for pin_input, shift in ((True, 0), (True, 5), (False, 21)):
+        outs, out_len, consumed, st = gpu_util.host_decode_pinned(ctx, 1, streams, caps, pin_input=pin_input, blob_shift=shift)
+        for i in range(n):
+            if i in (7, 600):
+                w = want[(7, 600).index(i)]
+                assert st[i]["code"] != 0 and outs[i] == w.out, i
+            else:
+                assert st[i]["code"] == 0 and outs[i] == plains[i] and int(consumed[i]) == len(streams[i]), i
+    os.environ["LZB_NO_GATE"] = "1"  # same call, upload in stream order before the kernel
+    try:
+        outs2, _, _, st2 = gpu_util.host_decode_pinned(ctx, 1, streams, caps)
+    finally:
+        del os.environ["LZB_NO_GATE"]
+    assert outs2 == outs and (st2["code"] == st["code"]).all()
