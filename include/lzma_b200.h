@@ -50,7 +50,10 @@ typedef struct lzb_options {
     uint8_t unpacked_mode; /* UnpackedSize variant */
     uint8_t has_provided;  /* the variant's Option<u64> is Some */
     uint8_t has_memlimit;  /* memlimit: Option<usize> is Some */
-    uint8_t reserved[5];
+    uint8_t allow_incomplete; /* Options::allow_incomplete (the stream API's flag, stream.rs:136-147): a .lzma stream whose
+                               * input ends in the middle of a symbol is not an error; every byte decoded from complete
+                               * symbols is returned (status LZB_OK) */
+    uint8_t reserved[4];
     uint64_t provided;
     uint64_t memlimit;
 } lzb_options;

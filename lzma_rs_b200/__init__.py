@@ -23,7 +23,8 @@ import numpy as _np
 from . import _native
 
 __all__ = ["lzma_decompress", "lzma_decompress_with_options", "lzma2_decompress", "xz_decompress",
-           "lzma_decompress_batch", "lzma2_decompress_batch", "xz_decompress_batch", "decompress", "error", "Context"]
+           "lzma_decompress_batch", "lzma2_decompress_batch", "xz_decompress_batch", "decompress", "error", "Context",
+           "Stream", "StreamResult"]
 
 
 class error:  # namespace mirroring lzma_rs::error (src/error.rs:7-37)
@@ -90,7 +91,7 @@ class decompress:  # namespace mirroring lzma_rs::decompress (src/decode/options
             self.allow_incomplete = allow_incomplete
 
         def _native(self):
-            return _native.make_options(self.unpacked_size.mode, self.unpacked_size.value, self.memlimit)
+            return _native.make_options(self.unpacked_size.mode, self.unpacked_size.value, self.memlimit, self.allow_incomplete)
 
     class raw:  # namespace mirroring lzma_rs::decompress::raw (feature `raw_decoder`, src/lib.rs:29-35)
         """Reusable raw decoders over the batch path.  The reference keeps a decoder's probability state between two
@@ -186,6 +187,63 @@ class decompress:  # namespace mirroring lzma_rs::decompress (src/decode/options
                 data, reader = _read_all(input)
                 r = (self._ctx or _ctx()).decompress_one(_native.FMT_LZMA2, data, None)
                 return _deliver(r, len(data), 0, reader, output)
+
+
+class Stream:
+    """lzma_rs::decompress::Stream (feature `stream`, src/decode/stream.rs:66-346) as a façade over the batch path.
+
+    The reference decodes incrementally inside `write`; the GPU path decodes whole streams, so this class buffers what
+    is written and decodes in `finish()`.  Same results, later errors: header errors are still raised by `write`
+    (stream.rs:157-190 parses the header as soon as its bytes are there), data errors surface in `finish()` instead of
+    in the `write` that delivered the bad bytes.  `Options.allow_incomplete` is honoured (stream.rs:136-147)."""
+
+    def __init__(self, output, options=None, ctx=None):
+        self._out, self._opt, self._ctx = output, options or decompress.Options(), ctx
+        self._buf, self._failed, self._done = bytearray(), False, False
+
+    @classmethod
+    def new_with_options(cls, options, output):
+        return cls(output, options)
+
+    def get_output(self):
+        return None if self._failed or self._done else self._out
+
+    def write(self, data):
+        if self._failed or self._done:
+            return 0  # stream.rs:230,310: the state is gone after a failed write; nothing is consumed
+        first = not self._buf
+        self._buf += data
+        if first and self._buf and self._buf[0] >= 225:  # LzmaParams::read_header, lzma.rs:104-109
+            self._failed = True
+            raise error.LzmaError(f"lzma error: LZMA header invalid properties: {self._buf[0]} must be < 225")
+        return len(data)
+
+    write_all = write
+
+    def flush(self):
+        if not (self._failed or self._done) and hasattr(self._out, "flush"):
+            self._out.flush()
+
+    def finish(self):
+        """Consumes the stream and returns the output sink (stream.rs:119-151)."""
+        if self._failed or self._done:
+            raise error.LzmaError("lzma error: can't finish stream because of previous write error")
+        self._done = True
+        if not self._buf:
+            return self._out
+        hdr = 5 if self._opt.unpacked_size.mode == decompress.UnpackedSizeMode.UseProvided else 13
+        if len(self._buf) < hdr + 5:  # header + the 5 range-coder start bytes were never complete (stream.rs:123-129)
+            raise error.LzmaError("lzma error: failed to read header")
+        r = (self._ctx or _ctx()).decompress_one(_native.FMT_LZMA, bytes(self._buf), self._opt)
+        if r.data:
+            self._out.write(r.data)
+        r.raise_for_status()
+        if hasattr(self._out, "flush"):
+            self._out.flush()
+        return self._out
+
+
+decompress.Stream = Stream
 
 
 class StreamResult:

@@ -19,7 +19,7 @@ E_CAPACITY, E_UNSUPPORTED = -1, -2
 
 class Options(C.Structure):  # lzb_options
     _fields_ = [("unpacked_mode", C.c_uint8), ("has_provided", C.c_uint8), ("has_memlimit", C.c_uint8),
-                ("reserved", C.c_uint8 * 5), ("provided", C.c_uint64), ("memlimit", C.c_uint64)]
+                ("allow_incomplete", C.c_uint8), ("reserved", C.c_uint8 * 4), ("provided", C.c_uint64), ("memlimit", C.c_uint64)]
 
 
 class Status(C.Structure):  # lzb_status
@@ -91,8 +91,9 @@ def format_status(lib, st_row):
     return buf.value.decode()
 
 
-def make_options(unpacked_mode=0, provided=None, memlimit=None):
+def make_options(unpacked_mode=0, provided=None, memlimit=None, allow_incomplete=False):
     o = Options()
+    o.allow_incomplete = 1 if allow_incomplete else 0
     o.unpacked_mode = unpacked_mode
     o.has_provided = 0 if provided is None else 1
     o.provided = 0 if provided is None else provided

@@ -575,12 +575,13 @@ struct lzb_batch {
     uint8_t* d_out = nullptr;
     DevBuf d_items, d_results, d_order, d_counter, d_scan, d_off;
     std::vector<LzbItem> items;  // host copy (hdr_len, preset info)
+    bool allow_incomplete = false;
     DecodePlan plan;
 };
 
 extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in, const uint64_t* in_off,
                                  uint32_t n, uint8_t* d_out, const uint64_t* out_off, lzb_batch** out) {
-    static const lzb_options defaults = {0, 0, 0, {0, 0, 0, 0, 0}, 0, 0};
+    static const lzb_options defaults = {0, 0, 0, 0, {0, 0, 0, 0}, 0, 0};
     if (!ctx || !out || !in_off || !out_off || (fmt != LZB_FMT_LZMA && fmt != LZB_FMT_LZMA2) || n == 0 || !d_in || !d_out)
         return LZB_RC_BAD_ARG;
     if (((uintptr_t)d_in & 15) || ((uintptr_t)d_out & 15)) return LZB_RC_BAD_ARG;
@@ -593,6 +594,7 @@ extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, 
     b->fmt = fmt;
     b->d_in = d_in;
     b->d_out = d_out;
+    b->allow_incomplete = opt && opt->allow_incomplete;
     cudaStream_t s = ctx->stream;
     auto fail = [&](int code) {
         lzb_batch_destroy(b);
@@ -655,7 +657,10 @@ extern "C" int lzb_batch_collect(lzb_batch* b, void* cuda_stream, uint64_t* out_
     std::vector<LzbResult> res(b->n);
     CUDA_TRY(ctx, cudaMemcpyAsync(res.data(), b->d_results.p, b->n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    lzb_options o = {};
+    o.allow_incomplete = b->allow_incomplete;
     for (uint32_t i = 0; i < b->n; i++) {
+        if (lzb::lenient_eof(b->fmt, &o, &res[i])) res[i].code = LZB_OK, res[i].sink_len = res[i].out_len;
         if (st) lzb::status_from_result(res[i], &st[i]);
         if (out_len) out_len[i] = res[i].sink_len;
         if (consumed) consumed[i] = b->items[i].hdr_len + res[i].consumed;

@@ -115,7 +115,7 @@ static void preset(LzbItem* it, int code, uint64_t a0 = 0) {
 
 // LzmaParams::read_header, lzma.rs:96-161
 void plan_lzma(const uint8_t* p, uint64_t len, uint64_t base_off, const lzb_options* opt, LzbItem* it, LzbScan* sc) {
-    static const lzb_options defaults = {0, 0, 0, {0, 0, 0, 0, 0}, 0, 0};
+    static const lzb_options defaults = {0, 0, 0, 0, {0, 0, 0, 0}, 0, 0};
     if (!opt) opt = &defaults;
     item_defaults(it, base_off, len);
     it->kind = LZB_ITEM_LZMA;
@@ -649,6 +649,14 @@ int decode_xz_batch(Executor& ex, const uint8_t* in, const uint64_t* in_off, uin
     return LZB_RC_OK;
 }
 
+// Options::allow_incomplete (options.rs:15-19, honoured by stream.rs:136-147): input that ends inside a symbol ends the
+// .lzma stream without an error, and everything decoded from complete symbols counts as output.  K1 reports the end
+// of input at the symbol boundary, before any side effect of the unfinished symbol, which is exactly what the
+// reference's dry run (lzma.rs:408-419, 470-483) leaves in the window.
+bool lenient_eof(int fmt, const lzb_options* opt, const LzbResult* r) {
+    return fmt == LZB_FMT_LZMA && opt && opt->allow_incomplete && r->code == LZB_E_IO_EOF;
+}
+
 // lzma_decompress[_with_options] / lzma2_decompress over a batch (lib.rs:44-60, 83-88): one work item per stream.
 int decode_batch(Executor& ex, int fmt, const lzb_options* opt, const uint8_t* in, const uint64_t* in_off, uint32_t n,
                  const uint64_t* out_off, StreamOut* outs) {
@@ -675,6 +683,7 @@ int decode_batch(Executor& ex, int fmt, const lzb_options* opt, const uint8_t* i
         if (rc != LZB_RC_OK) return rc;
     }
     for (uint32_t i = 0; i < n; i++) {
+        if (lenient_eof(fmt, opt, &results[i])) results[i].code = LZB_OK, results[i].sink_len = results[i].out_len;
         status_from_result(results[i], &outs[i].st);
         outs[i].out_len = results[i].sink_len;
         outs[i].consumed = items[i].hdr_len + results[i].consumed;

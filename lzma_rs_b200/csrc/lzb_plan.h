@@ -45,6 +45,7 @@ Lzma2Scan scan_lzma2(const uint8_t* p, uint64_t len);
 // .lzma header -> item (kind LZB_ITEM_LZMA or LZB_ITEM_PRESET).  in_off/in_len are relative to `base_off`.
 void plan_lzma(const uint8_t* p, uint64_t len, uint64_t base_off, const lzb_options* opt, LzbItem* it, LzbScan* sc);
 void plan_lzma2(const uint8_t* p, uint64_t len, uint64_t base_off, LzbItem* it, LzbScan* sc);
+bool lenient_eof(int fmt, const lzb_options* opt, const LzbResult* r);  // Options::allow_incomplete applies
 
 // Per-stream outcome of a batch call.
 struct StreamOut {

@@ -80,6 +80,7 @@ inline void lzma_decompress_with_options(std::istream& in, std::ostream& out, co
     n.provided = o.unpacked_size.value.value_or(0);
     n.has_memlimit = o.memlimit.has_value();
     n.memlimit = o.memlimit.value_or(0);
+    n.allow_incomplete = o.allow_incomplete;
     detail::run(LZB_FMT_LZMA, &n, in, out);
 }
 inline void lzma_decompress(std::istream& in, std::ostream& out) { lzma_decompress_with_options(in, out, {}); }

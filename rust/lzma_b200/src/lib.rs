@@ -61,7 +61,8 @@ struct LzbOptions {
     unpacked_mode: u8,
     has_provided: u8,
     has_memlimit: u8,
-    reserved: [u8; 5],
+    allow_incomplete: u8,
+    reserved: [u8; 4],
     provided: u64,
     memlimit: u64,
 }
@@ -170,7 +171,49 @@ fn options(o: &decompress::Options) -> LzbOptions {
         r.has_memlimit = 1;
         r.memlimit = m as u64;
     }
+    r.allow_incomplete = o.allow_incomplete as u8;
     r
+}
+
+/// `lzma_rs::decompress::Stream` (feature `stream`, src/decode/stream.rs:66-346) as a façade over the batch path:
+/// `write` buffers (and still rejects an invalid properties byte at once, stream.rs:157-190), `finish` decodes the
+/// whole stream on the GPU.  Same results as the reference; data errors surface in `finish` instead of `write`.
+pub struct Stream<W: io::Write> {
+    output: Option<W>,
+    buf: Vec<u8>,
+    options: decompress::Options,
+}
+impl<W: io::Write> Stream<W> {
+    pub fn new(output: W) -> Self { Self::new_with_options(&decompress::Options::default(), output) }
+    pub fn new_with_options(options: &decompress::Options, output: W) -> Self {
+        Stream { output: Some(output), buf: Vec::new(), options: *options }
+    }
+    pub fn get_output(&self) -> Option<&W> { self.output.as_ref() }
+    pub fn get_output_mut(&mut self) -> Option<&mut W> { self.output.as_mut() }
+    pub fn finish(mut self) -> error::Result<W> {
+        let mut out = self.output.take().ok_or_else(|| {
+            error::Error::LzmaError("can't finish stream because of previous write error".to_string())
+        })?;
+        if self.buf.is_empty() { return Ok(out); }
+        let hdr = if let decompress::UnpackedSize::UseProvided(_) = self.options.unpacked_size { 5 } else { 13 };
+        if self.buf.len() < hdr + 5 { return Err(error::Error::LzmaError("failed to read header".to_string())); }
+        run(FMT_LZMA, &options(&self.options), &mut &self.buf[..], &mut out)?;
+        Ok(out)
+    }
+}
+impl<W: io::Write> io::Write for Stream<W> {
+    fn write(&mut self, data: &[u8]) -> io::Result<usize> {
+        if self.output.is_none() { return Ok(0); }
+        let first = self.buf.is_empty();
+        self.buf.extend_from_slice(data);
+        if first && !self.buf.is_empty() && self.buf[0] >= 225 {
+            self.output = None;
+            return Err(io::Error::new(io::ErrorKind::Other,
+                format!("LZMA header invalid properties: {} must be < 225", self.buf[0])));
+        }
+        Ok(data.len())
+    }
+    fn flush(&mut self) -> io::Result<()> { match self.output.as_mut() { Some(o) => o.flush(), None => Ok(()) } }
 }
 
 /// `lzma_rs::lzma_decompress` (src/lib.rs:44-49)

@@ -380,3 +380,10 @@ def test_host_api_gated_upload(ctx):
     finally:
         del os.environ["LZB_NO_GATE"]
     assert outs2 == outs and (st2["code"] == st["code"]).all()
+
+
+def test_stream_facade(ctx):
+    """decompress::Stream façade on the device: the reference's own stream tests (src/decode/stream.rs:348-499),
+    including Options::allow_incomplete (known answer: half of small.txt's compressed bytes -> its first 26 bytes)."""
+    from test_stream_facade import check_stream_facade
+    check_stream_facade(ctx)
