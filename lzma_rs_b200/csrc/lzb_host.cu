@@ -207,8 +207,18 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
 // followed by order_big; d_counter holds two counters.
 int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem* d_items, const uint32_t* d_order,
                 const uint8_t* d_in_base, uint8_t* d_out_base, LzbResult* d_results, unsigned int* d_counter,
-                bool mirror = false, const unsigned long long* d_gate = nullptr) {
+                bool mirror = false, const unsigned long long* d_gate = nullptr,
+                std::function<int()>* before_first_kernel = nullptr) {
     CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned int), s));
+    // everything small this launch needs has been enqueued: now the gated upload of the input blob may occupy the copy
+    // engine.  It is enqueued BEFORE the kernel so that a launch that blocks the host (profilers, compute-sanitizer,
+    // CUDA_LAUNCH_BLOCKING) cannot wait for bytes nobody has sent yet.
+    auto fire = [&]() -> int {
+        if (!before_first_kernel || !*before_first_kernel) return LZB_RC_OK;
+        int rc = (*before_first_kernel)();
+        *before_first_kernel = nullptr;
+        return rc;
+    };
     const uint32_t ns = (uint32_t)p.order_small.size(), nb = (uint32_t)p.order_big.size();
     const LzbKC kc = LZB_KC_INIT;
     if (ns) {
@@ -232,6 +242,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
             CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[v], cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
             ctx->smem_configured[v] = ctx->smem_optin;
         }
+        if (int rc = fire()) return rc;
         kernels[v]<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, p.n_static, d_in_base, d_out_base, d_results,
                                                       d_counter, c.lclp, c.warp_bytes, ctx->d_matchws.as<uint16_t>(), mstride, kc,
                                                       mirror ? d_gate : nullptr);
@@ -246,6 +257,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
             ctx->smem_configured_big = ctx->smem_optin;
         }
         CUDA_TRY(ctx, ctx->d_litws.ensure((size_t)c.grid * c.warps * p.big_stride_u16 * 2));
+        if (int rc = fire()) return rc;
         lzb_decode_biglit_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order + ns, nb, 0u, d_in_base, d_out_base,
                                                                     d_results, d_counter + 1, c.lclp, c.warp_bytes,
                                                                     ctx->d_litws.as<uint16_t>(), p.big_stride_u16, kc,
@@ -271,14 +283,17 @@ class CudaExecutor : public lzb::Executor {
     CudaExecutor(lzb_ctx* ctx, cudaStream_t s, const uint8_t* d_in_base, uint8_t* d_out_base, uint8_t* host_mirror = nullptr,
                  const unsigned long long* d_gate = nullptr)
         : ctx_(ctx), s_(s), in_(d_in_base), out_(d_out_base), hmirror_(host_mirror), gate_(d_gate) {}
-    // Runs once, right after the first K1 launch has been enqueued: the gated upload of the input blob.  Issued after the
-    // launch so that the (small) uploads of the plan are not queued behind it on the copy engine.
-    std::function<int()> after_first_launch;
+    // Runs once, right before the first K1 launch is enqueued (after the small uploads of the plan, which must not queue
+    // behind it on the copy engine): the gated upload of the input blob.
+    std::function<int()> before_first_kernel;
+    cudaStream_t copy_stream = nullptr;  // where that upload runs
     Trace* trace = nullptr;
     bool all_mirrored() const { return hmirror_ != nullptr && !unmirrored_; }
 
     int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint64_t stored_bytes, LzbResult* results) override {
         int rc = run(items, n, max_lclp, stored_bytes, results);
+        if (rc != LZB_RC_OK) return rc;
+        rc = redo_timeouts(items, n, max_lclp, stored_bytes, results);
         if (rc != LZB_RC_OK) return rc;
         // the framing scan can under-estimate lc+lp on malformed LZMA2 streams: rerun just those with the maximum
         std::vector<uint32_t> redo;
@@ -353,6 +368,22 @@ class CudaExecutor : public lzb::Executor {
     }
 
    private:
+    // Streams whose input had not arrived within the gate's timeout (an environment that stalls the upload while K1
+    // runs): wait for the upload, then decode just those -- the gate is open by then.
+    int redo_timeouts(const LzbItem* items, uint32_t n, uint32_t lclp_hint, uint64_t stored_bytes, LzbResult* results) {
+        std::vector<uint32_t> redo;
+        for (uint32_t i = 0; i < n; i++)
+            if (results[i].code == LZB_E_INPUT_TIMEOUT) redo.push_back(i);
+        if (redo.empty()) return LZB_RC_OK;
+        if (copy_stream) CUDA_TRY(ctx_, cudaStreamSynchronize(copy_stream));
+        std::vector<LzbItem> sub(redo.size());
+        std::vector<LzbResult> subres(redo.size());
+        for (size_t k = 0; k < redo.size(); k++) sub[k] = items[redo[k]];
+        int rc = run(sub.data(), (uint32_t)sub.size(), lclp_hint, stored_bytes, subres.data());
+        if (rc != LZB_RC_OK) return rc;
+        for (size_t k = 0; k < redo.size(); k++) results[redo[k]] = subres[k];
+        return LZB_RC_OK;
+    }
     int run(const LzbItem* items, uint32_t n, uint32_t lclp_hint, uint64_t stored_bytes, LzbResult* results) {
         lzb_ctx* ctx = ctx_;
         DecodePlan plan;
@@ -385,16 +416,12 @@ class CudaExecutor : public lzb::Executor {
             cudaEventRecord(ev0, s_);
         }
         rc = launch_plan(ctx, s_, plan, ctx->d_items.as<LzbItem>(), ctx->d_order.as<uint32_t>(), in_, out_,
-                         ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>(), hmirror_ != nullptr, gate_);
+                         ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>(), hmirror_ != nullptr, gate_,
+                         &before_first_kernel);
         if (rc != LZB_RC_OK) return rc;
         if (tr) {
             cudaEventRecord(ev1, s_);
             trace->launched = trace->now();
-        }
-        if (after_first_launch) {
-            rc = after_first_launch();
-            after_first_launch = nullptr;
-            if (rc != LZB_RC_OK) return rc;
         }
         if (tr) trace->uploaded = trace->now();
         CUDA_TRY(ctx, cudaMemcpyAsync(results, ctx->d_results.p, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s_));
@@ -545,7 +572,8 @@ extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, c
         CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, in + in_lo, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     CudaExecutor ex(ctx, ctx->stream, d_in0 - in_lo, d_out0 - out_lo, host_mirror, d_gate);
-    ex.after_first_launch = upload;
+    ex.before_first_kernel = upload;
+    ex.copy_stream = upload ? ctx->copy_stream : nullptr;
     ex.trace = &trace;
     const double t_enq = trace.now();
     std::vector<lzb::StreamOut> outs(n);

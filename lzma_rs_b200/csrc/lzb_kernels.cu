@@ -33,8 +33,8 @@
 // device offset reached so far to gate[0].  A warp starts a stream once every 128-byte line the stream touches has
 // arrived (whole lines: K1 reads the blob through the non-coherent path, so a line must never be fetched before all of
 // it is there).  gate[1] = device offset minus blob offset, gate[2] = device offset of the end of the blob.
-// Returns false if the bytes did not arrive within 5 s (reported as LZB_E_INPUT_TIMEOUT; never seen in practice, it
-// keeps a lost copy from hanging the GPU).
+// Returns false if the bytes did not arrive within 5 s (LZB_E_INPUT_TIMEOUT: the host then waits for the upload and
+// decodes the stream again; it keeps a stalled copy from hanging the GPU).
 __device__ __noinline__ bool input_arrived(const LzbItem* it, const unsigned long long* gate) {
     if (it->kind == LZB_ITEM_PRESET || (it->flags & LZB_ITEM_F_IN_FROM_OUT)) return true;
     unsigned long long need = (it->in_off + it->in_len + gate[1] + 127ull) & ~127ull;
