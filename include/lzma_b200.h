@@ -191,6 +191,31 @@ void lzb_free(void *p);
 int lzb_crc_device(lzb_ctx *ctx, const uint8_t *d_data, const uint64_t *off, const uint64_t *len, uint32_t n,
                    uint32_t *crc32, uint64_t *crc64, void *cuda_stream);
 
+/* ---- compress side: lzma_rs::{lzma_compress, lzma_compress_with_options, lzma2_compress, xz_compress}
+ * (src/lib.rs:63-80, 91-97, 108-110).  The reference's encoders are format writers, not compressors: lzma_compress
+ * emits literals only (src/encode/dumbencoder.rs), lzma2_compress / xz_compress emit stored chunks only
+ * (src/encode/lzma2.rs, src/encode/xz.rs); the GPU writes the same bytes. ---- */
+typedef struct lzb_compress_options { /* compress::Options / UnpackedSize, src/encode/options.rs:1-30 (LZB_FMT_LZMA only) */
+    uint8_t skip_size_field;           /* UnpackedSize::SkipWritingToHeader */
+    uint8_t has_value;                 /* WriteToHeader(Some(value)): no end marker; WriteToHeader(None): marker */
+    uint8_t reserved[6];
+    uint64_t value;
+} lzb_compress_options;
+/* Output capacity stream of in_len bytes needs: exact for LZB_FMT_LZMA2 / LZB_FMT_XZ; for LZB_FMT_LZMA a bound that
+ * holds for any realistic input (in_len * 5/4 + 128) -- an adversarial input that needs more reports LZB_E_CAPACITY
+ * with the exact size in a0. */
+uint64_t lzb_encode_bound(int fmt, const lzb_compress_options *opt, uint64_t in_len);
+/* Encode n independent plaintexts from HOST memory into HOST memory: stream i = in[in_off[i], in_off[i+1]) ->
+ * out[out_off[i], ...), capacity out_off[i+1]-out_off[i]; out_len[i] = bytes written; st[i].code LZB_OK or
+ * LZB_E_CAPACITY (a0 = bytes needed).  opt may be NULL (= Options::default()). */
+int lzb_encode_batch(lzb_ctx *ctx, int fmt, const lzb_compress_options *opt, const uint8_t *in, const uint64_t *in_off,
+                     uint32_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_len, lzb_status *st);
+/* Same with DEVICE buffers (d_in readable up to the next multiple of 4 bytes past each plaintext); offsets and
+ * results are host arrays.  Runs on `cuda_stream` (NULL = the ctx's stream) and synchronises it. */
+int lzb_encode_batch_device(lzb_ctx *ctx, int fmt, const lzb_compress_options *opt, const uint8_t *d_in,
+                            const uint64_t *in_off, uint32_t n, uint8_t *d_out, const uint64_t *out_off,
+                            uint64_t *out_len, lzb_status *st, void *cuda_stream);
+
 /* Renders the reference's Display string for a status ("lzma error: ...", src/error.rs:28-37) into
  * buf (NUL-terminated, truncated to buf_len).  Returns the untruncated length. */
 size_t lzb_format_error(const lzb_status *st, char *buf, size_t buf_len);

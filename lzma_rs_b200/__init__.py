@@ -24,7 +24,8 @@ from . import _native
 
 __all__ = ["lzma_decompress", "lzma_decompress_with_options", "lzma2_decompress", "xz_decompress",
            "lzma_decompress_batch", "lzma2_decompress_batch", "xz_decompress_batch", "decompress", "error", "Context",
-           "Stream", "StreamResult"]
+           "Stream", "StreamResult", "compress", "lzma_compress", "lzma_compress_with_options", "lzma2_compress",
+           "xz_compress", "lzma_compress_batch", "lzma2_compress_batch", "xz_compress_batch"]
 
 
 class error:  # namespace mirroring lzma_rs::error (src/error.rs:7-37)
@@ -189,6 +190,33 @@ class decompress:  # namespace mirroring lzma_rs::decompress (src/decode/options
                 return _deliver(r, len(data), 0, reader, output)
 
 
+class compress:  # namespace mirroring lzma_rs::compress (src/encode/options.rs:1-30)
+    class UnpackedSize:
+        """UnpackedSize::{WriteToHeader(Option<u64>), SkipWritingToHeader}"""
+
+        def __init__(self, skip=False, value=None):
+            self.skip, self.value = skip, value
+
+        @classmethod
+        def WriteToHeader(cls, x=None):
+            return cls(False, x)
+
+        @classmethod
+        def SkipWritingToHeader(cls):
+            return cls(True)
+
+    class Options:
+        """compress::Options { unpacked_size } -- default WriteToHeader(None): unknown size + end marker"""
+
+        def __init__(self, unpacked_size=None):
+            self.unpacked_size = unpacked_size or compress.UnpackedSize.WriteToHeader(None)
+
+        def _native(self):
+            u = self.unpacked_size
+            return _native.CompressOptions(1 if u.skip else 0, 0 if (u.skip or u.value is None) else 1, (_C.c_uint8 * 6)(),
+                                           0 if (u.skip or u.value is None) else u.value)
+
+
 class Stream:
     """lzma_rs::decompress::Stream (feature `stream`, src/decode/stream.rs:66-346) as a façade over the batch path.
 
@@ -340,6 +368,30 @@ class Context:
             res.append(StreamResult(data, int(consumed[i]), st[i].copy(), disp))
         return res
 
+    def encode_batch(self, fmt, datas, options=None):
+        """lzb_encode_batch: the reference's encoders over a batch (fmt 0: literal-only .lzma, 1: stored-chunk LZMA2,
+        2: stored-chunk .xz).  Returns a list of bytes.  A .lzma stream that outgrows the default bound is retried with
+        the size the kernel reported."""
+        n = len(datas)
+        blob, in_off = _native.pack_streams(datas)
+        opt = (options or compress.Options())._native()
+        caps = _np.array([self._lib.lzb_encode_bound(fmt, _C.byref(opt), len(d)) for d in datas], dtype=_np.uint64)
+        while True:
+            out_off = _np.zeros(n + 1, dtype=_np.uint64)
+            _np.cumsum((caps + _np.uint64(15)) // _np.uint64(16) * _np.uint64(16), out=out_off[1:])
+            out = _np.empty(int(out_off[-1]) + 16, dtype=_np.uint8)
+            out_len = _np.zeros(n, dtype=_np.uint64)
+            st = _np.zeros(n, dtype=_native.STATUS_DTYPE)
+            rc = self._lib.lzb_encode_batch(self._h, fmt, _C.byref(opt), blob.ctypes.data, in_off.ctypes.data, n,
+                                            out.ctypes.data, out_off.ctypes.data, out_len.ctypes.data, st.ctypes.data)
+            if rc != _native.RC_OK:
+                raise RuntimeError(f"lzb_encode_batch failed rc={rc}: {self.last_error()}")
+            short = st["code"] == _native.E_CAPACITY
+            if not short.any():
+                break
+            caps = _np.where(short, st["a0"], caps).astype(_np.uint64)
+        return [out[int(out_off[i]):int(out_off[i]) + int(out_len[i])].tobytes() for i in range(n)]
+
     def decompress_one(self, fmt, data, options=None):
         """lzb_decompress_alloc: scan + decode (+ capacity retry for end-marker .lzma)."""
         opt = (options or decompress.Options())._native()
@@ -409,6 +461,46 @@ def lzma2_decompress(input, output=None):
 def xz_decompress(input, output=None):
     """lzma_rs::xz_decompress (src/lib.rs:100-105)."""
     return _one(_native.FMT_XZ, input, output, None)
+
+
+def _compress(fmt, inp, output, options):
+    data, _ = _read_all(inp)
+    enc = _ctx().encode_batch(fmt, [data], options)[0]
+    if output is not None:
+        output.write(enc)
+    return enc
+
+
+def lzma_compress(input, output=None):
+    """lzma_rs::lzma_compress (src/lib.rs:63-69): literal-only .lzma, like the reference's encoder."""
+    return _compress(_native.FMT_LZMA, input, output, None)
+
+
+def lzma_compress_with_options(input, output=None, options=None):
+    """lzma_rs::lzma_compress_with_options (src/lib.rs:72-80)."""
+    return _compress(_native.FMT_LZMA, input, output, options)
+
+
+def lzma2_compress(input, output=None):
+    """lzma_rs::lzma2_compress (src/lib.rs:91-97): stored chunks."""
+    return _compress(_native.FMT_LZMA2, input, output, None)
+
+
+def xz_compress(input, output=None):
+    """lzma_rs::xz_compress (src/lib.rs:108-110): one block of stored chunks, no check."""
+    return _compress(_native.FMT_XZ, input, output, None)
+
+
+def lzma_compress_batch(datas, options=None):
+    return _ctx().encode_batch(_native.FMT_LZMA, datas, options)
+
+
+def lzma2_compress_batch(datas):
+    return _ctx().encode_batch(_native.FMT_LZMA2, datas)
+
+
+def xz_compress_batch(datas):
+    return _ctx().encode_batch(_native.FMT_XZ, datas)
 
 
 def lzma_decompress_batch(streams, options=None):

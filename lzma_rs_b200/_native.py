@@ -22,6 +22,11 @@ class Options(C.Structure):  # lzb_options
                 ("allow_incomplete", C.c_uint8), ("reserved", C.c_uint8 * 4), ("provided", C.c_uint64), ("memlimit", C.c_uint64)]
 
 
+class CompressOptions(C.Structure):  # lzb_compress_options
+    _fields_ = [("skip_size_field", C.c_uint8), ("has_value", C.c_uint8), ("reserved", C.c_uint8 * 6),
+                ("value", C.c_uint64)]
+
+
 class Status(C.Structure):  # lzb_status
     _fields_ = [("code", C.c_int32), ("kind", C.c_int32), ("a0", C.c_uint64), ("a1", C.c_uint64), ("a2", C.c_uint64)]
 
@@ -32,7 +37,8 @@ assert STATUS_DTYPE.itemsize == C.sizeof(Status)
 # every symbol include/lzma_b200.h declares
 EXPORTS = ["lzb_create", "lzb_destroy", "lzb_last_error", "lzb_abi_version", "lzb_scan", "lzb_decode_batch",
            "lzb_decode_batch_device", "lzb_batch_prepare", "lzb_batch_launch", "lzb_batch_collect", "lzb_batch_destroy",
-           "lzb_batch_kernels_per_launch", "lzb_decompress_alloc", "lzb_free", "lzb_crc_device", "lzb_format_error"]
+           "lzb_batch_kernels_per_launch", "lzb_decompress_alloc", "lzb_free", "lzb_crc_device", "lzb_format_error",
+           "lzb_encode_bound", "lzb_encode_batch", "lzb_encode_batch_device"]
 
 _lib = None
 
@@ -77,6 +83,12 @@ def bind(path):
     lib.lzb_crc_device.argtypes = [vp, vp, u64p, u64p, C.c_uint32, vp, vp, vp]
     lib.lzb_format_error.argtypes = [C.POINTER(Status), C.c_char_p, C.c_size_t]
     lib.lzb_format_error.restype = C.c_size_t
+    if hasattr(lib, "lzb_encode_batch"):  # tools/kbench.py also binds older builds
+        lib.lzb_encode_bound.argtypes = [C.c_int, C.POINTER(CompressOptions), C.c_uint64]
+        lib.lzb_encode_bound.restype = C.c_uint64
+        lib.lzb_encode_batch.argtypes = [vp, C.c_int, C.POINTER(CompressOptions), vp, u64p, C.c_uint32, vp, u64p, u64p, vp]
+        lib.lzb_encode_batch_device.argtypes = [vp, C.c_int, C.POINTER(CompressOptions), vp, u64p, C.c_uint32, vp, u64p,
+                                                u64p, vp, vp]
     return lib
 
 

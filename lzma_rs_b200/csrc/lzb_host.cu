@@ -12,6 +12,7 @@
 #include <functional>
 #include <vector>
 
+#include "lzb_encode.h"
 #include "lzb_plan.h"
 #include "lzb_sched.h"
 #include "lzb_types.h"
@@ -42,6 +43,11 @@ extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, con
                                            LzbItem*, LzbScan*);
 extern "C" __global__ void lzb_crc_partial_kernel(const uint8_t*, const LzbCrcRange*, const uint32_t*, uint64_t,
                                                   uint32_t*, uint64_t*);
+extern "C" __global__ void lzb_store_kernel(const LzbEncItem*, const uint32_t*, const uint32_t*, const uint8_t*, uint8_t*,
+                                            uint32_t);
+extern "C" __global__ void lzb_frame_kernel(const LzbEncItem*, uint32_t, int, uint8_t*, const LzbXzHead, LzbEncResult*);
+extern "C" __global__ void lzb_literal_kernel(const LzbEncItem*, uint32_t, const uint8_t*, uint8_t*,
+                                              const lzb_compress_options, LzbEncResult*);
 extern "C" __global__ void lzb_crc_fold_kernel(const LzbCrcRange*, uint32_t, const uint32_t*, const uint64_t*,
                                                uint32_t*, uint64_t*);
 
@@ -87,7 +93,8 @@ struct lzb_ctx {
     char err[320] = {0};
     std::mutex mu;
     DevBuf d_in, d_out, d_items, d_results, d_order, d_counter, d_scan, d_off, d_crc_ranges, d_crc_segmap, d_crc_part32,
-        d_crc_part64, d_crc_out32, d_crc_out64, d_litws, d_matchws, d_gate;
+        d_crc_part64, d_crc_out32, d_crc_out64, d_litws, d_matchws, d_gate, d_enc_items, d_enc_results, d_enc_pieces;
+    int enc_smem_configured = 0;
 };
 #define LZB_GATE_CHUNK (8ull << 20)  // upload granularity of the gated host path
 #define LZB_GATE_MAX_CHUNKS 56
@@ -486,7 +493,8 @@ extern "C" void lzb_destroy(lzb_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_items, &ctx->d_results, &ctx->d_order, &ctx->d_counter, &ctx->d_scan,
                       &ctx->d_off, &ctx->d_crc_ranges, &ctx->d_crc_segmap, &ctx->d_crc_part32, &ctx->d_crc_part64,
-                      &ctx->d_crc_out32, &ctx->d_crc_out64, &ctx->d_litws, &ctx->d_matchws, &ctx->d_gate};
+                      &ctx->d_crc_out32, &ctx->d_crc_out64, &ctx->d_litws, &ctx->d_matchws, &ctx->d_gate,
+                      &ctx->d_enc_items, &ctx->d_enc_results, &ctx->d_enc_pieces};
     for (DevBuf* b : bufs) b->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -766,4 +774,119 @@ extern "C" int lzb_crc_device(lzb_ctx* ctx, const uint8_t* d_data, const uint64_
     for (uint32_t i = 0; i < n; i++) r[i] = lzb::CrcRange{off[i], len[i]};
     CudaExecutor ex(ctx, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, nullptr, const_cast<uint8_t*>(d_data));
     return ex.crc(r.data(), n, crc32, crc64);
+}
+
+// ------------------------------------------------------------------------------------------------
+// compress side (lzb_encode_kernels.cu)
+// ------------------------------------------------------------------------------------------------
+extern "C" uint64_t lzb_encode_bound(int fmt, const lzb_compress_options* opt, uint64_t in_len) {
+    (void)opt;
+    if (fmt == LZB_FMT_LZMA2 || fmt == LZB_FMT_XZ) return lzb_encode_exact(fmt, in_len);
+    return in_len + in_len / 4 + 128;
+}
+
+static uint32_t host_crc32(const uint8_t* p, size_t n) {
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) {
+        c ^= p[i];
+        for (int b = 0; b < 8; b++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+    }
+    return ~c;
+}
+
+extern "C" int lzb_encode_batch_device(lzb_ctx* ctx, int fmt, const lzb_compress_options* opt, const uint8_t* d_in,
+                                       const uint64_t* in_off, uint32_t n, uint8_t* d_out, const uint64_t* out_off,
+                                       uint64_t* out_len, lzb_status* st, void* cuda_stream) {
+    if (!ctx || !in_off || !out_off || !out_len || !st || fmt < 0 || fmt > 2) return LZB_RC_BAD_ARG;
+    if (n == 0) return LZB_RC_OK;
+    if (!d_in || !d_out) return LZB_RC_BAD_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    std::vector<LzbEncItem> items(n);
+    for (uint32_t i = 0; i < n; i++)
+        items[i] = LzbEncItem{in_off[i], in_off[i + 1] - in_off[i], out_off[i], out_off[i + 1] - out_off[i]};
+    CUDA_TRY(ctx, ctx->d_enc_items.ensure(n * sizeof(LzbEncItem)));
+    CUDA_TRY(ctx, ctx->d_enc_results.ensure(n * sizeof(LzbEncResult)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_enc_items.p, items.data(), n * sizeof(LzbEncItem), cudaMemcpyHostToDevice, s));
+    const LzbEncItem* d_items = ctx->d_enc_items.as<LzbEncItem>();
+    LzbEncResult* d_res = ctx->d_enc_results.as<LzbEncResult>();
+    if (fmt == LZB_FMT_LZMA) {  // K5: one thread per stream, 16 per CTA (12 KB of probabilities each)
+        static const lzb_compress_options defaults = {0, 0, {0, 0, 0, 0, 0, 0}, 0};
+        const int smem = LZB_ENC_LANES * LZB_ENC_TABLE_U16 * 2;
+        if (!ctx->enc_smem_configured) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(lzb_literal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            ctx->enc_smem_configured = 1;
+        }
+        const uint32_t grid = std::min<uint32_t>((n + LZB_ENC_LANES - 1) / LZB_ENC_LANES, (uint32_t)ctx->sm_count);
+        lzb_literal_kernel<<<grid, LZB_ENC_LANES, smem, s>>>(d_items, n, d_in, d_out, opt ? *opt : defaults, d_res);
+        CUDA_TRY(ctx, cudaGetLastError());
+    } else {  // K4: one CTA per 64 KiB piece of every stream that fits its capacity + one thread per stream for the frame
+        std::vector<uint32_t> piece_stream, first_piece(n);
+        for (uint32_t i = 0; i < n; i++) {
+            first_piece[i] = (uint32_t)piece_stream.size();
+            if (lzb_encode_exact(fmt, items[i].in_len) > items[i].out_cap) continue;
+            const uint64_t pieces = (items[i].in_len + 0xFFFFull) >> 16;
+            piece_stream.insert(piece_stream.end(), (size_t)pieces, i);
+        }
+        const size_t np = piece_stream.size();
+        CUDA_TRY(ctx, ctx->d_enc_pieces.ensure((np + n + 1) * 4));
+        uint32_t* d_piece_stream = ctx->d_enc_pieces.as<uint32_t>();
+        uint32_t* d_first_piece = d_piece_stream + np;
+        if (np) CUDA_TRY(ctx, cudaMemcpyAsync(d_piece_stream, piece_stream.data(), np * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_first_piece, first_piece.data(), n * 4, cudaMemcpyHostToDevice, s));
+        LzbXzHead head;  // write_header (xz.rs:31-45) + the block header of write_block (xz.rs:78-97)
+        static const uint8_t magic[8] = {0xFD, 0x37, 0x7A, 0x58, 0x5A, 0x00, /* StreamFlags: check None */ 0x00, 0x00};
+        static const uint8_t bh[8] = {8 >> 2, 0x00, 0x21, 1, 22, 0, 0, 0};
+        memcpy(head.b, magic, 8);
+        const uint32_t c1 = host_crc32(magic + 6, 2), c2 = host_crc32(bh, 8);
+        for (int i = 0; i < 4; i++) head.b[8 + i] = (uint8_t)(c1 >> (8 * i));
+        memcpy(head.b + 12, bh, 8);
+        for (int i = 0; i < 4; i++) head.b[20 + i] = (uint8_t)(c2 >> (8 * i));
+        if (np) {
+            lzb_store_kernel<<<(unsigned)np, 256, 0, s>>>(d_items, d_piece_stream, d_first_piece, d_in, d_out,
+                                                          fmt == LZB_FMT_XZ ? 24u : 0u);
+            CUDA_TRY(ctx, cudaGetLastError());
+        }
+        lzb_frame_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_items, n, fmt, d_out, head, d_res);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    std::vector<LzbEncResult> res(n);
+    CUDA_TRY(ctx, cudaMemcpyAsync(res.data(), d_res, n * sizeof(LzbEncResult), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < n; i++) {
+        memset(&st[i], 0, sizeof st[i]);
+        st[i].code = res[i].code;
+        st[i].kind = res[i].code == LZB_OK ? LZB_KIND_OK : LZB_KIND_INTERNAL;
+        st[i].a0 = res[i].code == LZB_OK ? 0 : res[i].out_len;
+        out_len[i] = res[i].code == LZB_OK ? res[i].out_len : 0;
+    }
+    return LZB_RC_OK;
+}
+
+extern "C" int lzb_encode_batch(lzb_ctx* ctx, int fmt, const lzb_compress_options* opt, const uint8_t* in,
+                                const uint64_t* in_off, uint32_t n, uint8_t* out, const uint64_t* out_off, uint64_t* out_len,
+                                lzb_status* st) {
+    if (!ctx || !in_off || !out_off || !out_len || !st || fmt < 0 || fmt > 2) return LZB_RC_BAD_ARG;
+    if (n == 0) return LZB_RC_OK;
+    if (!in || !out) return LZB_RC_BAD_ARG;
+    const uint64_t in_lo = in_off[0], in_hi = in_off[n], out_lo = out_off[0], out_hi = out_off[n];
+    uint8_t *d_in0, *d_out0;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        CUDA_TRY(ctx, ctx->d_in.ensure((in_hi - in_lo) + 64));
+        CUDA_TRY(ctx, ctx->d_out.ensure((out_hi - out_lo) + 64));
+        d_in0 = ctx->d_in.as<uint8_t>() + (in_lo & 15);
+        d_out0 = ctx->d_out.as<uint8_t>() + (out_lo & 15);
+        if (in_hi > in_lo)
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int rc = lzb_encode_batch_device(ctx, fmt, opt, d_in0 - in_lo, in_off, n, d_out0 - out_lo, out_off, out_len, st, nullptr);
+    if (rc != LZB_RC_OK) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (out_hi > out_lo)
+        CUDA_TRY(ctx, cudaMemcpyAsync(out + out_lo, d_out0, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LZB_RC_OK;
 }

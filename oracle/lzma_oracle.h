@@ -80,6 +80,19 @@ int lzo_decompress_batch(int fmt, const uint8_t *in, const uint64_t *in_off, uin
                          uint8_t *out, const uint64_t *out_off, uint64_t *out_len,
                          int32_t *kinds, int nthreads);
 
+/* ---- compress side (lzma_oracle_enc.c): src/lib.rs:63-80, 91-97, 108-110.  PARITY UNPINNED: the reference's tests hold
+ * no golden compressed vectors, only round trips; see the header of lzma_oracle_enc.c. ---- */
+/* compress::Options / compress::UnpackedSize, src/encode/options.rs:1-30 */
+typedef struct {
+    int skip_size_field; /* UnpackedSize::SkipWritingToHeader */
+    int has_value;       /* WriteToHeader(Some(value)) : no end marker; WriteToHeader(None) : 0xFFFF.. + end marker */
+    uint64_t value;
+} lzo_compress_options;
+int lzo_lzma_compress(const uint8_t *in, size_t n, const lzo_compress_options *opt, uint8_t **out, size_t *out_len);
+int lzo_lzma2_compress(const uint8_t *in, size_t n, uint8_t **out, size_t *out_len);
+int lzo_xz_compress(const uint8_t *in, size_t n, uint8_t **out, size_t *out_len);
+void lzo_buffer_free(uint8_t *p);
+
 /* CRC-32/ISO-HDLC and CRC-64/XZ (crate `crc` 3.x catalogue entries used by src/xz/crc.rs:3-4) */
 uint32_t lzo_crc32(const uint8_t *p, size_t n);
 uint64_t lzo_crc64(const uint8_t *p, size_t n);

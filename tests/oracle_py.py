@@ -25,14 +25,18 @@ class _Opt(C.Structure):
                 ("has_memlimit", C.c_int), ("memlimit", C.c_uint64)]
 
 
+class _COpt(C.Structure):  # lzo_compress_options
+    _fields_ = [("skip_size_field", C.c_int), ("has_value", C.c_int), ("value", C.c_uint64)]
+
+
 class _Res(C.Structure):
     _fields_ = [("out", C.POINTER(C.c_uint8)), ("out_len", C.c_size_t), ("consumed", C.c_size_t), ("err", _Err)]
 
 
 def build():
     """Compile the oracle if the .so is missing or stale."""
-    src = os.path.join(ORACLE_DIR, "lzma_oracle.c")
-    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("lzma_oracle.c", "lzma_oracle_enc.c", "lzma_oracle.h")]
+    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
 
 
@@ -51,6 +55,11 @@ def lib():
         _lib.lzo_error_display.argtypes = [C.POINTER(_Err), C.c_char_p, C.c_size_t]
         _lib.lzo_decompress_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_int]
+        for f in (_lib.lzo_lzma2_compress, _lib.lzo_xz_compress):
+            f.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
+        _lib.lzo_lzma_compress.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_COpt), C.POINTER(C.POINTER(C.c_uint8)),
+                                           C.POINTER(C.c_size_t)]
+        _lib.lzo_buffer_free.argtypes = [C.POINTER(C.c_uint8)]
         _lib.lzo_crc32.argtypes = [C.c_char_p, C.c_size_t]
         _lib.lzo_crc32.restype = C.c_uint32
         _lib.lzo_crc64.argtypes = [C.c_char_p, C.c_size_t]
@@ -132,3 +141,25 @@ def decompress_batch(fmt, blob, in_off, out_off, nthreads):
     failed = lib().lzo_decompress_batch(fmt, blob.ctypes.data, in_off.ctypes.data, n, out.ctypes.data,
                                         out_off.ctypes.data, out_len.ctypes.data, kinds.ctypes.data, nthreads)
     return out, out_len, kinds, failed
+
+
+def _take(fn, *args):
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    assert fn(*args, C.byref(out), C.byref(n)) == 0
+    data = C.string_at(out, n.value) if n.value else b""
+    lib().lzo_buffer_free(out)
+    return data
+
+
+def lzma_compress(data, skip_size_field=False, value=None):
+    """lzma_compress_with_options (src/lib.rs:72-80): WriteToHeader(value) / SkipWritingToHeader."""
+    o = _COpt(1 if skip_size_field else 0, 0 if value is None else 1, 0 if value is None else value)
+    return _take(lib().lzo_lzma_compress, bytes(data), len(data), C.byref(o))
+
+
+def lzma2_compress(data):
+    return _take(lib().lzo_lzma2_compress, bytes(data), len(data))
+
+
+def xz_compress(data):
+    return _take(lib().lzo_xz_compress, bytes(data), len(data))

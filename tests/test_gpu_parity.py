@@ -387,3 +387,51 @@ def test_stream_facade(ctx):
     including Options::allow_incomplete (known answer: half of small.txt's compressed bytes -> its first 26 bytes)."""
     from test_stream_facade import check_stream_facade
     check_stream_facade(ctx)
+
+
+def test_gpu_encoders(ctx):
+    """Compress side: lzma_compress / lzma2_compress / xz_compress on the GPU write exactly the bytes
+    of the oracle's restatement of the reference's encoders, for every option, at chunk-size edges and in ragged batches;
+    and the reference's own round-trip tests (tests/lzma.rs:16-28,146-168, tests/lzma2.rs, tests/xz.rs:30-52) pass
+    through GPU encode -> GPU decode."""
+    import lzma
+    import lzma_rs_b200 as L
+    rng = np.random.default_rng(77)
+    datas = [b"", b"a", b"Hello world", bytes(65535), bytes(65536), bytes(65537), b"\xff" * (1 << 20), bytes(1 << 20),
+             corpus.mixed_text(901, 200_000), rng.bytes(3 * 65536 + 17)]
+    datas += [corpus.mixed_text(1000 + i, int(rng.integers(0, 150_000))) for i in range(120)]
+    CO, US = L.compress.Options, L.compress.UnpackedSize
+    got = ctx.encode_batch(1, datas)
+    assert got == [oracle.lzma2_compress(d) for d in datas]
+    got = ctx.encode_batch(2, datas)
+    assert got == [oracle.xz_compress(d) for d in datas]
+    assert all(lzma.decompress(x, format=lzma.FORMAT_XZ) == d for x, d in zip(got[:12], datas[:12]))
+    small = datas[:6] + datas[8:40]
+    got = ctx.encode_batch(0, small)
+    assert got == [oracle.lzma_compress(d) for d in small]
+    got = ctx.encode_batch(0, small, CO(US.SkipWritingToHeader()))
+    assert got == [oracle.lzma_compress(d, skip_size_field=True) for d in small]
+    got = ctx.encode_batch(0, small[:8], CO(US.WriteToHeader(1234)))
+    assert got == [oracle.lzma_compress(d, value=1234) for d in small[:8]]
+    # capacity too small is a per-stream status, the neighbours are untouched
+    from lzma_rs_b200 import _native
+    import ctypes as C
+    blob, in_off = _native.pack_streams([b"x" * 1000, b"y" * 1000, b"z" * 1000])
+    out_off = np.array([0, 1008, 1008 + 500, 1008 + 500 + 1008], dtype=np.uint64)
+    out = np.zeros(int(out_off[-1]) + 16, dtype=np.uint8)
+    ol, st = np.zeros(3, dtype=np.uint64), np.zeros(3, dtype=_native.STATUS_DTYPE)
+    assert _native.load().lzb_encode_batch(ctx.handle, 1, None, blob.ctypes.data, in_off.ctypes.data, 3, out.ctypes.data,
+                                           out_off.ctypes.data, ol.ctypes.data, st.ctypes.data) == 0
+    assert st["code"].tolist() == [0, _native.E_CAPACITY, 0] and int(st[1]["a0"]) == 1004 and ol.tolist() == [1004, 0, 1004]
+    assert out[1008:1508].tobytes() == bytes(500)
+    # round trips through the public API, the reference's own test inputs
+    for d in (b"", b"Hello world", bytes(1 << 20), b"\xff" * (1 << 20), datas[8]):
+        assert L.lzma2_decompress(L.lzma2_compress(d)) == d
+        assert L.xz_decompress(L.xz_compress(d)) == d
+    for d in (b"", b"Hello world", datas[8]):
+        assert L.lzma_decompress(L.lzma_compress(d)) == d
+        enc = L.lzma_compress_with_options(d, None, CO(US.WriteToHeader(len(d))))
+        assert L.lzma_decompress(enc) == d
+        enc = L.lzma_compress_with_options(d, None, CO(US.SkipWritingToHeader()))
+        opts = L.decompress.Options(unpacked_size=L.decompress.UnpackedSize.UseProvided(len(d)))
+        assert L.lzma_decompress_with_options(enc, None, opts) == d
