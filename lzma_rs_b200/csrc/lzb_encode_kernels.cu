@@ -14,6 +14,7 @@
 
 #include "lzb_decode_core.h"  // warp_copy
 #include "lzb_encode.h"
+#include "lzb_types.h"
 
 // ------------------------------------------------------------------------------------------------
 // K4: stored chunks (lzma2.rs:4-26: status 1, BE u16 size - 1, payload; 0x00 after the last chunk)
@@ -216,5 +217,44 @@ extern "C" __global__ void __launch_bounds__(LZB_ENC_LANES)
         r.pad = 0;
         r.out_len = e.pos;
         results[s] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: decode of LZMA2 streams that consist of stored chunks only (LZB_ITEM_F_ALL_STORED: the framing scan walked them
+// to their 0x00 terminator with every payload complete, and the output fits) -- "LZMA2 uncompressed chunks become
+// straight memcpy".  One CTA per stream walks the 3-byte chunk headers (parse_uncompressed, lzma2.rs:195-229; a dict
+// reset changes nothing for data that is only copied) and its 8 warps copy 8 KiB slices of each chunk.
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(256)
+    lzb_stored_decode_kernel(const LzbItem* __restrict__ items, const uint32_t* __restrict__ list,
+                             const uint8_t* __restrict__ in, uint8_t* out, LzbResult* results) {
+    const uint32_t idx = list[blockIdx.x];
+    const LzbItem it = items[idx];
+    const uint8_t* p = in + it.in_off;
+    uint8_t* o = out + it.out_off;
+    const int lane = threadIdx.x & 31;
+    const uint32_t w0 = (threadIdx.x >> 5) * 8192u;
+    uint64_t q = 0, opos = 0;
+    uint32_t chunks = 0;
+    for (;;) {
+        const uint32_t status = __ldg(p + q);
+        chunks++;
+        q++;
+        if (status == 0) break;
+        const uint32_t n = ((__ldg(p + q) << 8) | __ldg(p + q + 1)) + 1;
+        q += 2;
+        if (w0 < n) warp_copy<true>(o + opos + w0, p + q + w0, n - w0 < 8192u ? n - w0 : 8192u, lane);
+        opos += n;
+        q += n;
+    }
+    if (threadIdx.x == 0) {
+        LzbResult r;
+        r.code = LZB_OK;
+        r.chunks = chunks;
+        r.a0 = r.a1 = 0;
+        r.out_len = r.sink_len = opos;
+        r.consumed = q;
+        results[idx] = r;
     }
 }

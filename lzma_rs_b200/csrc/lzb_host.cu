@@ -43,6 +43,7 @@ extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, con
                                            LzbItem*, LzbScan*);
 extern "C" __global__ void lzb_crc_partial_kernel(const uint8_t*, const LzbCrcRange*, const uint32_t*, uint64_t,
                                                   uint32_t*, uint64_t*);
+extern "C" __global__ void lzb_stored_decode_kernel(const LzbItem*, const uint32_t*, const uint8_t*, uint8_t*, LzbResult*);
 extern "C" __global__ void lzb_store_kernel(const LzbEncItem*, const uint32_t*, const uint32_t*, const uint8_t*, uint8_t*,
                                             uint32_t);
 extern "C" __global__ void lzb_frame_kernel(const LzbEncItem*, uint32_t, int, uint8_t*, const LzbXzHead, LzbEncResult*);
@@ -145,6 +146,7 @@ LaunchCfg decode_config(const lzb_ctx* ctx, uint32_t n, uint32_t lclp) {
 // lc+lp <= 4) and .lzma streams with lc+lp > 4 whose literal table goes to a global workspace.
 struct DecodePlan {
     std::vector<uint32_t> order_small, order_big;  // item indices, longest compressed stream first
+    std::vector<uint32_t> order_stored;            // stored-chunk-only LZMA2 streams: copy kernel, no range decoder
     LaunchCfg cfg_small{}, cfg_big{};
     uint32_t n_small = 0;         // streams of the first launch (order_small may also hold LZB_ORDER_PARK entries)
     uint32_t n_static = 0;        // leading order_small entries that are pre-assigned first items (lzb_sched.h)
@@ -154,14 +156,25 @@ struct DecodePlan {
 };
 
 void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lzma2_lclp_hint, uint64_t stored_bytes,
-               DecodePlan* p) {
+               DecodePlan* p, bool route_stored = true) {
     uint32_t lclp_small = 0, lclp_big = 0;
+    // stored-chunk-only streams whose output fits go to the copy kernel (not with a host mirror: that kernel does not
+    // stream pages to the host); everything below plans K1 for the rest
+    auto stored_route = [&](const LzbItem& it) {
+        return route_stored && it.kind == LZB_ITEM_LZMA2 && (it.flags & LZB_ITEM_F_ALL_STORED) &&
+               !(it.flags & LZB_ITEM_F_IN_FROM_OUT) && it.unpacked <= it.out_cap;
+    };
+    p->order_stored.clear();
     // K1 variants beside the lean default (which is 3-6 % faster on everything else: instruction-cache footprint):
     // vector stored-chunk copies when stored chunks carry >= 80 % of the batch's output (break-even measured at ~5x the
     // range-coded bytes: C3 with 3 stored chunks in 8 192 streams lost 6 % to the copy code it never needed), word-wide
     // run fills when the batch expands so much (> 16x) that it must be long runs
     uint64_t in_sum = 0, cap_sum = 0;
     for (uint32_t i = 0; i < n; i++) {
+        if (stored_route(items[i])) {
+            stored_bytes -= std::min<uint64_t>(stored_bytes, items[i].unpacked);
+            continue;
+        }
         in_sum += items[i].in_len;
         cap_sum += items[i].out_cap;
     }
@@ -170,7 +183,9 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
     p->order_big.clear();
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t lclp = (uint32_t)items[i].lc + items[i].lp;
-        if (items[i].kind == LZB_ITEM_LZMA && lclp > 4) {
+        if (stored_route(items[i])) {
+            p->order_stored.push_back(i);
+        } else if (items[i].kind == LZB_ITEM_LZMA && lclp > 4) {
             p->order_big.push_back(i);
             lclp_big = std::max(lclp_big, lclp);
         } else {
@@ -227,6 +242,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         return rc;
     };
     const uint32_t ns = (uint32_t)p.order_small.size(), nb = (uint32_t)p.order_big.size();
+    const uint32_t nst = (uint32_t)p.order_stored.size();
     const LzbKC kc = LZB_KC_INIT;
     if (ns) {
         const LaunchCfg& c = p.cfg_small;
@@ -271,12 +287,19 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
                                                                     mirror ? d_gate : nullptr);
         CUDA_TRY(ctx, cudaGetLastError());
     }
+    if (nst) {
+        if (int rc = fire()) return rc;
+        lzb_stored_decode_kernel<<<nst, 256, 0, s>>>(d_items, d_order + ns + nb, d_in_base, d_out_base, d_results);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     return LZB_RC_OK;
 }
 
 int upload_order(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, DevBuf& d_order) {
-    const size_t ns = p.order_small.size(), nb = p.order_big.size();
-    CUDA_TRY(ctx, d_order.ensure((ns + nb) * 4 + 4));
+    const size_t ns = p.order_small.size(), nb = p.order_big.size(), nst = p.order_stored.size();
+    CUDA_TRY(ctx, d_order.ensure((ns + nb + nst) * 4 + 4));
+    if (nst)
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_order.as<uint32_t>() + ns + nb, p.order_stored.data(), nst * 4, cudaMemcpyHostToDevice, s));
     if (ns) CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, p.order_small.data(), ns * 4, cudaMemcpyHostToDevice, s));
     if (nb) CUDA_TRY(ctx, cudaMemcpyAsync(d_order.as<uint32_t>() + ns, p.order_big.data(), nb * 4, cudaMemcpyHostToDevice, s));
     return LZB_RC_OK;
@@ -394,7 +417,7 @@ class CudaExecutor : public lzb::Executor {
     int run(const LzbItem* items, uint32_t n, uint32_t lclp_hint, uint64_t stored_bytes, LzbResult* results) {
         lzb_ctx* ctx = ctx_;
         DecodePlan plan;
-        make_plan(ctx, items, n, lclp_hint, stored_bytes, &plan);
+        make_plan(ctx, items, n, lclp_hint, stored_bytes, &plan, /*route_stored=*/hmirror_ == nullptr);
         CUDA_TRY(ctx, ctx->d_items.ensure(n * sizeof(LzbItem)));
         CUDA_TRY(ctx, ctx->d_results.ensure(n * sizeof(LzbResult)));
         CUDA_TRY(ctx, ctx->d_counter.ensure(64));
@@ -683,7 +706,7 @@ extern "C" int lzb_batch_launch(lzb_batch* b, void* cuda_stream) {
 }
 
 extern "C" int lzb_batch_kernels_per_launch(const lzb_batch* b) {
-    return b ? (int)!b->plan.order_small.empty() + (int)!b->plan.order_big.empty() : 0;
+    return b ? (int)!b->plan.order_small.empty() + (int)!b->plan.order_big.empty() + (int)!b->plan.order_stored.empty() : 0;
 }
 
 extern "C" int lzb_batch_collect(lzb_batch* b, void* cuda_stream, uint64_t* out_len, uint64_t* consumed, lzb_status* st) {

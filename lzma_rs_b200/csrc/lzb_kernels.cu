@@ -246,6 +246,10 @@ extern "C" __global__ void lzb_scan_kernel(int fmt, lzb_options opt, const uint8
         }
         sc.unpacked = total;
         sc.max_lclp = (uint8_t)maxl;
+        if ((sc.flags & 1) && total > 0 && sc.stored == total) {
+            it.flags |= LZB_ITEM_F_ALL_STORED;
+            it.unpacked = total;
+        }
     }
     if (len > 0xFFFFE000ull) {
         it.kind = LZB_ITEM_PRESET;

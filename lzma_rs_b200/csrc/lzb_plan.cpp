@@ -161,6 +161,10 @@ void plan_lzma2(const uint8_t* p, uint64_t len, uint64_t base_off, LzbItem* it, 
     sc->unpacked = s.unpacked;
     sc->flags = (s.well_formed ? 1u : 0u) | (s.stored ? 2u : 0u);
     sc->stored = s.stored;
+    if (s.well_formed && s.unpacked > 0 && s.stored == s.unpacked) {
+        it->flags |= LZB_ITEM_F_ALL_STORED;
+        it->unpacked = s.unpacked;
+    }
     sc->max_lclp = (uint8_t)s.max_lclp;
     if (len > 0xFFFFE000ull) preset(it, LZB_E_UNSUPPORTED);
 }

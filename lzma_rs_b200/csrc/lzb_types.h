@@ -27,7 +27,10 @@ struct LzbItem {
 enum { LZB_ITEM_LZMA = 0, LZB_ITEM_LZMA2 = 1, LZB_ITEM_PRESET = 2 };
 // in_off addresses the OUTPUT blob: the stream is the output of an earlier launch (chained .xz filters, xz.rs:240-249)
 // out_off addresses device scratch outside the caller's output region (never mirrored to the host)
-enum { LZB_ITEM_F_IN_FROM_OUT = 1, LZB_ITEM_F_OUT_SCRATCH = 2 };
+// the framing scan found a well-formed LZMA2 stream made of stored chunks only (what the reference's own encoders write,
+// src/encode/lzma2.rs:4-26); `unpacked` then holds its size.  Such streams need no range decoder: they are routed to
+// the stored-chunk copy kernel (lzb_stored_decode_kernel) when their output fits the capacity.
+enum { LZB_ITEM_F_IN_FROM_OUT = 1, LZB_ITEM_F_OUT_SCRATCH = 2, LZB_ITEM_F_ALL_STORED = 4 };
 #define LZB_UNKNOWN_SIZE 0xFFFFFFFFFFFFFFFFull
 // K1's order array: a warp whose pre-assigned first entry is this value takes no part in the launch (lzb_sched.h)
 #define LZB_ORDER_PARK 0xFFFFFFFFu

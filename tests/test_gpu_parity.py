@@ -435,3 +435,52 @@ def test_gpu_encoders(ctx):
         enc = L.lzma_compress_with_options(d, None, CO(US.SkipWritingToHeader()))
         opts = L.decompress.Options(unpacked_size=L.decompress.UnpackedSize.UseProvided(len(d)))
         assert L.lzma_decompress_with_options(enc, None, opts) == d
+
+
+def test_stored_only_route(ctx):
+    """LZMA2 streams made of stored chunks only (what the reference's own encoder writes) are decoded by the copy kernel
+    (lzb_stored_decode_kernel) instead of K1; everything else in the same batch still goes through K1.  Device path."""
+    import struct
+    import gpu_util
+    rng = np.random.default_rng(3)
+
+    def stored(data, sizes, first_status=1, other_status=2):
+        out, pos = bytearray(), 0
+        for k, n in enumerate(sizes):
+            out += bytes([first_status if k == 0 else other_status]) + struct.pack(">H", n - 1) + data[pos:pos + n]
+            pos += n
+        assert pos == len(data)
+        return bytes(out) + b"\0"
+
+    big = rng.bytes(5 * 65536 + 123)
+    odd = rng.bytes(70_001)
+    streams = [
+        corpus.stored_lzma2(big),                                        # reference encoder shape
+        stored(odd, [1, 65536, 2, 4461, 1]),                              # ragged chunk sizes, status 1 then 2
+        stored(odd[:10], [10], first_status=2),                           # never a dict reset: allowed
+        corpus.stored_lzma2(big)[:-1],                                    # terminator missing -> K1 reports the error
+        corpus.stored_lzma2(odd) + b"trailing bytes",                     # consumed stops after the 0x00
+        corpus.raw_lzma2(corpus.mixed_text(4, 100_000), dict_size=1 << 20),  # ordinary compressed stream
+        b"\0",                                                            # empty stream
+        corpus.stored_lzma2(big),                                         # capacity too small below
+    ]
+    caps = [len(big), len(odd), 10, len(big), len(odd), 100_000, 0, 1000]
+    b = gpu_util.DeviceBatch(ctx, 1, streams, caps).decode()
+    for i, s in enumerate(streams):
+        w = oracle.lzma2_decompress(s)
+        if i == 7:
+            assert b.st[i]["code"] == -1  # LZB_E_CAPACITY from K1
+            continue
+        assert (b.st[i]["code"] == 0) == w.ok, (i, b.display(i), w.display)
+        assert b.output(i) == w.out, i
+        if w.ok:
+            assert int(b.consumed[i]) == w.consumed, i
+        else:
+            assert b.display(i) == w.display, i
+    # a large all-stored batch, every byte checked
+    datas = [rng.bytes(int(rng.integers(1, 400_000))) for _ in range(64)]
+    streams = [corpus.stored_lzma2(d) for d in datas] * 8
+    b = gpu_util.DeviceBatch(ctx, 1, streams, [len(d) for d in datas] * 8).decode()
+    assert (b.st["code"] == 0).all()
+    for i in range(len(streams)):
+        assert b.output(i) == datas[i % 64] and int(b.consumed[i]) == len(streams[i])
