@@ -304,16 +304,13 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
 // bring dst to a 4-byte boundary, the body stores aligned 32-bit words assembled from two aligned source words with
 // a funnel shift (128 B per warp instruction instead of 32), the tail goes byte-wise.  SRC_CONST: the source is the
 // read-only input blob (ld.global.nc).
-// Deliberately NOT inlined: its 20 live registers, inlined into decode_item, push ptxas into allocating the decode
-// state in uniform registers, and the whole bit loop then runs on the (slow, single) uniform datapath -- measured 44 %
-// slower (tools/check_sass.py guards the build against that flip).  The call happens once per stored chunk.
+// Register pressure matters beyond this function: inlined into decode_item with 4 vectors per lane in flight (LZB_COPY_U
+// = 4, +20 live registers) it pushes ptxas into allocating K1's decode state in uniform registers, and the whole bit
+// loop then runs on the (single) uniform datapath -- measured 44 % slower (profiles/r01_uniform_flip.md;
+// tools/check_sass.py guards the build).  2 vectors per lane keep the normal allocation in every K1 variant; a
+// __noinline__ call was tried and flips more variants, not fewer.  K4 / K6 (lzb_encode_kernels.cu) use it as is.
 template <bool SRC_CONST>
-#if defined(__CUDACC__) && defined(LZB_COPY_NOINLINE)
-__device__ __noinline__ void warp_copy(
-#else
-LZB_DEV void warp_copy(
-#endif
-uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+LZB_DEV void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
 #ifndef __CUDACC__
     (void)lane;
     for (uint32_t k = 0; k < n; k++) dst[k] = src[k];  // 1-lane emulation: plain copy
@@ -321,9 +318,8 @@ uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
 #endif
 #ifdef __CUDACC__
     // dst is brought to a 16-byte boundary; the body stores aligned 16-byte vectors (512 B per warp instruction),
-    // each assembled from five aligned source words with funnel shifts.  Four vectors per lane are loaded before the
-    // first is stored (SRC_CONST loads are non-coherent, so nothing orders them behind the stores): 80 B per lane,
-    // 2.5 KB per warp, ~70 KB per SM in flight -- what a copy needs to cover HBM latency at 28 warps per SM.
+    // each assembled from five aligned source words with funnel shifts.  LZB_COPY_U vectors per lane are loaded before
+    // the first is stored (SRC_CONST loads are non-coherent, so nothing orders them behind the stores).
     uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
     if (head > n) head = n;
     if ((uint32_t)lane < head) dst[lane] = SRC_CONST ? LZB_LDG(src + lane) : src[lane];

@@ -483,6 +483,7 @@ static int plan_file(Executor& ex, XzFile& f, std::vector<LzbItem>& items, uint3
         Lzma2Scan sc = scan_lzma2(f.p + bp.bh.payload, f.len - bp.bh.payload);
         *max_lclp = std::max(*max_lclp, sc.max_lclp);
         *stored += sc.stored;
+        const bool all_stored = sc.well_formed && sc.unpacked > 0 && sc.stored == sc.unpacked;
         bp.pred_packed = sc.packed;
         bp.pred_unpacked = sc.unpacked;
         bp.out_rel = out_rel;
@@ -497,6 +498,10 @@ static int plan_file(Executor& ex, XzFile& f, std::vector<LzbItem>& items, uint3
         item_defaults(&it, f.in_base + bp.bh.payload, f.len - bp.bh.payload);
         it.out_off = f.out_base + out_rel;
         it.out_cap = bp.cap;
+        if (all_stored) {  // what the reference's own xz_compress writes: eligible for the stored-chunk copy kernel
+            it.flags |= LZB_ITEM_F_ALL_STORED;
+            it.unpacked = sc.unpacked;
+        }
         if (it.in_len > 0xFFFFE000ull) preset(&it, LZB_E_UNSUPPORTED);
         bp.item = (uint32_t)items.size();
         items.push_back(it);
