@@ -110,3 +110,106 @@ def decode_sharded(decode_fn, streams, n_total, src=0, group=None):
     idx, mine = scatter_streams(streams, src, group)
     outs = decode_fn(mine) if len(mine) else []
     return gather_outputs(idx, outs, n_total, src, group)
+
+
+# ------------------------------------------------------------------------------------------------
+# Device-resident form: the batch is ONE blob tensor on the source rank (a GPU tensor under NCCL).  Ranks get
+# CONTIGUOUS ranges of streams, balanced by compressed bytes, so that scatter and gather are plain slices of the
+# input / output blobs -- no packing pass, one NCCL send/recv per peer and direction over NVLink.
+# ------------------------------------------------------------------------------------------------
+def partition_contiguous(in_off, world):
+    """Stream index ranges [lo, hi) per rank: cut points where the cumulative compressed size crosses k/world."""
+    in_off = np.asarray(in_off, dtype=np.uint64)
+    n = len(in_off) - 1
+    base, total = int(in_off[0]), int(in_off[-1] - in_off[0])
+    cuts = [0]
+    for k in range(1, world):
+        target = base + total * k // world
+        c = int(np.searchsorted(in_off, np.uint64(target), side="left"))
+        cuts.append(min(max(c, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def align16(x):
+    return (np.asarray(x, dtype=np.uint64) + np.uint64(15)) // np.uint64(16) * np.uint64(16)
+
+
+def decode_sharded_tensors(decode_fn, blob, in_off, caps, src=0, group=None):
+    """scatter -> local decode -> gather on tensors.
+
+    On `src`: `blob` = uint8 tensor holding all streams (on the device under NCCL), `in_off` = n+1 uint64 offsets
+    into it, `caps` = n output capacities.  Other ranks pass None.  `decode_fn(blob_t, in_off, out_off, out_t)`
+    decodes this rank's shard in place (blob_t / out_t live where the backend wants them; offsets are numpy
+    uint64 arrays relative to those tensors) and returns (out_len, codes) numpy arrays.
+    Returns on `src`: (out tensor, out_off, out_len, codes) for the whole batch; elsewhere None."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = _dev(group)
+    if rank == src:
+        in_off = np.asarray(in_off, dtype=np.uint64)
+        out_off_all = np.zeros(len(in_off), dtype=np.uint64)
+        np.cumsum(align16(caps), out=out_off_all[1:])
+        ranges = partition_contiguous(in_off, world)
+        meta = [(in_off[lo:hi + 1].copy(), out_off_all[lo:hi + 1].copy()) for lo, hi in ranges]
+    else:
+        meta = None
+    box = [None]
+    dist.scatter_object_list(box, meta, src=src, group=group)  # offsets only
+    my_in, my_out = box[0]
+    n_loc = len(my_in) - 1
+    in_lo, in_hi, out_lo, out_hi = int(my_in[0]), int(my_in[-1]), int(my_out[0]), int(my_out[-1])
+    # 16 bytes of slack behind every shard: the kernels read whole aligned words
+    if rank == src:
+        out_all = torch.zeros(int(out_off_all[-1]) + 16, dtype=torch.uint8, device=dev)
+        reqs = []
+        for r, (lo, hi) in enumerate(ranges):
+            if r != src and in_off[hi] > in_off[lo]:
+                reqs.append(dist.isend(blob[int(in_off[lo]):int(in_off[hi])], dst=r, group=group))
+        shard, shard_base = blob, 0  # the source decodes straight out of the full blob
+        out_t, out_base = out_all, 0
+    else:
+        shard = torch.zeros(in_hi - in_lo + 16, dtype=torch.uint8, device=dev)
+        if in_hi > in_lo:
+            dist.recv(shard[:in_hi - in_lo], src=src, group=group)
+        shard_base = in_lo
+        out_t, out_base = torch.zeros(out_hi - out_lo + 16, dtype=torch.uint8, device=dev), out_lo
+        reqs = []
+    if n_loc:
+        out_len, codes = decode_fn(shard, my_in - np.uint64(shard_base), my_out - np.uint64(out_base), out_t)
+    else:
+        out_len, codes = np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.int32)
+    for q in reqs:
+        q.wait()
+    # gather: decoded shards are contiguous slices of the full output blob
+    res = [None] * world if rank == src else None
+    dist.gather_object((np.asarray(out_len), np.asarray(codes)), res, dst=src, group=group)
+    if rank != src:
+        if out_hi > out_lo:
+            dist.send(out_t[:out_hi - out_lo], dst=src, group=group)
+        return None
+    for r, (lo, hi) in enumerate(ranges):
+        if r != src and out_off_all[hi] > out_off_all[lo]:
+            dist.recv(out_all[int(out_off_all[lo]):int(out_off_all[hi])], src=r, group=group)
+    return out_all, out_off_all, np.concatenate([x[0] for x in res]), np.concatenate([x[1] for x in res])
+
+
+def cuda_decode_fn(ctx, fmt=1, options=None):
+    """decode_fn for decode_sharded_tensors on a GPU box: lzb_decode_batch_device on this rank's context."""
+    import ctypes as C
+    from . import _native, decompress
+
+    def fn(blob_t, in_off, out_off, out_t):
+        n = len(in_off) - 1
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+        out_len, consumed = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        st = np.zeros(n, dtype=_native.STATUS_DTYPE)
+        opt = (options or decompress.Options())._native()
+        rc = _native.load().lzb_decode_batch_device(ctx.handle, fmt, C.byref(opt), blob_t.data_ptr(), in_off.ctypes.data, n,
+                                                    out_t.data_ptr(), out_off.ctypes.data, out_len.ctypes.data,
+                                                    consumed.ctypes.data, st.ctypes.data, None)
+        if rc != 0:
+            raise RuntimeError(f"lzb_decode_batch_device failed rc={rc}: {ctx.last_error()}")
+        return out_len, st["code"].astype(np.int32)
+
+    return fn

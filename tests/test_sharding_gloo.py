@@ -33,6 +33,31 @@ def _worker(rank, world, port, q):
     ok = True
     if rank == 0:
         ok = out == plains
+
+    # tensor form: one blob on the source, contiguous ranges per rank, slices sent / received in place
+    import torch
+    from lzma_rs_b200 import _native
+
+    def decode_t(blob_t, in_off, out_off, out_t):
+        m = len(in_off) - 1
+        out_len, codes = np.zeros(m, dtype=np.uint64), np.zeros(m, dtype=np.int32)
+        b, o = blob_t.numpy(), out_t.numpy()
+        for i in range(m):
+            r = oracle_py.lzma2_decompress(b[int(in_off[i]):int(in_off[i + 1])].tobytes())
+            codes[i] = r.kind
+            out_len[i] = len(r.out)
+            o[int(out_off[i]):int(out_off[i]) + len(r.out)] = np.frombuffer(r.out, dtype=np.uint8)
+        return out_len, codes
+
+    if rank == 0:
+        blob, in_off = _native.pack_streams(streams)
+        res = sharding.decode_sharded_tensors(decode_t, torch.from_numpy(blob), in_off, [len(p) for p in plains], src=0)
+        out_t, out_off, out_len, codes = res
+        o = out_t.numpy()
+        ok = ok and (codes == 0).all() and all(
+            o[int(out_off[i]):int(out_off[i]) + int(out_len[i])].tobytes() == plains[i] for i in range(n))
+    else:
+        assert sharding.decode_sharded_tensors(decode_t, None, None, None, src=0) is None
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, ok))
@@ -49,6 +74,21 @@ def test_lpt_partition_balances_and_covers():
         loads = np.array([lens[p].sum() for p in parts])
         assert loads.max() - loads.min() <= lens.max()  # LPT bound
     assert [len(p) for p in lpt_partition([], 4)] == [0, 0, 0, 0]
+
+
+def test_partition_contiguous_balances_and_covers():
+    from lzma_rs_b200.sharding import partition_contiguous
+    rng = np.random.default_rng(4)
+    lens = rng.integers(0, 1 << 18, size=3000)
+    off = np.zeros(3001, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    off += np.uint64(48)  # a batch that starts inside a larger buffer
+    for world in (1, 2, 3, 8):
+        r = partition_contiguous(off, world)
+        assert r[0][0] == 0 and r[-1][1] == 3000 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        loads = np.array([int(off[h] - off[l]) for l, h in r])
+        assert loads.max() - loads.min() <= 2 * lens.max()
+    assert partition_contiguous(np.zeros(1, dtype=np.uint64), 4) == [(0, 0)] * 4
 
 
 def test_scatter_decode_gather_world2():
