@@ -582,8 +582,10 @@ static int validate_file(Executor& ex, XzFile& f, const std::vector<LzbItem>& it
         f.out_pos = bp.out_rel + unpacked;
         f.records.push_back(Record{(c.pos - bp.bh.start) - pad, unpacked});
         f.pos = c.pos;
-        if ((packed != bp.pred_packed || unpacked != bp.pred_unpacked) && k + 1 < f.plan.size()) {
-            f.lookahead = false;  // later blocks were planned at the wrong offsets
+        if ((packed != bp.pred_packed || unpacked != bp.pred_unpacked) && (k + 1 < f.plan.size() || f.terminal != T_NONE)) {
+            // everything planned behind this block -- later blocks, but also the index or a header error found at the
+            // predicted position -- was read at the wrong offset: plan again from the real end of this block
+            f.lookahead = false;
             return LZB_RC_OK;
         }
     }

@@ -31,3 +31,24 @@ def test_emulated_kernel_matches_oracle(family):
         bad += parity.check_group(_decode, fmt, dict(okey), named)
         n += len(named)
     assert not bad, f"{len(bad)}/{n} mismatches:\n" + "\n".join(bad[:40])
+
+
+def fuzz_regressions():
+    """Inputs on which tools/fuzz_soak.py once found a mismatch (tests/golden/fuzz_regressions/<seed>-r<round>-f<fmt>-<i>.bin)."""
+    import glob
+    import os
+    import re
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_regressions")
+    out = {}
+    for path in sorted(glob.glob(os.path.join(d, "*.bin"))):
+        fmt = int(re.search(r"-f(\d)-", os.path.basename(path)).group(1))
+        out.setdefault(fmt, []).append((os.path.basename(path), open(path, "rb").read()))
+    return out
+
+
+def test_fuzz_regressions():
+    regs = fuzz_regressions()
+    assert regs
+    for fmt, named in regs.items():
+        bad = parity.check_group(_decode, fmt, {}, named)
+        assert not bad, "\n".join(bad)

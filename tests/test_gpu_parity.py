@@ -484,3 +484,12 @@ def test_stored_only_route(ctx):
     assert (b.st["code"] == 0).all()
     for i in range(len(streams)):
         assert b.output(i) == datas[i % 64] and int(b.consumed[i]) == len(streams[i])
+
+
+def test_fuzz_regressions_on_gpu(ctx):
+    """Inputs on which the fuzz soak once found a mismatch (e.g. an .xz block whose real end differs from the framing
+    scan's prediction, followed by the index: the terminal had been read at the predicted offset)."""
+    from test_emul_parity import fuzz_regressions
+    for fmt, named in fuzz_regressions().items():
+        bad = parity.check_group(_host(ctx), fmt, {}, named)
+        assert not bad, "\n".join(bad)
