@@ -88,6 +88,10 @@ struct lzb_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t gate_ready = nullptr;
     unsigned long long* h_marks = nullptr;  // pinned: [0..2] initial gate words, [8..] one watermark per chunk
+    // lzb_decode_batch_device keeps ONE batch object alive between calls: its device buffers are reused instead of
+    // paying six cudaMalloc / cudaFree (each a device synchronisation) per call
+    struct lzb_batch* oneshot = nullptr;
+    std::mutex oneshot_mu;
     int sm_count = 0;
     int smem_optin = 0;
     int smem_configured[12] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1}, smem_configured_big = -1;
@@ -514,6 +518,10 @@ extern "C" void lzb_destroy(lzb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->oneshot) {
+        lzb_batch_destroy(ctx->oneshot);
+        ctx->oneshot = nullptr;
+    }
     DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_items, &ctx->d_results, &ctx->d_order, &ctx->d_counter, &ctx->d_scan,
                       &ctx->d_off, &ctx->d_crc_ranges, &ctx->d_crc_segmap, &ctx->d_crc_part32, &ctx->d_crc_part64,
                       &ctx->d_crc_out32, &ctx->d_crc_out64, &ctx->d_litws, &ctx->d_matchws, &ctx->d_gate,
@@ -638,16 +646,15 @@ struct lzb_batch {
     DecodePlan plan;
 };
 
-extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in, const uint64_t* in_off,
-                                 uint32_t n, uint8_t* d_out, const uint64_t* out_off, lzb_batch** out) {
+// Fills `b` (a fresh batch, or one whose device buffers are being reused) for one batch of streams.
+static int batch_prepare_into(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in, const uint64_t* in_off,
+                              uint32_t n, uint8_t* d_out, const uint64_t* out_off, lzb_batch* b) {
     static const lzb_options defaults = {0, 0, 0, 0, {0, 0, 0, 0}, 0, 0};
-    if (!ctx || !out || !in_off || !out_off || (fmt != LZB_FMT_LZMA && fmt != LZB_FMT_LZMA2) || n == 0 || !d_in || !d_out)
+    if (!ctx || !in_off || !out_off || (fmt != LZB_FMT_LZMA && fmt != LZB_FMT_LZMA2) || n == 0 || !d_in || !d_out)
         return LZB_RC_BAD_ARG;
     if (((uintptr_t)d_in & 15) || ((uintptr_t)d_out & 15)) return LZB_RC_BAD_ARG;
-    *out = nullptr;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    lzb_batch* b = new lzb_batch();
     b->ctx = ctx;
     b->n = n;
     b->fmt = fmt;
@@ -655,10 +662,7 @@ extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, 
     b->d_out = d_out;
     b->allow_incomplete = opt && opt->allow_incomplete;
     cudaStream_t s = ctx->stream;
-    auto fail = [&](int code) {
-        lzb_batch_destroy(b);
-        return code;
-    };
+    auto fail = [&](int code) { return code; };
 #define B_TRY(call)                                                                                   \
     do {                                                                                              \
         cudaError_t e_ = (call);                                                                      \
@@ -693,9 +697,27 @@ extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, 
     make_plan(ctx, b->items.data(), n, lclp, stored_bytes, &b->plan);
     if (upload_order(ctx, s, b->plan, b->d_order) != LZB_RC_OK) return fail(LZB_RC_CUDA);
     B_TRY(cudaStreamSynchronize(s));
-    *out = b;
     return LZB_RC_OK;
 #undef B_TRY
+}
+
+extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in, const uint64_t* in_off,
+                                 uint32_t n, uint8_t* d_out, const uint64_t* out_off, lzb_batch** out) {
+    if (!out) return LZB_RC_BAD_ARG;
+    *out = nullptr;
+    lzb_batch* b = new lzb_batch();
+    int rc = batch_prepare_into(ctx, fmt, opt, d_in, in_off, n, d_out, out_off, b);
+    if (rc != LZB_RC_OK) {
+        if (ctx) {
+            b->ctx = ctx;
+            lzb_batch_destroy(b);
+        } else {
+            delete b;
+        }
+        return rc;
+    }
+    *out = b;
+    return LZB_RC_OK;
 }
 
 extern "C" int lzb_batch_launch(lzb_batch* b, void* cuda_stream) {
@@ -729,7 +751,7 @@ extern "C" int lzb_batch_collect(lzb_batch* b, void* cuda_stream, uint64_t* out_
 
 extern "C" void lzb_batch_destroy(lzb_batch* b) {
     if (!b) return;
-    cudaSetDevice(b->ctx->device);
+    if (b->ctx) cudaSetDevice(b->ctx->device);
     DevBuf* bufs[] = {&b->d_items, &b->d_results, &b->d_order, &b->d_counter, &b->d_scan, &b->d_off};
     for (DevBuf* x : bufs) x->release();
     delete b;
@@ -739,13 +761,18 @@ extern "C" int lzb_decode_batch_device(lzb_ctx* ctx, int fmt, const lzb_options*
                                        const uint64_t* in_off, uint32_t n, uint8_t* d_out, const uint64_t* out_off,
                                        uint64_t* out_len, uint64_t* consumed, lzb_status* st, void* cuda_stream) {
     if (n == 0) return LZB_RC_OK;
-    lzb_batch* b = nullptr;
-    int rc = lzb_batch_prepare(ctx, fmt, opt, d_in, in_off, n, d_out, out_off, &b);
+    if (!ctx) return LZB_RC_BAD_ARG;
+    std::lock_guard<std::mutex> one(ctx->oneshot_mu);
+    if (!ctx->oneshot) {
+        ctx->oneshot = new lzb_batch();
+        ctx->oneshot->ctx = ctx;
+    }
+    lzb_batch* b = ctx->oneshot;
+    int rc = batch_prepare_into(ctx, fmt, opt, d_in, in_off, n, d_out, out_off, b);
     if (rc != LZB_RC_OK) return rc;
     if (cuda_stream) cudaStreamSynchronize(ctx->stream);  // prepare ran on the ctx stream
     rc = lzb_batch_launch(b, cuda_stream);
     if (rc == LZB_RC_OK) rc = lzb_batch_collect(b, cuda_stream, out_len, consumed, st);
-    lzb_batch_destroy(b);
     return rc;
 }
 

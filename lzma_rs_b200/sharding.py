@@ -142,37 +142,46 @@ def decode_sharded_tensors(decode_fn, blob, in_off, caps, src=0, group=None):
     into it, `caps` = n output capacities.  Other ranks pass None.  `decode_fn(blob_t, in_off, out_off, out_t)`
     decodes this rank's shard in place (blob_t / out_t live where the backend wants them; offsets are numpy
     uint64 arrays relative to those tensors) and returns (out_len, codes) numpy arrays.
-    Returns on `src`: (out tensor, out_off, out_len, codes) for the whole batch; elsewhere None."""
+    Returns on `src`: (out tensor, out_off, out_len, codes) for the whole batch; elsewhere None.
+    All metadata travels as int64 tensors (two small broadcasts, one small send per peer): no pickling on the path."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = _dev(group)
+    head = torch.zeros(2, dtype=torch.int64, device=dev)
     if rank == src:
         in_off = np.asarray(in_off, dtype=np.uint64)
-        out_off_all = np.zeros(len(in_off), dtype=np.uint64)
+        n = len(in_off) - 1
+        out_off_all = np.zeros(n + 1, dtype=np.uint64)
         np.cumsum(align16(caps), out=out_off_all[1:])
         ranges = partition_contiguous(in_off, world)
-        meta = [(in_off[lo:hi + 1].copy(), out_off_all[lo:hi + 1].copy()) for lo, hi in ranges]
-    else:
-        meta = None
-    box = [None]
-    dist.scatter_object_list(box, meta, src=src, group=group)  # offsets only
-    my_in, my_out = box[0]
-    n_loc = len(my_in) - 1
+        cuts = np.array([r[0] for r in ranges] + [n], dtype=np.int64)
+        head[0] = n
+        meta = torch.from_numpy(np.concatenate([cuts, in_off.astype(np.int64), out_off_all.astype(np.int64)])).to(dev)
+    dist.broadcast(head, src=src, group=group)
+    n = int(head[0])
+    if rank != src:
+        meta = torch.empty(world + 1 + 2 * (n + 1), dtype=torch.int64, device=dev)
+    dist.broadcast(meta, src=src, group=group)
+    m = meta.cpu().numpy()
+    cuts, in_all, out_all_off = m[:world + 1], m[world + 1:world + 1 + n + 1].astype(np.uint64), m[world + 2 + n:].astype(np.uint64)
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    my_in, my_out = in_all[lo:hi + 1], out_all_off[lo:hi + 1]
+    n_loc = hi - lo
     in_lo, in_hi, out_lo, out_hi = int(my_in[0]), int(my_in[-1]), int(my_out[0]), int(my_out[-1])
     # 16 bytes of slack behind every shard: the kernels read whole aligned words
     if rank == src:
-        out_all = torch.zeros(int(out_off_all[-1]) + 16, dtype=torch.uint8, device=dev)
+        out_t = torch.zeros(int(out_all_off[-1]) + 16, dtype=torch.uint8, device=dev)
         reqs = []
-        for r, (lo, hi) in enumerate(ranges):
-            if r != src and in_off[hi] > in_off[lo]:
-                reqs.append(dist.isend(blob[int(in_off[lo]):int(in_off[hi])], dst=r, group=group))
-        shard, shard_base = blob, 0  # the source decodes straight out of the full blob
-        out_t, out_base = out_all, 0
+        for r in range(world):
+            a, b = int(in_all[cuts[r]]), int(in_all[cuts[r + 1]])
+            if r != src and b > a:
+                reqs.append(dist.isend(blob[a:b], dst=r, group=group))
+        shard, shard_base, out_base = blob, 0, 0  # the source decodes straight out of / into the full blobs
     else:
         shard = torch.zeros(in_hi - in_lo + 16, dtype=torch.uint8, device=dev)
         if in_hi > in_lo:
             dist.recv(shard[:in_hi - in_lo], src=src, group=group)
-        shard_base = in_lo
-        out_t, out_base = torch.zeros(out_hi - out_lo + 16, dtype=torch.uint8, device=dev), out_lo
+        shard_base, out_base = in_lo, out_lo
+        out_t = torch.zeros(out_hi - out_lo + 16, dtype=torch.uint8, device=dev)
         reqs = []
     if n_loc:
         out_len, codes = decode_fn(shard, my_in - np.uint64(shard_base), my_out - np.uint64(out_base), out_t)
@@ -180,17 +189,28 @@ def decode_sharded_tensors(decode_fn, blob, in_off, caps, src=0, group=None):
         out_len, codes = np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.int32)
     for q in reqs:
         q.wait()
-    # gather: decoded shards are contiguous slices of the full output blob
-    res = [None] * world if rank == src else None
-    dist.gather_object((np.asarray(out_len), np.asarray(codes)), res, dst=src, group=group)
+    # gather: decoded shards are contiguous slices of the full output blob; per-stream results ride along as int64
     if rank != src:
+        res = torch.from_numpy(np.concatenate([np.asarray(out_len, dtype=np.int64), np.asarray(codes, dtype=np.int64)])).to(dev)
+        if n_loc:
+            dist.send(res, dst=src, group=group)
         if out_hi > out_lo:
             dist.send(out_t[:out_hi - out_lo], dst=src, group=group)
         return None
-    for r, (lo, hi) in enumerate(ranges):
-        if r != src and out_off_all[hi] > out_off_all[lo]:
-            dist.recv(out_all[int(out_off_all[lo]):int(out_off_all[hi])], src=r, group=group)
-    return out_all, out_off_all, np.concatenate([x[0] for x in res]), np.concatenate([x[1] for x in res])
+    all_len, all_codes = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.int32)
+    all_len[lo:hi], all_codes[lo:hi] = out_len, codes
+    for r in range(world):
+        a, b = int(cuts[r]), int(cuts[r + 1])
+        if r == src or b == a:
+            continue
+        res = torch.empty(2 * (b - a), dtype=torch.int64, device=dev)
+        dist.recv(res, src=r, group=group)
+        oa, ob = int(out_all_off[a]), int(out_all_off[b])
+        if ob > oa:
+            dist.recv(out_t[oa:ob], src=r, group=group)
+        rn = res.cpu().numpy()
+        all_len[a:b], all_codes[a:b] = rn[:b - a].astype(np.uint64), rn[b - a:].astype(np.int32)
+    return out_t, out_all_off, all_len, all_codes
 
 
 def cuda_decode_fn(ctx, fmt=1, options=None):

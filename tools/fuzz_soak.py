@@ -72,6 +72,8 @@ def main():
     ap.add_argument("--rounds", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--per-format", type=int, default=400)
+    ap.add_argument("--cases", action="store_true",
+                    help="mutate the streams of the parity corpus (tests/cases.py: hand-encoded, chained .xz, ...) instead")
     a = ap.parse_args()
     import corpus
     import parity
@@ -85,8 +87,16 @@ def main():
         decode = test_emul_parity._decode
     rnd = random.Random(a.seed)
     total, bad_total, t0 = 0, 0, time.time()
+    case_seeds = None
+    if a.cases:
+        import cases
+        case_seeds = {0: [], 1: [], 2: []}
+        for fam in ("valid_lzma2_cases", "valid_lzma_cases", "hand_encoded_cases", "xz_cases", "xz_chain_cases"):
+            for name, fmt, stream, opts in getattr(cases, fam)():
+                if not opts and len(stream) < 70_000:
+                    case_seeds[fmt].append(stream)
     for rd in range(a.rounds):
-        seeds = seeds_for(rnd, corpus)
+        seeds = seeds_for(rnd, corpus) if case_seeds is None else {f: rnd.sample(v, min(len(v), 40)) for f, v in case_seeds.items()}
         for fmt, srcs in seeds.items():
             named = [(f"r{rd}-f{fmt}-{i}", mutate(rnd, srcs[i % len(srcs)])) for i in range(a.per_format)]
             bad = parity.check_group(decode, fmt, {}, named)
