@@ -225,6 +225,8 @@ def cuda_decode_fn(ctx, fmt=1, options=None):
         out_len, consumed = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
         st = np.zeros(n, dtype=_native.STATUS_DTYPE)
         opt = (options or decompress.Options())._native()
+        # the shard was received by NCCL in order of torch's current stream; the library works on its own stream
+        torch.cuda.current_stream().synchronize()
         rc = _native.load().lzb_decode_batch_device(ctx.handle, fmt, C.byref(opt), blob_t.data_ptr(), in_off.ctypes.data, n,
                                                     out_t.data_ptr(), out_off.ctypes.data, out_len.ctypes.data,
                                                     consumed.ctypes.data, st.ctypes.data, None)
