@@ -85,6 +85,50 @@ inline void lzma_decompress_with_options(std::istream& in, std::ostream& out, co
 }
 inline void lzma_decompress(std::istream& in, std::ostream& out) { lzma_decompress_with_options(in, out, {}); }
 
+// lzma_rs::{lzma_compress, lzma_compress_with_options, lzma2_compress, xz_compress} (src/lib.rs:63-80, 91-97, 108-110).
+// The reference's encoders are format writers (literals only / stored chunks only); the GPU writes the same bytes.
+namespace compress {
+struct UnpackedSize {  // src/encode/options.rs:10-24
+    bool skip_writing_to_header = false;
+    std::optional<uint64_t> value;  // WriteToHeader(value)
+};
+struct Options {
+    UnpackedSize unpacked_size;
+};
+}  // namespace compress
+namespace detail {
+inline void encode(int fmt, const lzb_compress_options* opt, std::istream& in, std::ostream& out) {
+    std::vector<uint8_t> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    uint64_t cap = lzb_encode_bound(fmt, opt, buf.size());
+    for (;;) {
+        std::vector<uint8_t> o((size_t)cap + 16);
+        const uint64_t in_off[2] = {0, buf.size()}, out_off[2] = {0, cap};
+        uint64_t out_len = 0;
+        lzb_status st{};
+        static const uint8_t none = 0;
+        int rc = lzb_encode_batch(ctx(), fmt, opt, buf.empty() ? &none : buf.data(), in_off, 1, o.data(), out_off, &out_len, &st);
+        if (rc != LZB_RC_OK) throw std::runtime_error(std::string("lzma_b200: ") + lzb_last_error(ctx()));
+        if (st.code == LZB_E_CAPACITY) {
+            cap = st.a0;
+            continue;
+        }
+        out.write(reinterpret_cast<const char*>(o.data()), (std::streamsize)out_len);
+        out.flush();
+        return;
+    }
+}
+}  // namespace detail
+inline void lzma_compress_with_options(std::istream& in, std::ostream& out, const compress::Options& o) {
+    lzb_compress_options n{};
+    n.skip_size_field = o.unpacked_size.skip_writing_to_header;
+    n.has_value = !o.unpacked_size.skip_writing_to_header && o.unpacked_size.value.has_value();
+    n.value = o.unpacked_size.value.value_or(0);
+    detail::encode(LZB_FMT_LZMA, &n, in, out);
+}
+inline void lzma_compress(std::istream& in, std::ostream& out) { lzma_compress_with_options(in, out, {}); }
+inline void lzma2_compress(std::istream& in, std::ostream& out) { detail::encode(LZB_FMT_LZMA2, nullptr, in, out); }
+inline void xz_compress(std::istream& in, std::ostream& out) { detail::encode(LZB_FMT_XZ, nullptr, in, out); }
+
 // lzma_rs::decompress::raw (feature `raw_decoder`, src/lib.rs:29-35).  The reference keeps a decoder's probability
 // state between two decompress() calls unless reset() is called; the GPU path always starts from a fresh state, so a
 // second decompress() without reset() throws instead of decoding something else.

@@ -76,6 +76,14 @@ struct LzbStatus {
     a2: u64,
 }
 #[repr(C)]
+#[derive(Default, Clone, Copy)]
+struct LzbCompressOptions {
+    skip_size_field: u8,
+    has_value: u8,
+    reserved: [u8; 6],
+    value: u64,
+}
+#[repr(C)]
 struct LzbCtx {
     _private: [u8; 0],
 }
@@ -86,6 +94,11 @@ extern "C" {
         out_len: *mut usize, consumed: *mut usize, st: *mut LzbStatus,
     ) -> c_int;
     fn lzb_free(p: *mut c_void);
+    fn lzb_encode_bound(fmt: c_int, opt: *const LzbCompressOptions, in_len: u64) -> u64;
+    fn lzb_encode_batch(
+        ctx: *mut LzbCtx, fmt: c_int, opt: *const LzbCompressOptions, input: *const u8, in_off: *const u64, n: u32,
+        out: *mut u8, out_off: *const u64, out_len: *mut u64, st: *mut LzbStatus,
+    ) -> c_int;
     fn lzb_format_error(st: *const LzbStatus, buf: *mut c_char, buf_len: usize) -> usize;
 }
 const FMT_LZMA: c_int = 0;
@@ -226,6 +239,69 @@ pub fn lzma_decompress_with_options<R: io::BufRead, W: io::Write>(
 ) -> error::Result<()> {
     run(FMT_LZMA, &options(opts), input, output)
 }
+/// `lzma_rs::compress` (src/encode/options.rs:1-30)
+pub mod compress {
+    #[derive(Clone, Copy, Debug)]
+    pub enum UnpackedSize {
+        WriteToHeader(Option<u64>),
+        SkipWritingToHeader,
+    }
+    impl Default for UnpackedSize {
+        fn default() -> UnpackedSize { UnpackedSize::WriteToHeader(None) }
+    }
+    #[derive(Clone, Copy, Debug, Default)]
+    pub struct Options {
+        pub unpacked_size: UnpackedSize,
+    }
+}
+
+// The reference's encoders are format writers (literals only / stored chunks only); the GPU writes the same bytes.
+fn encode<R: io::BufRead, W: io::Write>(fmt: c_int, opt: &LzbCompressOptions, input: &mut R, output: &mut W) -> io::Result<()> {
+    let mut buf = Vec::new();
+    input.read_to_end(&mut buf)?;
+    let mut cap = unsafe { lzb_encode_bound(fmt, opt, buf.len() as u64) };
+    loop {
+        let mut out = vec![0u8; cap as usize + 16];
+        let (in_off, out_off) = ([0u64, buf.len() as u64], [0u64, cap]);
+        let (mut out_len, mut st) = (0u64, LzbStatus::default());
+        let rc = with_ctx(|c| unsafe {
+            lzb_encode_batch(c, fmt, opt, buf.as_ptr(), in_off.as_ptr(), 1, out.as_mut_ptr(), out_off.as_ptr(), &mut out_len, &mut st)
+        })?;
+        if rc != 0 {
+            return Err(io::Error::new(io::ErrorKind::Other, format!("lzma_b200 call failed: {}", rc)));
+        }
+        if st.code == -1 { // LZB_E_CAPACITY: a0 = bytes needed (adversarial input for the literal coder)
+            cap = st.a0;
+            continue;
+        }
+        return output.write_all(&out[..out_len as usize]);
+    }
+}
+/// `lzma_rs::lzma_compress` (src/lib.rs:63-69)
+pub fn lzma_compress<R: io::BufRead, W: io::Write>(input: &mut R, output: &mut W) -> io::Result<()> {
+    lzma_compress_with_options(input, output, &compress::Options::default())
+}
+/// `lzma_rs::lzma_compress_with_options` (src/lib.rs:72-80)
+pub fn lzma_compress_with_options<R: io::BufRead, W: io::Write>(
+    input: &mut R, output: &mut W, options: &compress::Options,
+) -> io::Result<()> {
+    let mut o = LzbCompressOptions::default();
+    match options.unpacked_size {
+        compress::UnpackedSize::SkipWritingToHeader => o.skip_size_field = 1,
+        compress::UnpackedSize::WriteToHeader(Some(x)) => { o.has_value = 1; o.value = x; }
+        compress::UnpackedSize::WriteToHeader(None) => {}
+    }
+    encode(FMT_LZMA, &o, input, output)
+}
+/// `lzma_rs::lzma2_compress` (src/lib.rs:91-97)
+pub fn lzma2_compress<R: io::BufRead, W: io::Write>(input: &mut R, output: &mut W) -> io::Result<()> {
+    encode(FMT_LZMA2, &LzbCompressOptions::default(), input, output)
+}
+/// `lzma_rs::xz_compress` (src/lib.rs:108-110)
+pub fn xz_compress<R: io::BufRead, W: io::Write>(input: &mut R, output: &mut W) -> io::Result<()> {
+    encode(FMT_XZ, &LzbCompressOptions::default(), input, output)
+}
+
 /// `lzma_rs::decompress::raw` (feature `raw_decoder`, src/lib.rs:29-35) over the batch path.  The reference keeps a
 /// decoder's probability state between two `decompress` calls unless `reset` is called; the GPU path always starts
 /// from a fresh state, so a second `decompress` without `reset` is an error instead of a different decode.

@@ -1,8 +1,10 @@
 // Exercises the C++ mirror of the reference API (lzma_rs_b200/host/lzma_rs.hpp) end to end on a GPU box:
+//   host_check <rt-lzma|rt-lzma2|rt-xz> <plain file> <output file>     -> compress then decompress (tests/lzma.rs:16-28 style)
 //   host_check <lzma|lzma2|xz|rawlzma> <input file> <output file>   -> exit 0 and writes the decoded bytes, or prints the
 //   reference-format error string to stderr and exits 3 (partial output is still written).
 #include <fstream>
 #include <iostream>
+#include <sstream>
 #include <string>
 
 #include "lzma_rs_b200/host/lzma_rs.hpp"
@@ -13,6 +15,16 @@ int main(int argc, char** argv) {
     std::ifstream in(argv[2], std::ios::binary);
     std::ofstream out(argv[3], std::ios::binary);
     try {
+        if (fmt.rfind("rt-", 0) == 0) {  // round trip through the compress side
+            std::stringstream packed;
+            if (fmt == "rt-lzma") lzma_rs::lzma_compress(in, packed);
+            else if (fmt == "rt-lzma2") lzma_rs::lzma2_compress(in, packed);
+            else lzma_rs::xz_compress(in, packed);
+            if (fmt == "rt-lzma") lzma_rs::lzma_decompress(packed, out);
+            else if (fmt == "rt-lzma2") lzma_rs::lzma2_decompress(packed, out);
+            else lzma_rs::xz_decompress(packed, out);
+            return 0;
+        }
         if (fmt == "lzma") lzma_rs::lzma_decompress(in, out);
         else if (fmt == "lzma2") lzma_rs::lzma2_decompress(in, out);
         else if (fmt == "rawlzma") {  // decompress::raw: split the 13-byte .lzma header off, decode the headerless payload

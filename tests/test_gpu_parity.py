@@ -186,6 +186,12 @@ def test_cpp_host_mirror(ctx, golden, tmp_path):
             assert r.returncode == 3 and r.stderr == v["error"], (name, r.stderr)
         else:
             assert r.returncode == 0, (name, r.stderr)
+    plain = corpus.mixed_text(31337, 150_000)
+    for fmt in ("rt-lzma", "rt-lzma2", "rt-xz"):  # compress side of the C++ mirror: round trips
+        src, dst = tmp_path / "plain.bin", tmp_path / "rt.bin"
+        src.write_bytes(plain)
+        r = subprocess.run([str(exe), fmt, str(src), str(dst)], capture_output=True, text=True)
+        assert r.returncode == 0 and dst.read_bytes() == plain, (fmt, r.stderr)
 
 
 def test_host_api_pinned_output_mirror(ctx):
