@@ -292,6 +292,19 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
 // ------------------------------------------------------------------------------------------------
 // K1: decode one stream with one warp
 // ------------------------------------------------------------------------------------------------
+// The status and its message arguments are written behind opaque (volatile) moves: plain assignments of constants get
+// hoisted ABOVE the branch into the hot path by the compiler (speculation is free in its cost model, but K1 is bound by
+// instruction issue: 4 instructions per literal and per match were spent preparing errors that never happen, 1.8 % of
+// all executed instructions in profiles/r01_k1_final.txt).
+#if defined(__CUDACC__) && !defined(LZB_FAIL_PLAIN)
+#define FAIL(c, x, y)                                                                  \
+    do {                                                                               \
+        asm volatile("mov.u32 %0, %1;" : "=r"(err) : "r"((int32_t)(c)));               \
+        asm volatile("mov.u64 %0, %1;" : "=l"(ea0) : "l"((uint64_t)(x)));              \
+        asm volatile("mov.u64 %0, %1;" : "=l"(ea1) : "l"((uint64_t)(y)));              \
+        goto finish;                                                                   \
+    } while (0)
+#else
 #define FAIL(c, x, y)        \
     do {                     \
         err = (c);           \
@@ -299,6 +312,7 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
         ea1 = (uint64_t)(y); \
         goto finish;         \
     } while (0)
+#endif
 
 // Warp copy of n bytes src -> dst (arbitrary, independent alignments; regions do not overlap): a few head bytes
 // bring dst to a 4-byte boundary, the body stores aligned 32-bit words assembled from two aligned source words with
