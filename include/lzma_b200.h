@@ -169,7 +169,10 @@ int lzb_decode_batch_device(lzb_ctx *ctx, int fmt, const lzb_options *opt, const
 /* Two-phase variant of the device path for timing and overlap: prepare uploads the offsets and runs the
  * per-stream scan kernel (header parse / LZMA2 framing walk) once; launch enqueues ONLY the decode
  * kernel on `cuda_stream` (no sync); collect synchronises and fetches results.  A prepared batch can
- * be launched repeatedly.  d_in and d_out must be 16-byte aligned. */
+ * be launched repeatedly.  d_in and d_out must be 16-byte aligned.  Every batch owns its device workspaces: different
+ * batches of one context may be in flight on different streams at the same time; launches of the SAME batch must not
+ * overlap (they share its result and workspace buffers).  The host entry points (lzb_decode_batch, lzb_encode_batch,
+ * lzb_decompress_alloc) serialise on the context. */
 typedef struct lzb_batch lzb_batch;
 int lzb_batch_prepare(lzb_ctx *ctx, int fmt, const lzb_options *opt, const uint8_t *d_in, const uint64_t *in_off,
                       uint32_t n, uint8_t *d_out, const uint64_t *out_off, lzb_batch **batch);

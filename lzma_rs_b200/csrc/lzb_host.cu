@@ -234,7 +234,12 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
 int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem* d_items, const uint32_t* d_order,
                 const uint8_t* d_in_base, uint8_t* d_out_base, LzbResult* d_results, unsigned int* d_counter,
                 bool mirror = false, const unsigned long long* d_gate = nullptr,
-                std::function<int()>* before_first_kernel = nullptr) {
+                std::function<int()>* before_first_kernel = nullptr, DevBuf* own_matchws = nullptr,
+                DevBuf* own_litws = nullptr) {
+    // per-warp workspaces: the ctx's own for the host API (calls are serialised by ctx->mu), the batch's own for prepared
+    // device batches, which may be in flight on different streams at the same time
+    DevBuf& matchws = own_matchws ? *own_matchws : ctx->d_matchws;
+    DevBuf& litws = own_litws ? *own_litws : ctx->d_litws;
     CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned int), s));
     // everything small this launch needs has been enqueued: now the gated upload of the input blob may occupy the copy
     // engine.  It is enqueued BEFORE the kernel so that a launch that blocks the host (profilers, compute-sanitizer,
@@ -253,7 +258,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         const int smem = (int)(c.warps * c.warp_bytes);
         // per-warp global workspace for the matched-literal columns (L2-resident: 8 KiB per warp at lc+lp = 3)
         const uint64_t mstride = lzb_matched_u16(c.lclp);
-        CUDA_TRY(ctx, ctx->d_matchws.ensure((size_t)c.grid * c.warps * mstride * 2));
+        CUDA_TRY(ctx, matchws.ensure((size_t)c.grid * c.warps * mstride * 2));
         // variants: [sched][mirror][lean | fill | copy]; mirror = host API with a pinned output buffer (finished pages
         // streamed to the host); sched = the launch carries a placement plan (lzb_sched.h)
         typedef void (*kern_t)(const LzbItem*, const uint32_t*, uint32_t, uint32_t, const uint8_t*, uint8_t*, LzbResult*,
@@ -271,7 +276,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         }
         if (int rc = fire()) return rc;
         kernels[v]<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, p.n_static, d_in_base, d_out_base, d_results,
-                                                      d_counter, c.lclp, c.warp_bytes, ctx->d_matchws.as<uint16_t>(), mstride, kc,
+                                                      d_counter, c.lclp, c.warp_bytes, matchws.as<uint16_t>(), mstride, kc,
                                                       mirror ? d_gate : nullptr);
         CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -283,11 +288,11 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
                                                ctx->smem_optin));
             ctx->smem_configured_big = ctx->smem_optin;
         }
-        CUDA_TRY(ctx, ctx->d_litws.ensure((size_t)c.grid * c.warps * p.big_stride_u16 * 2));
+        CUDA_TRY(ctx, litws.ensure((size_t)c.grid * c.warps * p.big_stride_u16 * 2));
         if (int rc = fire()) return rc;
         lzb_decode_biglit_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order + ns, nb, 0u, d_in_base, d_out_base,
                                                                     d_results, d_counter + 1, c.lclp, c.warp_bytes,
-                                                                    ctx->d_litws.as<uint16_t>(), p.big_stride_u16, kc,
+                                                                    litws.as<uint16_t>(), p.big_stride_u16, kc,
                                                                     mirror ? d_gate : nullptr);
         CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -640,7 +645,7 @@ struct lzb_batch {
     int fmt = 0;
     const uint8_t* d_in = nullptr;
     uint8_t* d_out = nullptr;
-    DevBuf d_items, d_results, d_order, d_counter, d_scan, d_off;
+    DevBuf d_items, d_results, d_order, d_counter, d_scan, d_off, d_matchws, d_litws;
     std::vector<LzbItem> items;  // host copy (hdr_len, preset info)
     bool allow_incomplete = false;
     DecodePlan plan;
@@ -724,7 +729,8 @@ extern "C" int lzb_batch_launch(lzb_batch* b, void* cuda_stream) {
     if (!b) return LZB_RC_BAD_ARG;
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : b->ctx->stream;
     return launch_plan(b->ctx, s, b->plan, b->d_items.as<LzbItem>(), b->d_order.as<uint32_t>(), b->d_in, b->d_out,
-                       b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>());
+                       b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>(), false, nullptr, nullptr, &b->d_matchws,
+                       &b->d_litws);
 }
 
 extern "C" int lzb_batch_kernels_per_launch(const lzb_batch* b) {
@@ -752,7 +758,8 @@ extern "C" int lzb_batch_collect(lzb_batch* b, void* cuda_stream, uint64_t* out_
 extern "C" void lzb_batch_destroy(lzb_batch* b) {
     if (!b) return;
     if (b->ctx) cudaSetDevice(b->ctx->device);
-    DevBuf* bufs[] = {&b->d_items, &b->d_results, &b->d_order, &b->d_counter, &b->d_scan, &b->d_off};
+    DevBuf* bufs[] = {&b->d_items, &b->d_results, &b->d_order, &b->d_counter, &b->d_scan, &b->d_off, &b->d_matchws,
+                      &b->d_litws};
     for (DevBuf* x : bufs) x->release();
     delete b;
 }
@@ -844,13 +851,10 @@ static uint32_t host_crc32(const uint8_t* p, size_t n) {
     return ~c;
 }
 
-extern "C" int lzb_encode_batch_device(lzb_ctx* ctx, int fmt, const lzb_compress_options* opt, const uint8_t* d_in,
-                                       const uint64_t* in_off, uint32_t n, uint8_t* d_out, const uint64_t* out_off,
-                                       uint64_t* out_len, lzb_status* st, void* cuda_stream) {
-    if (!ctx || !in_off || !out_off || !out_len || !st || fmt < 0 || fmt > 2) return LZB_RC_BAD_ARG;
-    if (n == 0) return LZB_RC_OK;
-    if (!d_in || !d_out) return LZB_RC_BAD_ARG;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+// caller holds ctx->mu
+static int encode_device_locked(lzb_ctx* ctx, int fmt, const lzb_compress_options* opt, const uint8_t* d_in,
+                                const uint64_t* in_off, uint32_t n, uint8_t* d_out, const uint64_t* out_off,
+                                uint64_t* out_len, lzb_status* st, void* cuda_stream) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     std::vector<LzbEncItem> items(n);
@@ -914,6 +918,16 @@ extern "C" int lzb_encode_batch_device(lzb_ctx* ctx, int fmt, const lzb_compress
     return LZB_RC_OK;
 }
 
+extern "C" int lzb_encode_batch_device(lzb_ctx* ctx, int fmt, const lzb_compress_options* opt, const uint8_t* d_in,
+                                       const uint64_t* in_off, uint32_t n, uint8_t* d_out, const uint64_t* out_off,
+                                       uint64_t* out_len, lzb_status* st, void* cuda_stream) {
+    if (!ctx || !in_off || !out_off || !out_len || !st || fmt < 0 || fmt > 2) return LZB_RC_BAD_ARG;
+    if (n == 0) return LZB_RC_OK;
+    if (!d_in || !d_out) return LZB_RC_BAD_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return encode_device_locked(ctx, fmt, opt, d_in, in_off, n, d_out, out_off, out_len, st, cuda_stream);
+}
+
 extern "C" int lzb_encode_batch(lzb_ctx* ctx, int fmt, const lzb_compress_options* opt, const uint8_t* in,
                                 const uint64_t* in_off, uint32_t n, uint8_t* out, const uint64_t* out_off, uint64_t* out_len,
                                 lzb_status* st) {
@@ -921,20 +935,16 @@ extern "C" int lzb_encode_batch(lzb_ctx* ctx, int fmt, const lzb_compress_option
     if (n == 0) return LZB_RC_OK;
     if (!in || !out) return LZB_RC_BAD_ARG;
     const uint64_t in_lo = in_off[0], in_hi = in_off[n], out_lo = out_off[0], out_hi = out_off[n];
-    uint8_t *d_in0, *d_out0;
-    {
-        std::lock_guard<std::mutex> lock(ctx->mu);
-        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-        CUDA_TRY(ctx, ctx->d_in.ensure((in_hi - in_lo) + 64));
-        CUDA_TRY(ctx, ctx->d_out.ensure((out_hi - out_lo) + 64));
-        d_in0 = ctx->d_in.as<uint8_t>() + (in_lo & 15);
-        d_out0 = ctx->d_out.as<uint8_t>() + (out_lo & 15);
-        if (in_hi > in_lo)
-            CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    int rc = lzb_encode_batch_device(ctx, fmt, opt, d_in0 - in_lo, in_off, n, d_out0 - out_lo, out_off, out_len, st, nullptr);
+    std::lock_guard<std::mutex> lock(ctx->mu);  // the staging buffers belong to this call from upload to download
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, ctx->d_in.ensure((in_hi - in_lo) + 64));
+    CUDA_TRY(ctx, ctx->d_out.ensure((out_hi - out_lo) + 64));
+    uint8_t* d_in0 = ctx->d_in.as<uint8_t>() + (in_lo & 15);
+    uint8_t* d_out0 = ctx->d_out.as<uint8_t>() + (out_lo & 15);
+    if (in_hi > in_lo)
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = encode_device_locked(ctx, fmt, opt, d_in0 - in_lo, in_off, n, d_out0 - out_lo, out_off, out_len, st, nullptr);
     if (rc != LZB_RC_OK) return rc;
-    std::lock_guard<std::mutex> lock(ctx->mu);
     if (out_hi > out_lo)
         CUDA_TRY(ctx, cudaMemcpyAsync(out + out_lo, d_out0, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
