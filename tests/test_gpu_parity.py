@@ -499,3 +499,42 @@ def test_fuzz_regressions_on_gpu(ctx):
     for fmt, named in fuzz_regressions().items():
         bad = parity.check_group(_host(ctx), fmt, {}, named)
         assert not bad, "\n".join(bad)
+
+
+def test_concurrent_batches_on_two_streams(ctx):
+    """Two prepared device batches of one context in flight at the same time on different CUDA streams: every batch owns
+    its result and workspace buffers (include/lzma_b200.h), so neither disturbs the other."""
+    import ctypes as C
+    import torch
+    from lzma_rs_b200 import _native
+    lib = _native.load()
+    opt = _native.make_options()
+    sets = []
+    for k in range(2):
+        plains = [corpus.mixed_text(9100 + 50 * k + i, 60_000 + 7000 * i) for i in range(40)]
+        comp = [corpus.raw_lzma2(p, dict_size=1 << 20) for p in plains] * 8
+        plains = plains * 8
+        blob, in_off = _native.pack_streams(comp)
+        sizes = np.array([len(p) for p in plains], dtype=np.uint64)
+        out_off = np.zeros(len(plains) + 1, dtype=np.uint64)
+        np.cumsum((sizes + np.uint64(15)) // np.uint64(16) * np.uint64(16), out=out_off[1:])
+        d_in = torch.from_numpy(blob).cuda()
+        d_out = torch.zeros(int(out_off[-1]) + 16, dtype=torch.uint8, device="cuda")
+        batch = C.c_void_p()
+        assert lib.lzb_batch_prepare(ctx.handle, 1, C.byref(opt), d_in.data_ptr(), in_off.ctypes.data, len(plains),
+                                     d_out.data_ptr(), out_off.ctypes.data, C.byref(batch)) == 0
+        sets.append((plains, in_off, out_off, d_in, d_out, batch, torch.cuda.Stream()))
+    for _ in range(3):  # both batches are enqueued before either is waited for
+        for s in sets:
+            assert lib.lzb_batch_launch(s[5], C.c_void_p(s[6].cuda_stream)) == 0
+    for plains, in_off, out_off, d_in, d_out, batch, stream in sets:
+        n = len(plains)
+        ol, cs, st = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=_native.STATUS_DTYPE)
+        assert lib.lzb_batch_collect(batch, C.c_void_p(stream.cuda_stream), ol.ctypes.data, cs.ctypes.data, st.ctypes.data) == 0
+        assert (st["code"] == 0).all()
+        host = d_out.cpu().numpy()
+        for i in range(n):
+            o = int(out_off[i])
+            assert host[o:o + int(ol[i])].tobytes() == plains[i], i
+    for s in sets:
+        lib.lzb_batch_destroy(s[5])
