@@ -296,13 +296,21 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
 // hoisted ABOVE the branch into the hot path by the compiler (speculation is free in its cost model, but K1 is bound by
 // instruction issue: 4 instructions per literal and per match were spent preparing errors that never happen, 1.8 % of
 // all executed instructions in profiles/r01_k1_final.txt).
+// Only in the instantiations without the host mirror: with it the same change measured 0.4 % slower (code layout), so
+// those keep the plain form (FAIL is only used inside decode_item, where MIRROR is a template parameter).
 #if defined(__CUDACC__) && !defined(LZB_FAIL_PLAIN)
-#define FAIL(c, x, y)                                                                  \
-    do {                                                                               \
-        asm volatile("mov.u32 %0, %1;" : "=r"(err) : "r"((int32_t)(c)));               \
-        asm volatile("mov.u64 %0, %1;" : "=l"(ea0) : "l"((uint64_t)(x)));              \
-        asm volatile("mov.u64 %0, %1;" : "=l"(ea1) : "l"((uint64_t)(y)));              \
-        goto finish;                                                                   \
+#define FAIL(c, x, y)                                                                      \
+    do {                                                                                   \
+        if (MIRROR) {                                                                      \
+            err = (c);                                                                     \
+            ea0 = (uint64_t)(x);                                                           \
+            ea1 = (uint64_t)(y);                                                           \
+        } else {                                                                           \
+            asm volatile("mov.u32 %0, %1;" : "=r"(err) : "r"((int32_t)(c)));               \
+            asm volatile("mov.u64 %0, %1;" : "=l"(ea0) : "l"((uint64_t)(x)));              \
+            asm volatile("mov.u64 %0, %1;" : "=l"(ea1) : "l"((uint64_t)(y)));              \
+        }                                                                                  \
+        goto finish;                                                                       \
     } while (0)
 #else
 #define FAIL(c, x, y)        \
