@@ -538,3 +538,13 @@ def test_concurrent_batches_on_two_streams(ctx):
             assert host[o:o + int(ol[i])].tobytes() == plains[i], i
     for s in sets:
         lib.lzb_batch_destroy(s[5])
+
+
+def test_reference_suite_on_gpu(ctx, golden):
+    """tests/lzma.rs, tests/lzma2.rs, tests/xz.rs of the reference, restated over the public Python mirror, on the device."""
+    import lzma_rs_b200 as L
+    from test_reference_suite import run_reference_suite
+    v = next(x for x in golden.vectors() if x["name"] == "foo.txt.lzma")
+    foo = L.lzma_decompress(golden.compressed(v))
+    assert hashlib.sha256(foo).hexdigest() == v["plain_sha256"]
+    run_reference_suite(L, foo)
