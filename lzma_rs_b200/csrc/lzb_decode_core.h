@@ -271,10 +271,7 @@ LZB_DEV uint32_t rev_bits(uint32_t v, uint32_t nb) {  // the low nb bits of v, r
 // One rolled loop of 16-byte stores: this runs once per stream / state reset, and K1's code must stay inside the
 // 32 KB instruction cache (an unrolled fill at four call sites cost 178 instructions).
 LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
-#if defined(__CUDACC__) && defined(LZB_FILL_OLD)
-    uint32_t* T32 = reinterpret_cast<uint32_t*>(T);
-    for (uint32_t i = lane; i < n_u16 / 2; i += LZB_LANES) T32[i] = 0x04000400u;
-#elif defined(__CUDACC__)
+#ifdef __CUDACC__
     uint4* T4 = reinterpret_cast<uint4*>(T);
     const uint4 v = make_uint4(0x04000400u, 0x04000400u, 0x04000400u, 0x04000400u);
 #ifndef LZB_FILL_UNROLL
