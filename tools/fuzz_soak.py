@@ -284,9 +284,16 @@ def main():
                     case_seeds[fmt].append(stream)
     for rd in range(a.rounds if a.lzma_structured else 0):
         gen = [lzma_structured(rnd, corpus) for _ in range(a.per_format)]
-        for fmt in (0, 1):
+        # .lzma streams also run under the other decompress::Options (options.rs:24-43): sizes provided from outside,
+        # small memory limits -- the same streams, the same options on both sides
+        opt_sets = [{}, {"unpacked_mode": 1, "provided": rnd.choice([0, 1, 7, 300])}, {"unpacked_mode": 1},
+                    {"memlimit": rnd.choice([0, 1, 100, 4096, 70_000])}, {"unpacked_mode": 2, "provided": rnd.choice([0, 5, 1000])},
+                    {"unpacked_mode": 2}]
+        for fmt, opts in [(0, o) for o in ([{}] + rnd.sample(opt_sets[1:], 2))] + [(1, {})]:
             named = [(f"r{rd}-f{fmt}-{i}", st) for i, (f, st) in enumerate(gen) if f == fmt]
-            bad = parity.check_group(decode, fmt, {}, named)
+            bad = parity.check_group(decode, fmt, opts, named)
+            if bad:
+                print(f"   options: {opts}", flush=True)
             total += len(named)
             if bad:
                 bad_total += len(bad)
