@@ -52,3 +52,25 @@ def test_fuzz_regressions():
     for fmt, named in regs.items():
         bad = parity.check_group(_decode, fmt, {}, named)
         assert not bad, "\n".join(bad)
+
+
+def structured_fuzz(decode, seed, n):
+    """A fixed-seed slice of tools/fuzz_soak.py's structure-aware generators: .xz files assembled field by field with
+    valid CRCs around odd values, and .lzma / LZMA2 streams built symbol by symbol with a real range encoder."""
+    import os
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import corpus
+    import fuzz_soak
+    rnd = random.Random(seed)
+    bad = parity.check_group(decode, 2, {}, [(f"xz-{i}", fuzz_soak.xz_structured(rnd, corpus)) for i in range(n)])
+    gen = [fuzz_soak.lzma_structured(rnd, corpus) for _ in range(2 * n)]
+    for fmt, opts in ((0, {}), (0, {"unpacked_mode": 1, "provided": 7}), (0, {"memlimit": 100}), (1, {})):
+        bad += parity.check_group(decode, fmt, opts, [(f"l{fmt}-{i}", s) for i, (f, s) in enumerate(gen) if f == fmt])
+    return bad
+
+
+def test_structured_fuzz():
+    bad = structured_fuzz(_decode, 20261017, 500)
+    assert not bad, f"{len(bad)} mismatches:\n" + "\n".join(bad[:20])

@@ -548,3 +548,10 @@ def test_reference_suite_on_gpu(ctx, golden):
     foo = L.lzma_decompress(golden.compressed(v))
     assert hashlib.sha256(foo).hexdigest() == v["plain_sha256"]
     run_reference_suite(L, foo)
+
+
+def test_structured_fuzz_on_gpu(ctx):
+    """Structure-aware differential fuzz (tools/fuzz_soak.py generators, fixed seed) through the CUDA path."""
+    from test_emul_parity import structured_fuzz
+    bad = structured_fuzz(_host(ctx), 20261018, 1500)
+    assert not bad, f"{len(bad)} mismatches:\n" + "\n".join(bad[:20])
