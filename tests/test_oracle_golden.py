@@ -82,3 +82,43 @@ def test_memlimit_error(golden):
     v = next(x for x in golden.vectors() if x["name"] == "inline-hello.lzma")
     r = oracle.lzma_decompress(golden.compressed(v), memlimit=0)
     assert not r.ok and "exceeded memory limit of 0" in r.display and r.out == b""
+
+
+def test_oracle_accepts_what_liblzma_accepts():
+    """The reference's own differential oracle is liblzma (tests/lzma.rs:109-114, fuzz/fuzz_targets/compare_xz.rs).  lzma-rs
+    is the more lenient of the two except for features it lacks, so over mutated and field-fuzzed streams: whatever
+    liblzma decodes, the oracle decodes to the same bytes -- apart from check ids other than None/CRC32/CRC64/SHA-256,
+    which the reference rejects (src/xz/mod.rs:65-75) and liblzma skips."""
+    import lzma
+    import os
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import corpus
+    import fuzz_soak
+    import oracle_py as oracle
+
+    def lib(fmt, b):
+        try:
+            d = lzma.LZMADecompressor(format=lzma.FORMAT_XZ if fmt == 2 else lzma.FORMAT_ALONE)
+            out = d.decompress(b)
+            return out if d.eof and not d.unused_data else None
+        except Exception:
+            return None
+
+    rnd = random.Random(4)
+    accepted = 0
+    for _ in range(4):
+        seeds = fuzz_soak.seeds_for(rnd, corpus)
+        items = [(2, fuzz_soak.xz_structured(rnd, corpus)) for _ in range(150)]
+        items += [(f, fuzz_soak.mutate(rnd, seeds[f][i % len(seeds[f])])) for f in (0, 2) for i in range(150)]
+        for fmt, b in items:
+            ref = lib(fmt, b)
+            if ref is None:
+                continue
+            r = oracle.xz_decompress(b) if fmt == 2 else oracle.lzma_decompress(b)
+            if not r.ok and "Invalid check method" in r.display:
+                continue
+            accepted += 1
+            assert r.ok and r.out == ref, (fmt, r.display, b[:24].hex())
+    assert accepted > 50
