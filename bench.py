@@ -426,8 +426,16 @@ def main():
         kernel_ms = float(np.mean(step_ms))  # this rank's average launch duration, CUDA events on the launch stream
         achieved = (in_bytes + out_bytes) / (kernel_ms * 1e-3) / 1e9
         ncap, quota = effective_cpus()
-        cpu_gbs, cpu_dt, cpu_k, cpu_total, cpu_used = cpu_reference_run(comp, plain, 2, 1, cpu_thread_candidates(ncap, quota),
-                                                                        a.cpu_sample)
+        if world == 1:
+            cpu_gbs, cpu_dt, cpu_k, cpu_total, cpu_used = cpu_reference_run(comp, plain, 2, 1,
+                                                                            cpu_thread_candidates(ncap, quota), a.cpu_sample)
+            cpu_obj = {"value": cpu_gbs, "unit": "GB/s", "cores": effective_cores(cpu_used, ncap, quota), "kind": "port",
+                       "sample": f"{cpu_k} of {n} streams ({cpu_total} B out), one stream per task, best of thread "
+                                 f"counts {cpu_thread_candidates(ncap, quota)} -> {cpu_used} pthreads (os.cpu_count "
+                                 f"{ncpu}, cgroup quota {quota}); C restatement of lzma-rs src/decode (oracle/)"}
+        else:  # the CPU baseline is a property of the box, measured at N=1 only: here the other ranks share its cores
+            cpu_obj = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port",
+                       "sample": "not timed at N > 1 (rank 0 at N = 1 only): see the N = 1 line of the same box"}
         traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu capture
         tpath = os.path.join(ROOT, "profiles", "r01_k1_traffic.json")
         if os.path.exists(tpath):
@@ -450,12 +458,10 @@ def main():
             "gpu_launches": kernels_per_step * a.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
-                         "kernel": "lzb_decode_wide_kernel" if CFG["kind"] in ("rep0", "stored") else "lzb_decode_kernel", "peak_source": peak_src,
+                         "kernel": {"rep0": "lzb_decode_fill_kernel", "stored": "lzb_stored_decode_kernel"}.get(CFG["kind"], "lzb_decode_kernel"),
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": in_bytes + out_bytes, "kernel_ms": kernel_ms},
-            "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": effective_cores(cpu_used, ncap, quota), "kind": "port",
-                             "sample": f"{cpu_k} of {n} streams ({cpu_total} B out), one stream per task, best of thread "
-                                       f"counts {cpu_thread_candidates(ncap, quota)} -> {cpu_used} pthreads (os.cpu_count "
-                                       f"{ncpu}, cgroup quota {quota}); C restatement of lzma-rs src/decode (oracle/)"},
+            "cpu_baseline": cpu_obj,
             "clocks": clocks,
         }
         print(json.dumps(line))
