@@ -449,8 +449,10 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "streams_per_gpu": n, "distinct_streams": min(distinct, n),
                        "compressed_bytes_per_gpu": in_bytes, "decompressed_bytes_per_gpu": out_bytes,
-                       "l2": f"inputs+outputs {(in_bytes + out_bytes) >> 20} MiB per step > {L2_BYTES // 1000000} MB L2 "
-                             "(no flush needed)",
+                       "l2": (f"inputs+outputs {(in_bytes + out_bytes) >> 20} MiB per step > {L2_BYTES // 1000000} MB L2 "
+                              "(no flush needed)") if in_bytes + out_bytes > L2_BYTES else
+                             (f"inputs+outputs {(in_bytes + out_bytes) >> 20} MiB per step FIT the {L2_BYTES // 1000000} MB L2 and "
+                              "are not flushed: reduced --streams run, not a benchmark configuration"),
                        "parallelism": f"{world} x independent shard (no collective)", "verified": verified},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": in_bytes * world,
                     "d2h_bytes_per_step": out_bytes * world, "ms_per_step": e2e_ms_max,
