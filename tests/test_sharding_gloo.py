@@ -103,3 +103,58 @@ def test_scatter_decode_gather_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+def _worker_small(rank, world, port, q):
+    """Tensor form with more ranks than the data needs: some ranks get no stream at all, or only empty ones."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import corpus
+    import oracle_py
+    from lzma_rs_b200 import _native, sharding
+
+    def decode_t(blob_t, in_off, out_off, out_t):
+        m = len(in_off) - 1
+        out_len, codes = np.zeros(m, dtype=np.uint64), np.zeros(m, dtype=np.int32)
+        b, o = blob_t.numpy(), out_t.numpy()
+        for i in range(m):
+            r = oracle_py.lzma2_decompress(b[int(in_off[i]):int(in_off[i + 1])].tobytes())
+            codes[i], out_len[i] = r.kind, len(r.out)
+            o[int(out_off[i]):int(out_off[i]) + len(r.out)] = np.frombuffer(r.out, dtype=np.uint8)
+        return out_len, codes
+
+    ok = True
+    for sizes in ([50_000, 10, 0], [0, 0], [7], []):
+        if rank == 0:
+            plains = [corpus.mixed_text(40 + i, s) for i, s in enumerate(sizes)]
+            streams = [corpus.raw_lzma2(p) for p in plains]
+            blob, in_off = _native.pack_streams(streams)
+            res = sharding.decode_sharded_tensors(decode_t, torch.from_numpy(blob), in_off, [len(p) for p in plains], src=0)
+            out_t, out_off, out_len, codes = res
+            o = out_t.numpy()
+            ok = ok and len(out_len) == len(plains) and bool((codes == 0).all()) and all(
+                o[int(out_off[i]):int(out_off[i]) + int(out_len[i])].tobytes() == plains[i] for i in range(len(plains)))
+        else:
+            sharding.decode_sharded_tensors(decode_t, None, None, None, src=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, ok))
+
+
+def test_tensor_sharding_with_idle_ranks_world3():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_small, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
