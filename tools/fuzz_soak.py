@@ -3,7 +3,9 @@
 compare_xz.rs:28-37: both fail the same way or both decode the same bytes), against the oracle.
 
     python tools/fuzz_soak.py --backend emul --rounds 50 --seed 1      K1's source compiled for the CPU (no GPU needed)
-    python tools/fuzz_soak.py --backend gpu  --rounds 50 --seed 1      the CUDA path through the C ABI
+    python tools/fuzz_soak.py --backend gpu  --rounds 50 --seed 1      the CUDA path through the C ABI (host entry point)
+    python tools/fuzz_soak.py --backend gpu-device ...                 the device-resident entry point (not yet run: added
+                                                                       after round 1's GPU budget was spent)
 
 Each round mutates a fresh set of seed streams (all three formats, several lc/lp/pb, stored chunks, multi-chunk
 LZMA2, multi-block / chained .xz) 400 times per format and compares display string, output bytes and consumed count."""
@@ -251,7 +253,7 @@ def mutate(rnd, b):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--backend", choices=["emul", "gpu"], default="emul")
+    ap.add_argument("--backend", choices=["emul", "gpu", "gpu-device"], default="emul")
     ap.add_argument("--rounds", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--per-format", type=int, default=400)
@@ -264,7 +266,27 @@ def main():
     a = ap.parse_args()
     import corpus
     import parity
-    if a.backend == "gpu":
+    if a.backend == "gpu-device":
+        # the device-resident entry point (K2 scan on the device, capacities fixed by the caller, no retry): .lzma and raw
+        # LZMA2 only; a stream that reports LZB_E_CAPACITY is decoded again through the host path, which retries
+        import gpu_util
+        from lzma_rs_b200 import Context
+        ctx = Context()
+
+        def decode(fmt, streams, opts):
+            if fmt == 2:
+                return gpu_util.host_decode(ctx, fmt, streams, opts)
+            caps = ctx.scan(fmt, *__import__("lzma_rs_b200")._native.pack_streams(streams), gpu_util.options_from(opts))
+            b = gpu_util.DeviceBatch(ctx, fmt, streams, caps, opts).decode()
+            res = []
+            for i, s in enumerate(streams):
+                if int(b.st[i]["code"]) == -1:
+                    res.append(gpu_util.host_decode(ctx, fmt, [s], opts)[0])
+                else:
+                    res.append(test_emul_parity.emul_py.Result(b.output(i), int(b.consumed[i]), b.st[i].copy(), b.display(i)))
+            return res
+        import test_emul_parity
+    elif a.backend == "gpu":
         import gpu_util
         from lzma_rs_b200 import Context
         ctx = Context()
