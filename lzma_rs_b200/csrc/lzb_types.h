@@ -79,7 +79,8 @@ enum {
 // Multipliers / addends the bit loop reads from the kernel's constant bank.  Passing them as launch parameters keeps
 // nvcc/ptxas from strength-reducing `x * 2 + y` into ALU-pipe shifts and selects: as IMADs with a constant-bank
 // operand they run on the (otherwise idle) FMA pipe, which halves the ALU-pipe pressure that bounds K1.
-// Warps (= resident streams) per CTA, one CTA per SM: bounded by registers (65 536 / (32 * 24) = 85 per thread).
+// Warps (= resident streams) per CTA, one CTA per SM: bounded by shared memory (28 x 7 808 B of tables) and by
+// registers (65 536 / (32 * 28) = 73 -> 72 per thread; K1 uses 70).
 #ifndef LZB_MAX_WARPS
 #define LZB_MAX_WARPS 28
 #endif
@@ -91,6 +92,6 @@ struct LzbKC {
 
 // Shared-memory u16 per warp: small tables + plain literal columns.  Matched-literal columns (only touched by
 // the first literal after a match, until its first mismatching bit) go to global memory (L1/L2): that halves
-// the shared-memory footprint and raises residency from 14 to 24 streams per SM at lc+lp = 3.
+// the shared-memory footprint and raises residency from 14 to 28 streams per SM at lc+lp = 3.
 static inline uint32_t lzb_table_u16(uint32_t lclp) { return (uint32_t)T_LIT + (0x100u << lclp); }
 static inline uint32_t lzb_matched_u16(uint32_t lclp) { return 0x200u << lclp; }
