@@ -51,8 +51,12 @@ typedef struct lzb_options {
     uint8_t has_provided;  /* the variant's Option<u64> is Some */
     uint8_t has_memlimit;  /* memlimit: Option<usize> is Some */
     uint8_t allow_incomplete; /* Options::allow_incomplete (the stream API's flag, stream.rs:136-147): a .lzma stream whose
-                               * input ends in the middle of a symbol is not an error; every byte decoded from complete
-                               * symbols is returned (status LZB_OK) */
+                               * input ends in the middle of a symbol, or whose decoded length disagrees with its declared
+                               * size, is not an error; every byte decoded from complete symbols is returned (LZB_OK).
+                               * For unknown-size streams that is a few symbols MORE than the reference's incremental
+                               * decoder returns (it stops as soon as its input is exhausted, lzma.rs:450-452; the batch
+                               * decoder also takes the symbols behind that point that need no further byte); the
+                               * Stream facades of the host layers trim the difference. */
     uint8_t reserved[4];
     uint64_t provided;
     uint64_t memlimit;

@@ -262,13 +262,51 @@ class Stream:
         hdr = 5 if self._opt.unpacked_size.mode == decompress.UnpackedSizeMode.UseProvided else 13
         if len(self._buf) < hdr + 5:  # header + the 5 range-coder start bytes were never complete (stream.rs:123-129)
             raise error.LzmaError("lzma error: failed to read header")
-        r = (self._ctx or _ctx()).decompress_one(_native.FMT_LZMA, bytes(self._buf), self._opt)
-        if r.data:
-            self._out.write(r.data)
-        r.raise_for_status()
+        ctx, buf = (self._ctx or _ctx()), bytes(self._buf)
+        if self._opt.allow_incomplete and len(buf) == hdr + 5:
+            return self._out  # header and start bytes only: the reference has not decoded anything yet (stream.rs:296-305)
+        strict = decompress.Options(self._opt.unpacked_size, self._opt.memlimit, False)
+        r = ctx.decompress_one(_native.FMT_LZMA, buf, strict)
+        data = r.data
+        if self._opt.allow_incomplete and (r.ok or int(r.status["code"]) in (_native.E_IO_EOF, _native.E_UNPACKED_MISMATCH)):
+            data = self._incomplete_output(ctx, buf)
+            r = None
+        if data:
+            self._out.write(data)
+        if r is not None:
+            r.raise_for_status()
         if hasattr(self._out, "flush"):
             self._out.flush()
         return self._out
+
+    def _incomplete_output(self, ctx, buf):
+        """Options::allow_incomplete: what the reference's incremental decoder has produced when finish() skips the final
+        pass (stream.rs:136-147) -- for input that ends inside a symbol, and also for complete unknown-size streams.  It stops at the first symbol boundary at which its input is exhausted (lzma.rs:450-452), or in
+        front of the symbol it cannot complete; the batch decoder (C ABI flag `allow_incomplete`) also decodes the
+        symbols behind that boundary that happen to need no further input byte.  Those are trimmed here with two more
+        decodes: without the last byte the decoder stops in front of the symbol that consumes it; a decode with the
+        size fixed just behind that point then ends exactly behind that symbol."""
+        lenient = decompress.Options(self._opt.unpacked_size, self._opt.memlimit, True)
+        full = ctx.decompress_one(_native.FMT_LZMA, buf, lenient)  # every byte of every complete symbol
+        us = self._opt.unpacked_size
+        known = (us.value is not None) if us.mode != decompress.UnpackedSizeMode.ReadFromHeader else \
+            buf[5:13] != b"\xff" * 8
+        if known:  # with a known size the reference has no "input exhausted" stop (lzma.rs:442-445 comes first)
+            return full.data
+        short = ctx.decompress_one(_native.FMT_LZMA, buf[:-1], lenient)
+        before = len(short.data) if short.ok else 0  # output in front of the symbol that consumes the last byte
+        if before >= len(full.data):
+            return full.data  # that symbol is the unfinished one
+        use_provided = self._opt.unpacked_size.mode == decompress.UnpackedSizeMode.UseProvided
+        sized = decompress.Options(decompress.UnpackedSize(2 if use_provided else 1, before + 1), self._opt.memlimit, False)
+        r = ctx.decompress_one(_native.FMT_LZMA, buf, sized)
+        if r.ok:
+            end = before + 1
+        elif int(r.status["code"]) == _native.E_UNPACKED_MISMATCH:
+            end = int(r.status["a1"])  # the symbol overshot the size: a1 = the length it reached
+        else:
+            end = before
+        return full.data[:min(end, len(full.data))]
 
 
 decompress.Stream = Stream

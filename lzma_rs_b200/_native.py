@@ -15,6 +15,7 @@ FMT_LZMA, FMT_LZMA2, FMT_XZ = 0, 1, 2
 RC_OK, RC_BAD_ARG, RC_NO_DEVICE, RC_CUDA, RC_OOM = 0, -1, -2, -3, -4
 KIND_OK, KIND_IO, KIND_HEADER_TOO_SHORT, KIND_LZMA, KIND_XZ, KIND_INTERNAL = range(6)
 E_CAPACITY, E_UNSUPPORTED = -1, -2
+E_IO_EOF, E_UNPACKED_MISMATCH = 1, 6  # LZB_E_IO_EOF, LZB_E_UNPACKED_MISMATCH
 
 
 class Options(C.Structure):  # lzb_options

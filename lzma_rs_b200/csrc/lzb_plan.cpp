@@ -664,8 +664,11 @@ int decode_xz_batch(Executor& ex, const uint8_t* in, const uint64_t* in_off, uin
 // .lzma stream without an error, and everything decoded from complete symbols counts as output.  K1 reports the end
 // of input at the symbol boundary, before any side effect of the unfinished symbol, which is exactly what the
 // reference's dry run (lzma.rs:408-419, 470-483) leaves in the window.
+// The stream API never runs the final size check either when the flag is set (it belongs to ProcessingMode::Finish,
+// lzma.rs:513-521, which finish() skips): a stream that ends short of, or overshoots, its declared size also counts.
 bool lenient_eof(int fmt, const lzb_options* opt, const LzbResult* r) {
-    return fmt == LZB_FMT_LZMA && opt && opt->allow_incomplete && r->code == LZB_E_IO_EOF;
+    return fmt == LZB_FMT_LZMA && opt && opt->allow_incomplete &&
+           (r->code == LZB_E_IO_EOF || r->code == LZB_E_UNPACKED_MISMATCH);
 }
 
 // lzma_decompress[_with_options] / lzma2_decompress over a batch (lib.rs:44-60, 83-88): one work item per stream.

@@ -531,8 +531,16 @@ static int ds_decode_distance(decstate *s, rangedec *rc, size_t length, size_t *
 
 enum { ST_CONTINUE = 0, ST_FINISHED = 1 };
 
-/* process_next_inner with update = true, lzma.rs:278-393 */
+/* process_next_inner, lzma.rs:278-393.  update = 0 is the stream API's dry run (try_process_next, lzma.rs:408-419): the
+ * decisions are computed but neither the window nor the state may change.  Within one symbol every probability is
+ * used at most once, so the decisions do not depend on the updates; the caller runs the dry run on a COPY of the
+ * DecoderState, and here update = 0 only has to skip what touches the window (append_literal / append_lz and the
+ * errors they can raise, which the reference's dry run cannot see either). */
+static int ds_process_next_ex(decstate *s, lzbuf *out, rangedec *rc, int *status, int update, lzo_error *e);
 static int ds_process_next(decstate *s, lzbuf *out, rangedec *rc, int *status, lzo_error *e) {
+    return ds_process_next_ex(s, out, rc, status, 1, e);
+}
+static int ds_process_next_ex(decstate *s, lzbuf *out, rangedec *rc, int *status, int update, lzo_error *e) {
     size_t pos_state = out->len & (((size_t)1 << s->pb) - 1);
     uint32_t bit;
     size_t len;
@@ -542,6 +550,7 @@ static int ds_process_next(decstate *s, lzbuf *out, rangedec *rc, int *status, l
     if (!bit) { /* literal, 287-307 */
         uint8_t byte = 0;
         TRY(ds_decode_literal(s, out, rc, &byte, e));
+        if (!update) return 0;
         TRY(lzb_append_literal(out, byte, e));
         s->state = s->state < 4 ? 0 : (s->state < 10 ? s->state - 3 : s->state - 6);
         return 0;
@@ -554,7 +563,7 @@ static int ds_process_next(decstate *s, lzbuf *out, rangedec *rc, int *status, l
             if (rc_decode_bit(rc, &s->is_rep_0long[(s->state << 4) + pos_state], &bit)) return IOFAIL(e);
             if (!bit) { /* short rep, 321-327 */
                 s->state = s->state < 7 ? 9 : 11;
-                return lzb_append_lz(out, 1, s->rep[0] + 1, e);
+                return update ? lzb_append_lz(out, 1, s->rep[0] + 1, e) : 0;
             }
         } else {
             size_t idx, d, i;
@@ -589,7 +598,7 @@ static int ds_process_next(decstate *s, lzbuf *out, rangedec *rc, int *status, l
         }
     }
     len += 2;
-    return lzb_append_lz(out, len, s->rep[0] + 1, e);
+    return update ? lzb_append_lz(out, len, s->rep[0] + 1, e) : 0;
 }
 
 /* process -> process_mode(Finish), lzma.rs:255-261, 435-455, 496-523 */
@@ -671,6 +680,258 @@ static int lzma_decompress_impl(reader *r, const lzo_options *opt, bytes *sink, 
     }
     lzb_drop(&out);
     ds_drop(&st);
+    return rcode;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * decompress::Stream (feature `stream`): src/decode/stream.rs:66-346 over process_mode(Partial),
+ * lzma.rs:421-524.  Used to check the buffering facade of the product (lzma_rs_b200.Stream).
+ * ---------------------------------------------------------------------------------------- */
+#define MAX_REQUIRED_INPUT 20 /* lzma.rs:13 */
+#define MAX_TMP_LEN 18        /* stream.rs:11-24: 13 header bytes + 5 range-coder start bytes */
+
+struct lzo_stream {
+    lzo_options opt;
+    int allow_incomplete;
+    int state; /* 0 Header, 1 Data, 2 gone (a write failed: stream.rs:310) */
+    uint8_t tmp[MAX_TMP_LEN];
+    size_t tmp_len;
+    bytes sink;
+    decstate st;
+    lzbuf out;
+    uint32_t range, code;
+    uint8_t partial[MAX_REQUIRED_INPUT]; /* DecoderState::partial_input_buf, lzma.rs:183-184 */
+    size_t partial_len;
+};
+
+/* try_process_next, lzma.rs:408-419: a dry run of one symbol over `buf`; returns nonzero if it fails in any way */
+static int ds_try_process_next(decstate *s, lzbuf *out, const uint8_t *buf, size_t n, uint32_t range, uint32_t code) {
+    decstate copy = *s;
+    reader r = {buf, 0, n};
+    rangedec rc;
+    lzo_error e;
+    int status, rcode;
+    size_t bytes_lit = s->literal_rows * 0x300 * sizeof(uint16_t);
+    copy.literal_probs = (uint16_t *)malloc(bytes_lit);
+    if (!copy.literal_probs) abort();
+    memcpy(copy.literal_probs, s->literal_probs, bytes_lit);
+    rc.in = view_all(&r);
+    rc.range = range;
+    rc.code = code;
+    rcode = ds_process_next_ex(&copy, out, &rc, &status, 0, &e);
+    free(copy.literal_probs);
+    return rcode;
+}
+
+/* read_partial_input_buf, lzma.rs:421-433: fill the 20-byte buffer from the stream */
+static void ds_read_partial(lzo_stream *z, rangedec *rc) {
+    size_t avail = rc->in.lim - rc->in.r->pos, room = MAX_REQUIRED_INPUT - z->partial_len;
+    size_t k = avail < room ? avail : room;
+    memcpy(z->partial + z->partial_len, rc->in.r->p + rc->in.r->pos, k);
+    rc->in.r->pos += k;
+    z->partial_len += k;
+}
+
+/* process_mode, lzma.rs:435-524, both modes (partial = 1: ProcessingMode::Partial) */
+static int ds_process_mode(lzo_stream *z, rangedec *rc, int partial, lzo_error *e) {
+    decstate *s = &z->st;
+    lzbuf *out = &z->out;
+    for (;;) {
+        int status;
+        if (s->has_unpacked) {
+            if ((uint64_t)out->len >= s->unpacked_size) break;
+        } else if ((partial ? v_eof(&rc->in) : rc_is_finished_ok(rc)) && z->partial_len == 0) {
+            break;
+        }
+        if (z->partial_len > 0) {
+            uint8_t tmp[MAX_REQUIRED_INPUT];
+            reader tr;
+            rangedec trc;
+            size_t used;
+            ds_read_partial(z, rc);
+            memcpy(tmp, z->partial, sizeof tmp);
+            if (partial && z->partial_len < MAX_REQUIRED_INPUT &&
+                ds_try_process_next(s, out, tmp, z->partial_len, rc->range, rc->code))
+                return 0; /* need more data */
+            tr.p = tmp;
+            tr.pos = 0;
+            tr.end = z->partial_len;
+            trc.in = view_all(&tr);
+            trc.range = rc->range;
+            trc.code = rc->code;
+            TRY(ds_process_next(s, out, &trc, &status, e));
+            rc->range = trc.range;
+            rc->code = trc.code;
+            used = tr.pos;
+            memmove(z->partial, tmp + used, z->partial_len - used);
+            z->partial_len -= used;
+            if (status == ST_FINISHED) break;
+        } else {
+            const uint8_t *buf = rc->in.r->p + rc->in.r->pos; /* fill_buf(): the rest of this write's bytes */
+            size_t n = rc->in.lim - rc->in.r->pos;
+            if (partial && n < MAX_REQUIRED_INPUT && ds_try_process_next(s, out, buf, n, rc->range, rc->code)) {
+                ds_read_partial(z, rc);
+                return 0;
+            }
+            TRY(ds_process_next(s, out, rc, &status, e));
+            if (status == ST_FINISHED) break;
+        }
+    }
+    if (s->has_unpacked && !partial && s->unpacked_size != (uint64_t)out->len)
+        return fail(e, LZO_ERR_LZMA, "Expected unpacked size of %llu but decompressed to %zu",
+                    (unsigned long long)s->unpacked_size, out->len);
+    return 0;
+}
+
+lzo_stream *lzo_stream_new(const lzo_options *opt, int allow_incomplete) {
+    static const lzo_options defaults = {0, 0, 0, 0, 0};
+    lzo_stream *z = (lzo_stream *)calloc(1, sizeof *z);
+    if (!z) abort();
+    z->opt = opt ? *opt : defaults;
+    z->allow_incomplete = allow_incomplete;
+    return z;
+}
+
+/* Stream::read_header, stream.rs:157-190.  Returns 0 and *to_data = 1 (Data) / 0 (stay in Header: need more bytes),
+ * or the fatal error kind.  Consumes from `in` exactly what the reference's reads consume. */
+static int stream_read_header(lzo_stream *z, view *in, int *to_data, lzo_error *e) {
+    uint8_t props;
+    uint32_t pb, lc, lp, dict_size;
+    int has_unpacked = 0;
+    uint64_t unpacked = 0, v;
+    rangedec rc;
+    *to_data = 0;
+    /* LzmaParams::read_header, lzma.rs:96-161: HeaderTooShort means "try again later" here */
+    if (v_u8(in, &props)) return 0;
+    pb = props;
+    if (pb >= 225) return fail(e, LZO_ERR_LZMA, "LZMA header invalid properties: %u must be < 225", pb);
+    lc = pb % 9;
+    pb /= 9;
+    lp = pb % 5;
+    pb /= 5;
+    if (v_u32le(in, &dict_size)) return 0;
+    if (dict_size < 0x1000) dict_size = 0x1000;
+    switch (z->opt.unpacked_mode) {
+    case 0:
+        if (v_u64le(in, &v)) return 0;
+        if (v != 0xFFFFFFFFFFFFFFFFull) has_unpacked = 1, unpacked = v;
+        break;
+    case 1:
+        if (v_u64le(in, &v)) return 0;
+        has_unpacked = z->opt.has_provided;
+        unpacked = z->opt.provided;
+        break;
+    default:
+        has_unpacked = z->opt.has_provided;
+        unpacked = z->opt.provided;
+        break;
+    }
+    if (rc_new(&rc, *in)) return 0; /* "Failed to create a RangeDecoder because we need more data" */
+    ds_new(&z->st, lc, lp, pb, has_unpacked, unpacked);
+    lzb_init_circ(&z->out, &z->sink, dict_size, z->opt.has_memlimit ? (size_t)z->opt.memlimit : (size_t)-1);
+    z->range = rc.range;
+    z->code = rc.code;
+    *to_data = 1;
+    return 0;
+}
+
+/* Stream::read_data, stream.rs:192-207 */
+static int stream_read_data(lzo_stream *z, reader *r, lzo_error *e) {
+    rangedec rc;
+    rc.in = view_all(r);
+    rc.range = z->range;
+    rc.code = z->code;
+    TRY(ds_process_mode(z, &rc, 1, e));
+    z->range = rc.range;
+    z->code = rc.code;
+    return 0;
+}
+
+static void stream_drop_data(lzo_stream *z) {
+    lzb_drop(&z->out);
+    ds_drop(&z->st);
+}
+
+/* <Stream as io::Write>::write, stream.rs:227-325.  Returns the error kind (0 = Ok(*consumed)). */
+int lzo_stream_write(lzo_stream *z, const uint8_t *data, size_t n, size_t *consumed, lzo_error *e) {
+    reader input = {data, 0, n};
+    int rcode = 0, to_data = 0;
+    e->kind = 0;
+    e->msg[0] = 0;
+    if (z->state == 0) {
+        if (z->tmp_len > 0) { /* fill the tmp buffer, then try the header from it */
+            size_t k = n < MAX_TMP_LEN - z->tmp_len ? n : MAX_TMP_LEN - z->tmp_len;
+            reader tr;
+            view tv;
+            memcpy(z->tmp + z->tmp_len, data, k);
+            input.pos = k;
+            z->tmp_len += k;
+            tr.p = z->tmp;
+            tr.pos = 0;
+            tr.end = z->tmp_len;
+            tv = view_all(&tr);
+            rcode = stream_read_header(z, &tv, &to_data, e);
+            if (!rcode && to_data) { /* keep what follows the header + start bytes for the next call */
+                memmove(z->tmp, z->tmp + tr.pos, z->tmp_len - tr.pos);
+                z->tmp_len -= tr.pos;
+            }
+        } else {
+            view iv = view_all(&input);
+            rcode = stream_read_header(z, &iv, &to_data, e);
+            if (!rcode && !to_data) { /* not enough bytes: remember them (partial reads are undone first) */
+                size_t k = n < MAX_TMP_LEN ? n : MAX_TMP_LEN;
+                input.pos = 0;
+                memcpy(z->tmp, data, k);
+                input.pos = k;
+                z->tmp_len = k;
+            }
+        }
+        if (rcode) {
+            z->state = 2;
+            return rcode;
+        }
+        if (to_data) z->state = 1;
+    } else if (z->state == 1) {
+        if (z->tmp_len > 0) {
+            reader tr = {z->tmp, 0, z->tmp_len};
+            rcode = stream_read_data(z, &tr, e);
+            z->tmp_len = 0;
+        }
+        if (!rcode) rcode = stream_read_data(z, &input, e);
+        if (rcode) {
+            stream_drop_data(z);
+            z->state = 2;
+            return rcode;
+        }
+    }
+    *consumed = input.pos;
+    return 0;
+}
+
+/* Stream::finish, stream.rs:119-151.  Frees the stream.  res->out = what reached the sink (the reference returns the
+ * sink only on success; on error it is reported here as well, for comparison with the facade's partial output). */
+int lzo_stream_finish(lzo_stream *z, lzo_result *res) {
+    int rcode = 0;
+    memset(res, 0, sizeof *res);
+    if (z->state == 2) {
+        rcode = fail(&res->err, LZO_ERR_LZMA, "can't finish stream because of previous write error");
+    } else if (z->state == 0) {
+        if (z->tmp_len > 0) rcode = fail(&res->err, LZO_ERR_LZMA, "failed to read header");
+    } else {
+        if (!z->allow_incomplete) {
+            reader tr = {z->tmp, 0, z->tmp_len};
+            rangedec rc;
+            rc.in = view_all(&tr);
+            rc.range = z->range;
+            rc.code = z->code;
+            rcode = ds_process_mode(z, &rc, 0, &res->err);
+        }
+        if (!rcode) lzb_finish(&z->out);
+        stream_drop_data(z);
+    }
+    res->out = z->sink.data;
+    res->out_len = z->sink.len;
+    free(z);
     return rcode;
 }
 

@@ -80,6 +80,14 @@ int lzo_decompress_batch(int fmt, const uint8_t *in, const uint64_t *in_off, uin
                          uint8_t *out, const uint64_t *out_off, uint64_t *out_len,
                          int32_t *kinds, int nthreads);
 
+/* decompress::Stream (feature `stream`, src/decode/stream.rs): the incremental push decoder, restated with its dry-run
+ * logic (lzma.rs:408-524), to check the product's buffering facade.  write returns the error kind (0 = Ok, *consumed =
+ * bytes accepted); finish frees the stream and reports the sink contents. */
+typedef struct lzo_stream lzo_stream;
+lzo_stream *lzo_stream_new(const lzo_options *opt, int allow_incomplete);
+int lzo_stream_write(lzo_stream *z, const uint8_t *data, size_t n, size_t *consumed, lzo_error *err);
+int lzo_stream_finish(lzo_stream *z, lzo_result *res);
+
 /* ---- compress side (lzma_oracle_enc.c): src/lib.rs:63-80, 91-97, 108-110.  PARITY UNPINNED: the reference's tests hold
  * no golden compressed vectors, only round trips; see the header of lzma_oracle_enc.c. ---- */
 /* compress::Options / compress::UnpackedSize, src/encode/options.rs:1-30 */

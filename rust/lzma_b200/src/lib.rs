@@ -191,6 +191,9 @@ fn options(o: &decompress::Options) -> LzbOptions {
 /// `lzma_rs::decompress::Stream` (feature `stream`, src/decode/stream.rs:66-346) as a façade over the batch path:
 /// `write` buffers (and still rejects an invalid properties byte at once, stream.rs:157-190), `finish` decodes the
 /// whole stream on the GPU.  Same results as the reference; data errors surface in `finish` instead of `write`.
+/// With `allow_incomplete` on an unknown-size stream this shim returns every byte of every complete symbol, which can be
+/// a few bytes MORE than the reference (it stops as soon as its input is exhausted); the Python façade
+/// (`lzma_rs_b200.Stream._incomplete_output`) shows the two extra decodes that trim the difference.
 pub struct Stream<W: io::Write> {
     output: Option<W>,
     buf: Vec<u8>,

@@ -163,3 +163,44 @@ def lzma2_compress(data):
 
 def xz_compress(data):
     return _take(lib().lzo_xz_compress, bytes(data), len(data))
+
+
+class Stream:
+    """decompress::Stream restated in the oracle (lzo_stream_*): write / write_all / finish like the reference's."""
+
+    def __init__(self, unpacked_mode=0, provided=None, memlimit=None, allow_incomplete=False):
+        L = lib()
+        L.lzo_stream_new.restype = C.c_void_p
+        L.lzo_stream_new.argtypes = [C.POINTER(_Opt), C.c_int]
+        L.lzo_stream_write.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(_Err)]
+        L.lzo_stream_finish.argtypes = [C.c_void_p, C.POINTER(_Res)]
+        opt = make_options(unpacked_mode, provided, memlimit)
+        self._h = L.lzo_stream_new(C.byref(opt), 1 if allow_incomplete else 0)
+
+    def write(self, data):
+        """Returns (consumed, None) or (0, OracleResult-like error with .kind/.display)."""
+        n, err = C.c_size_t(), _Err()
+        kind = lib().lzo_stream_write(self._h, bytes(data), len(data), C.byref(n), C.byref(err))
+        if kind:
+            buf = C.create_string_buffer(400)
+            lib().lzo_error_display(C.byref(err), buf, 400)
+            return 0, OracleResult(b"", 0, kind, err.msg.decode(), buf.value.decode())
+        return n.value, None
+
+    def write_all(self, data):
+        """io::Write::write_all: None on success, else the error (WriteZero when a write accepts nothing)."""
+        data = bytes(data)
+        while data:
+            k, err = self.write(data)
+            if err is not None:
+                return err
+            if k == 0:
+                return OracleResult(b"", 0, 1, "failed to write whole buffer", "io error: failed to write whole buffer")
+            data = data[k:]
+        return None
+
+    def finish(self):
+        res = _Res()
+        lib().lzo_stream_finish(self._h, C.byref(res))
+        self._h = None
+        return _finish(res)
