@@ -115,3 +115,29 @@ def test_facade_matches_stream_oracle():
                 else:
                     assert _same_error(want[1], got[1]), (cut, chunk, allow, want[1], got[1])
     assert n > 300
+
+
+def test_facade_matches_stream_oracle_on_generated_streams():
+    """Valid .lzma streams of every shape the symbol-level generator produces (all property combinations incl. lc+lp > 4,
+    known and unknown sizes, with and without end marker), complete or cut at a random byte, any write chunking."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_soak
+    ctx = emul_ctx()
+    rnd = random.Random(14)
+    n = 0
+    for _ in range(700):
+        fmt, data = fuzz_soak.lzma_structured(rnd, corpus)
+        if fmt != 0 or len(data) < 2 or not oracle.lzma_decompress(data).ok:
+            continue
+        for rep in range(2):
+            cut = len(data) if rep == 0 else rnd.randrange(1, len(data) + 1)
+            allow = rnd.random() < 0.6
+            chunk = rnd.choice([1, 3, 19, 20, 21, 100, 1 << 20])
+            want = _oracle_outcome(data[:cut], chunk, allow_incomplete=allow)
+            got = _facade_outcome(ctx, data[:cut], chunk, allow_incomplete=allow)
+            n += 1
+            assert want[0] == got[0], (data.hex(), cut, chunk, allow, want, got)
+            assert want[1] == got[1] if want[0] else _same_error(want[1], got[1]), (data.hex(), cut, chunk, allow)
+    assert n > 300
