@@ -16,6 +16,9 @@
  * tests/xz.rs, src/decode/stream.rs tests; fixtures under tests/files) and
  * cross-checked against liblzma 5.4.5 (Python `lzma`), the same differential oracle the
  * reference's tests use (tests/lzma.rs:109-114, fuzz/fuzz_targets/compare_xz.rs:28-37).
+ * Also restated: the incremental decoder decompress::Stream (lzo_stream_*, pinned on the known answers of
+ * src/decode/stream.rs:348-499) and, in lzma_oracle_enc.c, the reference's three encoders (UNPINNED: the reference
+ * holds no golden compressed bytes; checked by round trips and against liblzma's decoders).
  */
 #ifndef LZMA_ORACLE_H
 #define LZMA_ORACLE_H
