@@ -194,6 +194,51 @@ class Lzma2Decoder {  // lzma2.rs:11-82
 }  // namespace raw
 }  // namespace decompress
 inline void lzma2_decompress(std::istream& in, std::ostream& out) { detail::run(LZB_FMT_LZMA2, nullptr, in, out); }
+
+// lzma_rs::decompress::Stream (feature `stream`, src/decode/stream.rs:66-346) as a buffering facade: write() stores the
+// bytes (and rejects an invalid properties byte at once, like the reference), finish() decodes the whole stream on the
+// GPU and hands everything to the sink.  Same results as the reference's incremental decoder on valid input; data
+// errors surface in finish().  With allow_incomplete on an unknown-size stream it returns every byte of every complete
+// symbol, a few bytes more than the reference (lzma_rs_b200.Stream._incomplete_output shows how to trim).
+namespace decompress {
+class Stream {
+   public:
+    explicit Stream(std::ostream& out, const Options& o = {}) : out_(&out), opt_(o) {}
+    size_t write(const void* data, size_t n) {
+        if (!out_) return 0;  // a previous write failed (stream.rs:230,310)
+        const bool first = buf_.empty();
+        buf_.append(static_cast<const char*>(data), n);
+        if (first && !buf_.empty() && (unsigned char)buf_[0] >= 225) {
+            const unsigned props = (unsigned char)buf_[0];
+            out_ = nullptr;
+            lzb_status st{};
+            st.code = LZB_E_LZMA_PROPS;
+            st.kind = LZB_KIND_LZMA;
+            st.a0 = props;
+            throw error::Error(error::Kind::LzmaError,
+                               "lzma error: LZMA header invalid properties: " + std::to_string(props) + " must be < 225", st);
+        }
+        return n;
+    }
+    std::ostream& finish() {
+        lzb_status st{};
+        if (!out_) throw error::Error(error::Kind::LzmaError, "lzma error: can't finish stream because of previous write error", st);
+        std::ostream& out = *out_;
+        out_ = nullptr;
+        if (buf_.empty()) return out;
+        const size_t hdr = opt_.unpacked_size.mode == UnpackedSize::UseProvided ? 5 : 13;
+        if (buf_.size() < hdr + 5) throw error::Error(error::Kind::LzmaError, "lzma error: failed to read header", st);
+        std::istringstream in(buf_);
+        lzma_decompress_with_options(in, out, opt_);
+        return out;
+    }
+
+   private:
+    std::ostream* out_;
+    Options opt_;
+    std::string buf_;
+};
+}  // namespace decompress
 inline void xz_decompress(std::istream& in, std::ostream& out) { detail::run(LZB_FMT_XZ, nullptr, in, out); }
 
 }  // namespace lzma_rs
