@@ -487,7 +487,10 @@ def lzma_decompress(input, output=None):
 
 
 def lzma_decompress_with_options(input, output=None, options=None):
-    """lzma_rs::lzma_decompress_with_options (src/lib.rs:52-60)."""
+    """lzma_rs::lzma_decompress_with_options (src/lib.rs:52-60).  `allow_incomplete` is an option of the stream API only
+    (options.rs:15-19): the one-shot decoder ignores it, here as in the reference."""
+    if options is not None and options.allow_incomplete:
+        options = decompress.Options(options.unpacked_size, options.memlimit, False)
     return _one(_native.FMT_LZMA, input, output, options)
 
 

@@ -73,15 +73,21 @@ inline void run(int fmt, const lzb_options* opt, std::istream& in, std::ostream&
 }
 }  // namespace detail
 
-inline void lzma_decompress_with_options(std::istream& in, std::ostream& out, const decompress::Options& o) {
+namespace detail {
+inline void run_lzma(std::istream& in, std::ostream& out, const decompress::Options& o, bool allow_incomplete) {
     lzb_options n{};
     n.unpacked_mode = (uint8_t)o.unpacked_size.mode;
     n.has_provided = o.unpacked_size.value.has_value();
     n.provided = o.unpacked_size.value.value_or(0);
     n.has_memlimit = o.memlimit.has_value();
     n.memlimit = o.memlimit.value_or(0);
-    n.allow_incomplete = o.allow_incomplete;
-    detail::run(LZB_FMT_LZMA, &n, in, out);
+    n.allow_incomplete = allow_incomplete;
+    run(LZB_FMT_LZMA, &n, in, out);
+}
+}  // namespace detail
+// allow_incomplete is an option of the stream API only (options.rs:15-19): the one-shot decoder ignores it
+inline void lzma_decompress_with_options(std::istream& in, std::ostream& out, const decompress::Options& o) {
+    detail::run_lzma(in, out, o, false);
 }
 inline void lzma_decompress(std::istream& in, std::ostream& out) { lzma_decompress_with_options(in, out, {}); }
 
@@ -229,7 +235,7 @@ class Stream {
         const size_t hdr = opt_.unpacked_size.mode == UnpackedSize::UseProvided ? 5 : 13;
         if (buf_.size() < hdr + 5) throw error::Error(error::Kind::LzmaError, "lzma error: failed to read header", st);
         std::istringstream in(buf_);
-        lzma_decompress_with_options(in, out, opt_);
+        detail::run_lzma(in, out, opt_, opt_.allow_incomplete);
         return out;
     }
 

@@ -184,7 +184,6 @@ fn options(o: &decompress::Options) -> LzbOptions {
         r.has_memlimit = 1;
         r.memlimit = m as u64;
     }
-    r.allow_incomplete = o.allow_incomplete as u8;
     r
 }
 
@@ -213,7 +212,9 @@ impl<W: io::Write> Stream<W> {
         if self.buf.is_empty() { return Ok(out); }
         let hdr = if let decompress::UnpackedSize::UseProvided(_) = self.options.unpacked_size { 5 } else { 13 };
         if self.buf.len() < hdr + 5 { return Err(error::Error::LzmaError("failed to read header".to_string())); }
-        run(FMT_LZMA, &options(&self.options), &mut &self.buf[..], &mut out)?;
+        let mut o = options(&self.options);
+        o.allow_incomplete = self.options.allow_incomplete as u8; // a stream-API option: the one-shot functions ignore it
+        run(FMT_LZMA, &o, &mut &self.buf[..], &mut out)?;
         Ok(out)
     }
 }

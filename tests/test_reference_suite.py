@@ -56,50 +56,24 @@ def run_reference_suite(api, foo_txt):
         assert api.xz_decompress(api.xz_compress(x)) == x
 
 
-class _CpuTierApi:
-    """The reference's entry points with the device replaced: decode = K1's source on the host emulation
-    (tests/host_emulation), encode = the oracle's restatement of the reference's encoders."""
+class _CpuTierCtx:
+    """Stands in for lzma_rs_b200.Context behind the REAL public entry points (L.lzma_decompress, L.Stream, ...): decode =
+    K1's source on the host emulation (tests/host_emulation), encode = the oracle's restatement of the reference's
+    encoders.  Everything above the context -- option handling, reader/writer roles, error types -- is product code."""
 
     def __init__(self):
         from test_raw_header import _EmulCtx
-        self.ctx = _EmulCtx()
+        self._emul = _EmulCtx()
 
-    def _dec(self, fmt, data, opts):
-        r = self.ctx.decompress_one(fmt, data, opts)
-        r.raise_for_status()
-        return r.data
+    def decompress_one(self, fmt, data, options=None):
+        return self._emul.decompress_one(fmt, data, options)
 
-    def lzma_decompress(self, d):
-        return self._dec(0, d, None)
-
-    def lzma_decompress_with_options(self, d, out, opts):
-        return self._dec(0, d, opts)
-
-    def lzma2_decompress(self, d):
-        return self._dec(1, d, None)
-
-    def xz_decompress(self, d):
-        return self._dec(2, d, None)
-
-    def Stream(self, out, opts=None):
-        return L.Stream(out, opts, self.ctx)
-
-    def lzma_compress(self, d):
+    def encode_batch(self, fmt, datas, options=None):
         import oracle_py
-        return oracle_py.lzma_compress(d)
-
-    def lzma_compress_with_options(self, d, out, opts):
-        import oracle_py
-        u = opts.unpacked_size
-        return oracle_py.lzma_compress(d, skip_size_field=u.skip, value=None if u.skip else u.value)
-
-    def lzma2_compress(self, d):
-        import oracle_py
-        return oracle_py.lzma2_compress(d)
-
-    def xz_compress(self, d):
-        import oracle_py
-        return oracle_py.xz_compress(d)
+        u = (options or CO()).unpacked_size
+        enc = {0: lambda d: oracle_py.lzma_compress(d, skip_size_field=u.skip, value=None if u.skip else u.value),
+               1: oracle_py.lzma2_compress, 2: oracle_py.xz_compress}[fmt]
+        return [enc(bytes(d)) for d in datas]
 
 
 def test_reference_suite_cpu_tier(golden):
@@ -107,4 +81,13 @@ def test_reference_suite_cpu_tier(golden):
     import oracle_py
     foo = oracle_py.lzma_decompress(golden.compressed(v)).out
     assert len(foo) == v["plain_len"]
-    run_reference_suite(_CpuTierApi(), foo)
+    saved = L._default_ctx
+    L._default_ctx = _CpuTierCtx()
+    try:
+        run_reference_suite(L, foo)
+        # allow_incomplete belongs to the stream API: the one-shot entry point ignores it (options.rs:15-19)
+        half = L.lzma_compress(b"Some data" * 20)[:40]
+        with pytest.raises(L.error.IoError, match="failed to fill whole buffer"):
+            L.lzma_decompress_with_options(half, None, DO(allow_incomplete=True))
+    finally:
+        L._default_ctx = saved
