@@ -388,13 +388,6 @@ def test_host_api_gated_upload(ctx):
     assert outs2 == outs and (st2["code"] == st["code"]).all()
 
 
-def test_stream_facade(ctx):
-    """decompress::Stream façade on the device: the reference's own stream tests (src/decode/stream.rs:348-499),
-    including Options::allow_incomplete (known answer: half of small.txt's compressed bytes -> its first 26 bytes)."""
-    from test_stream_facade import check_stream_facade
-    check_stream_facade(ctx)
-
-
 def test_gpu_encoders(ctx):
     """Compress side: lzma_compress / lzma2_compress / xz_compress on the GPU write exactly the bytes
     of the oracle's restatement of the reference's encoders, for every option, at chunk-size edges and in ragged batches;
@@ -555,3 +548,10 @@ def test_structured_fuzz_on_gpu(ctx):
     from test_emul_parity import structured_fuzz
     bad = structured_fuzz(_host(ctx), 20261018, 1500)
     assert not bad, f"{len(bad)} mismatches:\n" + "\n".join(bad[:20])
+
+
+def test_stream_facade(ctx):
+    """decompress::Stream façade on the device: the reference's own stream tests (src/decode/stream.rs:348-499),
+    including Options::allow_incomplete (known answer: half of small.txt's compressed bytes -> its first 26 bytes)."""
+    from test_stream_facade import check_stream_facade
+    check_stream_facade(ctx)
