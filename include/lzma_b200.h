@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LZB_ABI_VERSION 1
+#define LZB_ABI_VERSION 2
 
 /* ---- call-level return codes (infrastructure; distinct from per-stream decode status) ---- */
 enum {
@@ -185,6 +185,62 @@ int lzb_batch_collect(lzb_batch *batch, void *cuda_stream, uint64_t *out_len, ui
 void lzb_batch_destroy(lzb_batch *batch);
 /* Number of kernels one lzb_batch_launch enqueues (for bench.py's gpu_launches claim). */
 int lzb_batch_kernels_per_launch(const lzb_batch *batch);
+
+/* ---- device-side sizing and layout (replaces the reference's incremental growth of its output
+ * Vec: the sizes the reference learns chunk by chunk in lzma2.rs:128-136, 204-207 / from the .lzma header in
+ * lzma.rs:128-148 are computed for the whole batch on the device, and so is the output layout).  Everything is a
+ * DEVICE pointer except `total`: a batch that was produced on the GPU (or arrived over NVLink) is sized, laid out and
+ * decoded without its offsets or sizes ever visiting the host.
+ *   d_in_off   n+1 offsets of the streams in d_in
+ *   d_capacity n   output bytes stream i needs (same rule as lzb_scan for raw formats), may be NULL
+ *   d_out_off  n+1 exclusive prefix sum of the capacities rounded up to 16 bytes, may be NULL
+ *   total      host, *total = d_out_off[n] (the output blob to allocate), may be NULL (then no synchronisation happens)
+ * fmt = LZB_FMT_LZMA or LZB_FMT_LZMA2.  Runs on `cuda_stream` (NULL = the ctx's stream). */
+int lzb_scan_device(lzb_ctx *ctx, int fmt, const lzb_options *opt, const uint8_t *d_in, const uint64_t *d_in_off,
+                    uint32_t n, uint64_t *d_capacity, uint64_t *d_out_off, uint64_t *total, void *cuda_stream);
+/* lzb_batch_prepare with DEVICE offset arrays (e.g. the d_out_off lzb_scan_device produced). */
+int lzb_batch_prepare_device(lzb_ctx *ctx, int fmt, const lzb_options *opt, const uint8_t *d_in, const uint64_t *d_in_off,
+                             uint32_t n, uint8_t *d_out, const uint64_t *d_out_off, lzb_batch **batch);
+
+/* ---- multi-GPU (lzb_create(ctx**, dev_ids, n_dev); 8(e): independent streams shard with no data-path
+ * collective).  Two forms:
+ *  (1) one process, several devices: lzb_multi owns one lzb_ctx per device and lzb_decode_batch_multi splits a HOST
+ *      batch into contiguous stream ranges balanced by compressed bytes; every device uploads its own range over its
+ *      own PCIe link, decodes, and streams its output pages back into the caller's buffer -- n_dev copies of
+ *      lzb_decode_batch running concurrently.
+ *  (2) one process per device (torchrun / MPI ranks): the batch lives in ONE rank's HBM; that rank exports its input
+ *      and output blobs (lzb_ipc_export), the others open them (lzb_ipc_open: CUDA IPC, NVLink peer mapping) and call
+ *      lzb_decode_batch_peer on their stream range: the compressed bytes are pulled over NVLink in chunks behind K1's
+ *      input gate while the kernel already decodes, and K1 writes finished output pages straight into the owner's blob
+ *      (peer stores), so scatter, decode and gather are one launch with no staging copy and no collective. */
+typedef struct lzb_multi lzb_multi;
+int lzb_create_multi(lzb_multi **m, const int *dev_ids, int n_dev); /* dev_ids NULL / n_dev <= 0: every visible device */
+void lzb_destroy_multi(lzb_multi *m);
+int lzb_multi_device_count(const lzb_multi *m);
+lzb_ctx *lzb_multi_ctx(lzb_multi *m, int k); /* the k-th device's context (owned by m) */
+const char *lzb_multi_last_error(const lzb_multi *m);
+/* Same contract as lzb_decode_batch.  split[0..n_dev] (may be NULL) receives the stream ranges the devices got. */
+int lzb_decode_batch_multi(lzb_multi *m, int fmt, const lzb_options *opt, const uint8_t *in, const uint64_t *in_off,
+                           uint32_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_len, uint64_t *consumed,
+                           lzb_status *st, uint32_t *split);
+
+typedef struct lzb_ipc_handle {
+    uint8_t handle[64]; /* cudaIpcMemHandle_t of the allocation that contains the pointer */
+    uint64_t offset;    /* of the pointer inside that allocation */
+    uint64_t bytes;     /* informational */
+} lzb_ipc_handle;
+int lzb_ipc_export(lzb_ctx *ctx, const void *d_ptr, uint64_t bytes, lzb_ipc_handle *h);
+int lzb_ipc_open(lzb_ctx *ctx, const lzb_ipc_handle *h, void **d_ptr); /* maps the exporter's memory into this process */
+int lzb_ipc_close(lzb_ctx *ctx, void *d_ptr);                          /* d_ptr as returned by lzb_ipc_open */
+/* Decode streams whose bytes live in memory this device can reach but that is not its own HBM -- a peer GPU's blob
+ * (lzb_ipc_open, or cudaDeviceEnablePeerAccess in one process) or pinned host memory -- into a blob of the same kind:
+ *   stream i input = src_in[in_off[i], in_off[i+1]),  output -> dst_out[out_off[i], ...)   (out_off[i] 16-byte aligned)
+ * fmt = LZB_FMT_LZMA or LZB_FMT_LZMA2; offsets / results are host arrays.  The framing scan (K2) reads src_in in
+ * place; the input follows in chunks behind the gate; output pages are stored to dst_out by the decode kernel.
+ * Synchronises before returning. */
+int lzb_decode_batch_peer(lzb_ctx *ctx, int fmt, const lzb_options *opt, const uint8_t *src_in, const uint64_t *in_off,
+                          uint32_t n, uint8_t *dst_out, const uint64_t *out_off, uint64_t *out_len, uint64_t *consumed,
+                          lzb_status *st);
 
 /* Single-stream convenience for the Rust/C++ shim: scan + decode + (for end-marker .lzma) capacity
  * retry.  *out is malloc'ed by the library (free with lzb_free) and holds *out_len bytes -- on error

@@ -31,6 +31,24 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t, uint32_t) { return __bu
 static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { return (hi << s) | (lo >> (32 - s)); }
 #endif
 
+// Round-2 restructurings of the non-literal half of K1 (each can be switched off for an A/B measurement with
+// tools/kbench.py: -DLZB_R2_xxx=0).  DESIGN.md section 4 has the measured effect of each.
+#ifndef LZB_R2_DIRECT
+#define LZB_R2_DIRECT 1  // rc_direct: carry-chain bit accumulation + min() code update, sentinel-terminated loop
+#endif
+#ifndef LZB_R2_TREES
+#define LZB_R2_TREES 1   // align (and, == 1, the per-slot reverse trees) unrolled: 15 instead of 22 instructions per level
+#endif
+#ifndef LZB_R2_COPY
+#define LZB_R2_COPY 1    // short non-overlapping matches: one predicated load/store pass, prev/match byte by shuffle
+#endif
+#ifndef LZB_R2_CHECKS
+#define LZB_R2_CHECKS 1  // per-symbol limit checks folded into one compare pair, the ordered checks only behind it
+#endif
+#ifndef LZB_R2_STATE
+#define LZB_R2_STATE 1   // arithmetic state transitions instead of the packed-nibble table; 3-instruction literal row
+#endif
+
 #define LZB_PRAGMA_(x) _Pragma(#x)
 #define LZB_PRAGMA(x) LZB_PRAGMA_(x)
 #define RC_TOP (1u << 24)
@@ -208,9 +226,30 @@ LZB_DEV uint32_t rc_bit(Dec& d, const LzbKC& kc, const Tab& t, uint32_t idx) {
     return bit;
 }
 
-// get(count), rangecoder.rs:72-90.  (Taking the bits in normalisation-free groups of 31 - clz(range) - 23 halvings
-// was tried: same result, no gain -- the loop is not where the time goes.)
+// get(count), rangecoder.rs:72-90 (count >= 1 at the only call site).  (Taking the bits in normalisation-free groups
+// of 31 - clz(range) - 23 halvings was tried: same result, no gain.)
+// Device form: the compare is the carry of code + ~range + 1 (set when code >= range: that is how ptxas lowers
+// sub.cc, checked in the SASS: IADD3 ..., P0 / IMAD.X ..., P0); `addc` shifts it into the accumulator behind a
+// sentinel 1, so the loop ends when the sentinel reaches bit `count` (no counter), and the conditional subtraction is
+// min(code, code - range): when code < range the difference wraps above code.
+// 10 instructions per bit instead of 13 (profiles/r01_k1_final.txt lines 1427-1437).
 LZB_DEV uint32_t rc_direct(Dec& d, uint32_t count) {
+#if defined(__CUDACC__) && LZB_R2_DIRECT
+    uint32_t r = 1;
+    const uint32_t end = 1u << count;
+#pragma unroll 1
+    do {
+        d.range >>= 1;
+        asm("{\n\t.reg .u32 t;\n\t"
+            "sub.cc.u32 t, %1, %2;\n\t"   // carry = (code >= range) = the bit
+            "addc.u32 %0, %0, %0;\n\t"    // r = 2r + bit
+            "min.u32 %1, %1, t;\n\t}"
+            : "+r"(r), "+r"(d.code)
+            : "r"(d.range));
+        rc_normalize(d);
+    } while (r < end);
+    return r - end;
+#else
     uint32_t r = 0;
 #pragma unroll 1
     for (uint32_t i = 0; i < count; i++) {
@@ -221,6 +260,7 @@ LZB_DEV uint32_t rc_direct(Dec& d, uint32_t count) {
         r = (r << 1) | (b ? 1u : 0u);
     }
     return r;
+#endif
 }
 
 // Bit-tree walk (parse_bit_tree, rangecoder.rs:122-134) of `nb` levels; `t` is the tree's table (node m at index m).
@@ -255,6 +295,27 @@ LZB_DEV uint32_t rc_tree_walk(Dec& d, const LzbKC& kc, const Tab& t, uint32_t nb
 template <class Tab>
 LZB_DEV uint32_t rc_tree_rt(Dec& d, const LzbKC& kc, const Tab& t, uint32_t nb) {
     return rc_tree_walk<false, 0>(d, kc, t, nb);
+}
+
+// Walk of nb <= MAXNB levels (nb >= 1), unrolled with an exit test per level: no loop counter, no constant reloads
+// inside a rolled body (the rolled loop costs 22 instructions per level, an unrolled level 15 + the exit test).
+template <int MAXNB, class Tab>
+LZB_DEV uint32_t rc_tree_upto(Dec& d, const LzbKC& kc, const Tab& t, uint32_t nb) {
+    const uint32_t x0 = t.x0(kc), x1 = t.x1(kc);
+    uint32_t node = t.root(kc);
+    uint32_t pv = t.ldn(kc, node);
+#pragma unroll
+    for (int i = 0; i < MAXNB; i++) {
+        uint32_t np;
+        const uint32_t child = rc_step_tree(d, kc, pv, np, node, x0, x1);
+        t.stn(kc, node, np);
+        node = child;
+        const bool more = (uint32_t)(i + 1) < nb;
+        if (i + 1 < MAXNB && more) pv = t.ldn(kc, node);
+        rc_normalize(d);
+        if (!more) break;
+    }
+    return t.node_index(kc, node);
 }
 
 LZB_DEV uint32_t rev_bits(uint32_t v, uint32_t nb) {  // the low nb bits of v, reversed
@@ -582,6 +643,15 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
         uint32_t stop_at = has_target ? dict_base + target : 0xFFFFFFFFu;
         if (has_target && target > 0xFFFFFFFFu - dict_base) stop_at = 0xFFFFFFFFu;
         uint32_t lit_limit = cap < mem_stop ? cap : mem_stop;
+#if LZB_R2_CHECKS
+        // first position a match may not reach: capacity / memlimit, and for LZMA2 the chunk's declared size
+        uint32_t match_limit = is_lzma1 ? lit_limit : LZB_MIN(lit_limit, stop_at);
+        LZB_KEEP(match_limit);
+#endif
+#if LZB_R2_STATE
+        uint32_t row_mask = (1u << (lc + lp)) - 1;
+        LZB_KEEP(row_mask);
+#endif
         LZB_KEEP(pb_mask);
         LZB_KEEP(lp_mask);
         LZB_KEEP(lit_shift);
@@ -603,7 +673,12 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
             // literal context row (decode_literal, lzma.rs:526-538).  After a literal (state < 7) prev_byte is in a
             // register, so the root of the plain literal tree is fetched while is_match is being decoded.
+#if LZB_R2_STATE
+            // ((len & lp_mask) << lc) + (prev_byte >> (8 - lc)) as one shift of len:prev_byte
+            const uint32_t lit_row = (((len << 8) | prev_byte) >> lit_shift) & row_mask;
+#else
             const uint32_t lit_row = ((len & lp_mask) << lc) + (prev_byte >> lit_shift);
+#endif
             const PlainTab probs = plain.at(kc, lit_row * plain_stride);
             const uint32_t i_is_match = T_IS_MATCH + (state << 4) + pos_state;
             const uint32_t p_is_match = tab.ld16(kc, i_is_match);
@@ -654,16 +729,28 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     }
                     sym = probs.node_index(kc, node);
                 }
+#if LZB_R2_CHECKS
+                if (LZB_UNLIKELY((d.p > d.lim) | (opos >= lit_limit))) {
+                    if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
+                    if (opos >= mem_stop) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
+                    FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);
+                }
+#else
                 if (LZB_UNLIKELY(d.p > d.lim)) FAIL(LZB_E_IO_EOF, 0, 0);
                 if (LZB_UNLIKELY(opos >= lit_limit)) {
                     if (LZB_UNLIKELY(opos >= mem_stop)) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
                     FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);
                 }
+#endif
                 prev_byte = sym & 0xFFu;
                 if (lane == 0) out[opos] = (uint8_t)prev_byte;
                 opos += 1;
-                // state after a literal (lzma.rs:299-305): 0,0,0,0,1,2,3,4,5,6,4,5 as packed nibbles
+                // state after a literal (lzma.rs:299-305): 0,0,0,0,1,2,3,4,5,6,4,5
+#if LZB_R2_STATE
+                state = state < 10 ? (state > 3 ? state - 3 : 0u) : state - 6;
+#else
                 state = (uint32_t)(0x546543210000ull >> (state * 4)) & 0xFu;
+#endif
                 mb_valid = false;
                 continue;
             }
@@ -710,7 +797,12 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                         const uint32_t base = L + (c1 ? (uint32_t)T_LEN_MID : (uint32_t)T_LEN_LOW) + pos_state * 8;
                         l = rc_tree_walk<true, 3>(d, kc, tab.at(kc, base), 3) - 8 + c1 * 8;
                     } else {
-                        l = rc_tree_rt(d, kc, tab.at(kc, L + T_LEN_HIGH), 8) - 256 + 16;
+#if LZB_R2_TREES
+                        if (WIDE == 1)  // run-length batches (config 5) take this coder on every symbol
+                            l = rc_tree_walk<true, 8>(d, kc, tab.at(kc, L + T_LEN_HIGH), 8) - 256 + 16;
+                        else
+#endif
+                            l = rc_tree_rt(d, kc, tab.at(kc, L + T_LEN_HIGH), 8) - 256 + 16;
                     }
                     if (is_rep) {
                         state = state < 7 ? 8 : 11;
@@ -725,10 +817,18 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                             uint32_t r = (2u | (pos_slot & 1u)) << nd;
                             if (pos_slot < 14) {  // per-slot reverse tree (own aligned block, see lzb_types.h)
                                 const uint32_t off = 2u * ((1u << nd) - 2u) + ((pos_slot & 1u) << nd);
+#if LZB_R2_TREES == 1
+                                r += rev_bits(rc_tree_upto<5>(d, kc, tab.at(kc, T_POS_DEC + off), nd), nd);
+#else
                                 r += rev_bits(rc_tree_rt(d, kc, tab.at(kc, T_POS_DEC + off), nd), nd);
+#endif
                             } else {
                                 r += rc_direct(d, nd - 4) << 4;
+#if LZB_R2_TREES
+                                r += rev_bits(rc_tree_walk<true, 4>(d, kc, tab.at(kc, T_ALIGN), 4), 4);
+#else
                                 r += rev_bits(rc_tree_rt(d, kc, tab.at(kc, T_ALIGN), 4), 4);
+#endif
                             }
                             rep0 = r;
                         }
@@ -745,17 +845,38 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
             // ---- append_lz(mlen, rep0 + 1), lzbuffer.rs:125-143 / 272-297
             {
-                if (LZB_UNLIKELY(rep0 >= dict_size)) FAIL(LZB_E_LZ_DIST_DICT, (uint64_t)rep0 + 1, dict_size);
-                if (LZB_UNLIKELY(rep0 >= len)) FAIL(LZB_E_LZ_DIST_OUT, (uint64_t)rep0 + 1, len);
-                if (LZB_UNLIKELY(mem_stop - opos < mlen && mem_stop != 0xFFFFFFFFu)) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
-                if (!is_lzma1 && len + mlen > target)  // the window is never flushed past this point
-                    FAIL(LZB_E_UNPACKED_MISMATCH, target, (uint64_t)len + mlen);
-                if (LZB_UNLIKELY(cap - opos < mlen)) FAIL(LZB_E_CAPACITY, (uint64_t)opos + mlen, 0);
+#if LZB_R2_CHECKS
+                // one compare pair on the common path; the reference's ordered checks only behind it (any failure of
+                // the pair implies that one of them fails: match_limit is the smallest of their limits)
+                if (LZB_UNLIKELY((rep0 >= LZB_MIN(dict_size, len)) | (match_limit - opos < mlen)))
+#endif
+                {
+                    if (LZB_UNLIKELY(rep0 >= dict_size)) FAIL(LZB_E_LZ_DIST_DICT, (uint64_t)rep0 + 1, dict_size);
+                    if (LZB_UNLIKELY(rep0 >= len)) FAIL(LZB_E_LZ_DIST_OUT, (uint64_t)rep0 + 1, len);
+                    if (LZB_UNLIKELY(mem_stop - opos < mlen && mem_stop != 0xFFFFFFFFu)) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
+                    if (!is_lzma1 && len + mlen > target)  // the window is never flushed past this point
+                        FAIL(LZB_E_UNPACKED_MISMATCH, target, (uint64_t)len + mlen);
+                    if (LZB_UNLIKELY(cap - opos < mlen)) FAIL(LZB_E_CAPACITY, (uint64_t)opos + mlen, 0);
+                }
                 const uint32_t dist = rep0 + 1;
                 const uint8_t* src = out + opos - dist;
                 uint8_t* dst = out + opos;
                 LZB_SYNCWARP();  // earlier stores of other lanes are visible to these loads
                 uint32_t i_last = mlen - 1, i_next = mlen;
+#if defined(__CUDACC__) && LZB_R2_COPY
+                if (mlen < 32u && dist >= mlen) {
+                    // the common match: one predicated pass.  Lanes 0..mlen-1 move the bytes; lane mlen also loads the byte
+                    // behind the source range (= out[new opos - dist], the match byte of a following literal) unless that is
+                    // dst[0] itself (dist == mlen), which lane 0 holds.  prev_byte / match_byte then come from a shuffle
+                    // instead of two more global round trips on the next symbol's dependency chain.
+                    const uint32_t nload = mlen + (dist > mlen ? 1u : 0u);
+                    uint32_t v = 0;
+                    if ((uint32_t)lane < nload) v = src[lane];
+                    if ((uint32_t)lane < mlen) dst[lane] = (uint8_t)v;
+                    prev_byte = __shfl_sync(0xffffffffu, v, (int)i_last);
+                    match_byte = __shfl_sync(0xffffffffu, v, (int)(dist > mlen ? mlen : 0u));
+                } else
+#endif
                 if (dist >= mlen) {
                     for (uint32_t i = lane; i < mlen; i += LZB_LANES) dst[i] = src[i];
                     if (dist == mlen) i_next = 0;

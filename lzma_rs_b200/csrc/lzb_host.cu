@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <mutex>
 #include <numeric>
+#include <thread>
+#include <utility>
 #include <chrono>
 #include <functional>
 #include <vector>
@@ -40,7 +42,8 @@ LZB_K1_PROTO(lzb_decode_sched_copy_kernel);
 LZB_K1_PROTO(lzb_decode_sched_copy_mirror_kernel);
 LZB_K1_PROTO(lzb_decode_biglit_kernel);
 extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, const uint64_t*, const uint64_t*, uint32_t,
-                                           LzbItem*, LzbScan*);
+                                           LzbItem*, LzbScan*, uint64_t, uint64_t*);
+extern "C" __global__ void lzb_layout_kernel(const uint64_t*, uint32_t, uint64_t*);
 extern "C" __global__ void lzb_crc_partial_kernel(const uint8_t*, const LzbCrcRange*, const uint32_t*, uint64_t,
                                                   uint32_t*, uint64_t*);
 extern "C" __global__ void lzb_stored_decode_kernel(const LzbItem*, const uint32_t*, const uint8_t*, uint8_t*, LzbResult*);
@@ -91,14 +94,15 @@ struct lzb_ctx {
     // lzb_decode_batch_device keeps ONE batch object alive between calls: its device buffers are reused instead of
     // paying six cudaMalloc / cudaFree (each a device synchronisation) per call
     struct lzb_batch* oneshot = nullptr;
+    struct lzb_batch* peer_batch = nullptr;  // lzb_decode_batch_peer's reusable batch (under ctx->mu)
     std::mutex oneshot_mu;
     int sm_count = 0;
     int smem_optin = 0;
-    int smem_configured[12] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1}, smem_configured_big = -1;
     char err[320] = {0};
     std::mutex mu;
+    std::vector<std::pair<void*, void*>> ipc_open;  // (pointer handed out, base returned by cudaIpcOpenMemHandle)
     DevBuf d_in, d_out, d_items, d_results, d_order, d_counter, d_scan, d_off, d_crc_ranges, d_crc_segmap, d_crc_part32,
-        d_crc_part64, d_crc_out32, d_crc_out64, d_litws, d_matchws, d_gate, d_enc_items, d_enc_results, d_enc_pieces;
+        d_crc_part64, d_crc_out32, d_crc_out64, d_litws, d_matchws, d_gate, d_enc_items, d_enc_results, d_enc_pieces, d_cap;
     int enc_smem_configured = 0;
 };
 #define LZB_GATE_CHUNK (8ull << 20)  // upload granularity of the gated host path
@@ -128,6 +132,19 @@ struct Trace {
 struct LaunchCfg {
     uint32_t lclp, warp_bytes, warps, grid;
 };
+
+// K1 variants: [sched][mirror][lean | fill | copy] (+ the lc+lp > 4 kernel).  Their dynamic shared-memory limit is raised
+// once per device in lzb_create, so launches never touch function attributes (several threads may launch prepared
+// batches of one context at the same time).
+typedef void (*k1_t)(const LzbItem*, const uint32_t*, uint32_t, uint32_t, const uint8_t*, uint8_t*, LzbResult*,
+                     unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long, const LzbKC,
+                     const unsigned long long*);
+const k1_t k1_variants[13] = {
+    lzb_decode_kernel,              lzb_decode_fill_kernel,              lzb_decode_copy_kernel,
+    lzb_decode_mirror_kernel,       lzb_decode_fill_mirror_kernel,       lzb_decode_copy_mirror_kernel,
+    lzb_decode_sched_kernel,        lzb_decode_sched_fill_kernel,        lzb_decode_sched_copy_kernel,
+    lzb_decode_sched_mirror_kernel, lzb_decode_sched_fill_mirror_kernel, lzb_decode_sched_copy_mirror_kernel,
+    lzb_decode_biglit_kernel};
 
 LaunchCfg decode_config(const lzb_ctx* ctx, uint32_t n, uint32_t lclp) {
     LaunchCfg c;
@@ -261,19 +278,8 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         CUDA_TRY(ctx, matchws.ensure((size_t)c.grid * c.warps * mstride * 2));
         // variants: [sched][mirror][lean | fill | copy]; mirror = host API with a pinned output buffer (finished pages
         // streamed to the host); sched = the launch carries a placement plan (lzb_sched.h)
-        typedef void (*kern_t)(const LzbItem*, const uint32_t*, uint32_t, uint32_t, const uint8_t*, uint8_t*, LzbResult*,
-                               unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long, const LzbKC,
-                               const unsigned long long*);
-        static const kern_t kernels[12] = {
-            lzb_decode_kernel,              lzb_decode_fill_kernel,              lzb_decode_copy_kernel,
-            lzb_decode_mirror_kernel,       lzb_decode_fill_mirror_kernel,       lzb_decode_copy_mirror_kernel,
-            lzb_decode_sched_kernel,        lzb_decode_sched_fill_kernel,        lzb_decode_sched_copy_kernel,
-            lzb_decode_sched_mirror_kernel, lzb_decode_sched_fill_mirror_kernel, lzb_decode_sched_copy_mirror_kernel};
+        const k1_t* kernels = k1_variants;
         const int v = (p.n_static ? 6 : 0) + (mirror ? 3 : 0) + p.wide;
-        if (smem > ctx->smem_configured[v]) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[v], cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
-            ctx->smem_configured[v] = ctx->smem_optin;
-        }
         if (int rc = fire()) return rc;
         kernels[v]<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, p.n_static, d_in_base, d_out_base, d_results,
                                                       d_counter, c.lclp, c.warp_bytes, matchws.as<uint16_t>(), mstride, kc,
@@ -283,11 +289,6 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
     if (nb) {
         const LaunchCfg& c = p.cfg_big;
         const int smem = (int)(c.warps * c.warp_bytes);
-        if (smem > ctx->smem_configured_big) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(lzb_decode_biglit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               ctx->smem_optin));
-            ctx->smem_configured_big = ctx->smem_optin;
-        }
         CUDA_TRY(ctx, litws.ensure((size_t)c.grid * c.warps * p.big_stride_u16 * 2));
         if (int rc = fire()) return rc;
         lzb_decode_biglit_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order + ns, nb, 0u, d_in_base, d_out_base,
@@ -485,6 +486,45 @@ class CudaExecutor : public lzb::Executor {
     std::vector<void*> scratch_;
 };
 
+// Arms K1's input gate for a blob of `in_bytes` bytes at `src` (pinned host memory, or a peer GPU's memory) that goes to
+// ctx->d_in + lead: the gate words are uploaded on ctx->stream, and `*upload` becomes the closure that enqueues the
+// chunked copy (+ one watermark update per chunk) on ctx->copy_stream.  The closure is run by launch_plan right before
+// the first K1 launch is enqueued.
+int arm_gate(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_lo, uint64_t in_bytes,
+             std::function<int()>* upload, const unsigned long long** d_gate) {
+    uint64_t chunk = LZB_GATE_CHUNK;
+    while ((lead + in_bytes + chunk - 1) / chunk > LZB_GATE_MAX_CHUNKS) chunk *= 2;
+    CUDA_TRY(ctx, ctx->d_gate.ensure(64));
+    unsigned long long* hm = ctx->h_marks;
+    hm[0] = 0;                                      // watermark: device offset reached so far
+    hm[1] = (unsigned long long)(lead - in_lo);     // device offset = blob offset + this (mod 2^64)
+    hm[2] = (unsigned long long)(lead + in_bytes);  // device offset of the end of the blob
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, hm, 24, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->gate_ready, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gate_ready, 0));
+    *upload = [=]() -> int {
+        uint32_t k = 0;
+        for (uint64_t lo = lead; lo < lead + in_bytes; k++) {  // chunk boundaries at device offsets k * chunk
+            const uint64_t hi = std::min<uint64_t>((lo / chunk + 1) * chunk, lead + in_bytes);
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + lo, src + (lo - lead), hi - lo, cudaMemcpyDefault,
+                                          ctx->copy_stream));
+            hm[8 + k] = hi;
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, &hm[8 + k], 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            lo = hi;
+        }
+        return LZB_RC_OK;
+    };
+    *d_gate = ctx->d_gate.as<unsigned long long>();
+    return LZB_RC_OK;
+}
+
+struct CopyJoin {  // no exit path may leave copies in flight into ctx->d_in
+    cudaStream_t s;
+    ~CopyJoin() {
+        if (s) cudaStreamSynchronize(s);
+    }
+};
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -514,6 +554,11 @@ extern "C" int lzb_create(lzb_ctx** out, int device) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    for (k1_t k : k1_variants)
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin) != cudaSuccess) {
+            lzb_destroy(ctx);
+            return LZB_RC_CUDA;
+        }
     *out = ctx;
     return LZB_RC_OK;
 }
@@ -527,10 +572,14 @@ extern "C" void lzb_destroy(lzb_ctx* ctx) {
         lzb_batch_destroy(ctx->oneshot);
         ctx->oneshot = nullptr;
     }
+    if (ctx->peer_batch) {
+        lzb_batch_destroy(ctx->peer_batch);
+        ctx->peer_batch = nullptr;
+    }
     DevBuf* bufs[] = {&ctx->d_in, &ctx->d_out, &ctx->d_items, &ctx->d_results, &ctx->d_order, &ctx->d_counter, &ctx->d_scan,
                       &ctx->d_off, &ctx->d_crc_ranges, &ctx->d_crc_segmap, &ctx->d_crc_part32, &ctx->d_crc_part64,
                       &ctx->d_crc_out32, &ctx->d_crc_out64, &ctx->d_litws, &ctx->d_matchws, &ctx->d_gate,
-                      &ctx->d_enc_items, &ctx->d_enc_results, &ctx->d_enc_pieces};
+                      &ctx->d_enc_items, &ctx->d_enc_results, &ctx->d_enc_pieces, &ctx->d_cap};
     for (DevBuf* b : bufs) b->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -580,38 +629,11 @@ extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, c
     // lzb_kernels.cu), so the upload overlaps the decode.  Otherwise: one copy, in stream order before the kernel.
     const unsigned long long* d_gate = nullptr;
     std::function<int()> upload;
-    struct CopyJoin {  // no exit path may leave copies in flight into ctx->d_in
-        cudaStream_t s;
-        ~CopyJoin() {
-            if (s) cudaStreamSynchronize(s);
-        }
-    } join{nullptr};
+    CopyJoin join{nullptr};
     const uint64_t in_bytes = in_hi - in_lo, lead = in_lo & 15;
     if (host_mirror && in_bytes >= 2 * LZB_GATE_CHUNK && !getenv("LZB_NO_GATE")) {
-        uint64_t chunk = LZB_GATE_CHUNK;
-        while ((lead + in_bytes + chunk - 1) / chunk > LZB_GATE_MAX_CHUNKS) chunk *= 2;
-        CUDA_TRY(ctx, ctx->d_gate.ensure(64));
-        unsigned long long* hm = ctx->h_marks;
-        hm[0] = 0;                                        // watermark: device offset reached so far
-        hm[1] = (unsigned long long)(lead - in_lo);       // device offset = blob offset + this (mod 2^64)
-        hm[2] = (unsigned long long)(lead + in_bytes);    // device offset of the end of the blob
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, hm, 24, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaEventRecord(ctx->gate_ready, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gate_ready, 0));
         join.s = ctx->copy_stream;
-        upload = [=]() -> int {
-            uint32_t k = 0;
-            for (uint64_t lo = lead; lo < lead + in_bytes; k++) {  // chunk boundaries at device offsets k * chunk
-                const uint64_t hi = std::min<uint64_t>((lo / chunk + 1) * chunk, lead + in_bytes);
-                CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + lo, in + in_lo + (lo - lead), hi - lo,
-                                              cudaMemcpyHostToDevice, ctx->copy_stream));
-                hm[8 + k] = hi;
-                CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, &hm[8 + k], 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-                lo = hi;
-            }
-            return LZB_RC_OK;
-        };
-        d_gate = ctx->d_gate.as<unsigned long long>();
+        if (int rc = arm_gate(ctx, in + in_lo, lead, in_lo, in_bytes, &upload, &d_gate)) return rc;
     } else if (in_bytes) {
         CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, in + in_lo, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
@@ -649,16 +671,24 @@ struct lzb_batch {
     std::vector<LzbItem> items;  // host copy (hdr_len, preset info)
     bool allow_incomplete = false;
     DecodePlan plan;
+    uint32_t lclp_hint = 0;
+    uint64_t stored_bytes = 0;
+    DevBuf d_redo_items, d_redo_results, d_redo_order, d_redo_counter;  // second pass of lzb_batch_collect (rare)
 };
 
 // Fills `b` (a fresh batch, or one whose device buffers are being reused) for one batch of streams.
+// dev_offsets: in_off / out_off are device arrays.  mirror_base: see lzb_scan_kernel (0 = no mirror; with a mirror every
+// stream goes through K1: the stored-chunk copy kernel does not stream pages).  scan_in: blob the framing scan reads
+// (nullptr = d_in; lzb_decode_batch_peer scans the remote copy while d_in is still being filled).
 static int batch_prepare_into(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in, const uint64_t* in_off,
-                              uint32_t n, uint8_t* d_out, const uint64_t* out_off, lzb_batch* b) {
+                              uint32_t n, uint8_t* d_out, const uint64_t* out_off, lzb_batch* b, bool dev_offsets = false,
+                              uint64_t mirror_base = 0, const uint8_t* scan_in = nullptr, bool take_lock = true) {
     static const lzb_options defaults = {0, 0, 0, 0, {0, 0, 0, 0}, 0, 0};
     if (!ctx || !in_off || !out_off || (fmt != LZB_FMT_LZMA && fmt != LZB_FMT_LZMA2) || n == 0 || !d_in || !d_out)
         return LZB_RC_BAD_ARG;
     if (((uintptr_t)d_in & 15) || ((uintptr_t)d_out & 15)) return LZB_RC_BAD_ARG;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::unique_lock<std::mutex> lock(ctx->mu, std::defer_lock);
+    if (take_lock) lock.lock();
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     b->ctx = ctx;
     b->n = n;
@@ -683,10 +713,12 @@ static int batch_prepare_into(lzb_ctx* ctx, int fmt, const lzb_options* opt, con
     B_TRY(b->d_off.ensure(2 * (size_t)(n + 1) * 8));
     uint64_t* d_in_off = b->d_off.as<uint64_t>();
     uint64_t* d_out_off = d_in_off + (n + 1);
-    B_TRY(cudaMemcpyAsync(d_in_off, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-    B_TRY(cudaMemcpyAsync(d_out_off, out_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-    lzb_scan_kernel<<<(n + 127) / 128, 128, 0, s>>>(fmt, opt ? *opt : defaults, d_in, d_in_off, d_out_off, n,
-                                                    b->d_items.as<LzbItem>(), b->d_scan.as<LzbScan>());
+    const cudaMemcpyKind off_kind = dev_offsets ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    B_TRY(cudaMemcpyAsync(d_in_off, in_off, (n + 1) * 8, off_kind, s));
+    B_TRY(cudaMemcpyAsync(d_out_off, out_off, (n + 1) * 8, off_kind, s));
+    lzb_scan_kernel<<<(n + 127) / 128, 128, 0, s>>>(fmt, opt ? *opt : defaults, scan_in ? scan_in : d_in, d_in_off,
+                                                    d_out_off, n, b->d_items.as<LzbItem>(), b->d_scan.as<LzbScan>(),
+                                                    mirror_base, nullptr);
     B_TRY(cudaGetLastError());
     std::vector<LzbScan> scan(n);
     b->items.resize(n);
@@ -699,11 +731,49 @@ static int batch_prepare_into(lzb_ctx* ctx, int fmt, const lzb_options* opt, con
         if (b->items[i].kind == LZB_ITEM_LZMA2) lclp = std::max<uint32_t>(lclp, scan[i].max_lclp);
         stored_bytes += scan[i].stored;
     }
-    make_plan(ctx, b->items.data(), n, lclp, stored_bytes, &b->plan);
+    b->lclp_hint = lclp;
+    b->stored_bytes = stored_bytes;
+    make_plan(ctx, b->items.data(), n, lclp, stored_bytes, &b->plan, /*route_stored=*/mirror_base == 0);
     if (upload_order(ctx, s, b->plan, b->d_order) != LZB_RC_OK) return fail(LZB_RC_CUDA);
     B_TRY(cudaStreamSynchronize(s));
     return LZB_RC_OK;
 #undef B_TRY
+}
+
+// Second pass over the few streams the first launch could not finish (same rule as CudaExecutor::decode on the host
+// path): LZMA2 streams whose framing scan under-estimated lc+lp -- the scan skips `packed` bytes per chunk while the
+// decoder continues where the range coder stopped (SURVEY 3.5 leniency (d)), so a later chunk header it never saw can ask
+// for more -- are rerun with tables sized for lc+lp = 4; streams whose input missed the gate's timeout are rerun once the
+// copy stream has drained.  `res` is patched in place.
+static int batch_redo(lzb_batch* b, cudaStream_t s, std::vector<LzbResult>& res, bool mirror) {
+    lzb_ctx* ctx = b->ctx;
+    std::vector<uint32_t> redo;
+    for (uint32_t i = 0; i < b->n; i++) {
+        const bool lclp = b->items[i].kind == LZB_ITEM_LZMA2 && res[i].code == LZB_E_UNSUPPORTED && res[i].a0 <= 4 &&
+                          res[i].a1 < 4;
+        if (lclp || res[i].code == LZB_E_INPUT_TIMEOUT) redo.push_back(i);
+    }
+    if (redo.empty()) return LZB_RC_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    const uint32_t m = (uint32_t)redo.size();
+    std::vector<LzbItem> sub(m);
+    for (uint32_t k = 0; k < m; k++) sub[k] = b->items[redo[k]];
+    DecodePlan plan;
+    make_plan(ctx, sub.data(), m, 4, b->stored_bytes, &plan, /*route_stored=*/!mirror);
+    CUDA_TRY(ctx, b->d_redo_items.ensure(m * sizeof(LzbItem)));
+    CUDA_TRY(ctx, b->d_redo_results.ensure(m * sizeof(LzbResult)));
+    CUDA_TRY(ctx, b->d_redo_counter.ensure(64));
+    CUDA_TRY(ctx, cudaMemcpyAsync(b->d_redo_items.p, sub.data(), m * sizeof(LzbItem), cudaMemcpyHostToDevice, s));
+    if (int rc = upload_order(ctx, s, plan, b->d_redo_order)) return rc;
+    if (int rc = launch_plan(ctx, s, plan, b->d_redo_items.as<LzbItem>(), b->d_redo_order.as<uint32_t>(), b->d_in, b->d_out,
+                             b->d_redo_results.as<LzbResult>(), b->d_redo_counter.as<unsigned int>(), mirror, nullptr,
+                             nullptr, &b->d_matchws, &b->d_litws))
+        return rc;
+    std::vector<LzbResult> subres(m);
+    CUDA_TRY(ctx, cudaMemcpyAsync(subres.data(), b->d_redo_results.p, m * sizeof(LzbResult), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    for (uint32_t k = 0; k < m; k++) res[redo[k]] = subres[k];
+    return LZB_RC_OK;
 }
 
 extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in, const uint64_t* in_off,
@@ -728,6 +798,8 @@ extern "C" int lzb_batch_prepare(lzb_ctx* ctx, int fmt, const lzb_options* opt, 
 extern "C" int lzb_batch_launch(lzb_batch* b, void* cuda_stream) {
     if (!b) return LZB_RC_BAD_ARG;
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : b->ctx->stream;
+    // a caller driving several GPUs from one thread may have another device current
+    if (cudaSetDevice(b->ctx->device) != cudaSuccess) return LZB_RC_CUDA;
     return launch_plan(b->ctx, s, b->plan, b->d_items.as<LzbItem>(), b->d_order.as<uint32_t>(), b->d_in, b->d_out,
                        b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>(), false, nullptr, nullptr, &b->d_matchws,
                        &b->d_litws);
@@ -741,9 +813,11 @@ extern "C" int lzb_batch_collect(lzb_batch* b, void* cuda_stream, uint64_t* out_
     if (!b) return LZB_RC_BAD_ARG;
     lzb_ctx* ctx = b->ctx;
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     std::vector<LzbResult> res(b->n);
     CUDA_TRY(ctx, cudaMemcpyAsync(res.data(), b->d_results.p, b->n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (int rc = batch_redo(b, s, res, false)) return rc;
     lzb_options o = {};
     o.allow_incomplete = b->allow_incomplete;
     for (uint32_t i = 0; i < b->n; i++) {
@@ -759,7 +833,7 @@ extern "C" void lzb_batch_destroy(lzb_batch* b) {
     if (!b) return;
     if (b->ctx) cudaSetDevice(b->ctx->device);
     DevBuf* bufs[] = {&b->d_items, &b->d_results, &b->d_order, &b->d_counter, &b->d_scan, &b->d_off, &b->d_matchws,
-                      &b->d_litws};
+                      &b->d_litws, &b->d_redo_items, &b->d_redo_results, &b->d_redo_order, &b->d_redo_counter};
     for (DevBuf* x : bufs) x->release();
     delete b;
 }
@@ -781,6 +855,276 @@ extern "C" int lzb_decode_batch_device(lzb_ctx* ctx, int fmt, const lzb_options*
     rc = lzb_batch_launch(b, cuda_stream);
     if (rc == LZB_RC_OK) rc = lzb_batch_collect(b, cuda_stream, out_len, consumed, st);
     return rc;
+}
+
+extern "C" int lzb_batch_prepare_device(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in,
+                                        const uint64_t* d_in_off, uint32_t n, uint8_t* d_out, const uint64_t* d_out_off,
+                                        lzb_batch** out) {
+    if (!out) return LZB_RC_BAD_ARG;
+    *out = nullptr;
+    lzb_batch* b = new lzb_batch();
+    int rc = batch_prepare_into(ctx, fmt, opt, d_in, d_in_off, n, d_out, d_out_off, b, /*dev_offsets=*/true);
+    if (rc != LZB_RC_OK) {
+        if (ctx) {
+            b->ctx = ctx;
+            lzb_batch_destroy(b);
+        } else {
+            delete b;
+        }
+        return rc;
+    }
+    *out = b;
+    return LZB_RC_OK;
+}
+
+// Sizes + output layout of a device-resident batch, all on the device (K2 + lzb_layout_kernel).
+extern "C" int lzb_scan_device(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in, const uint64_t* d_in_off,
+                               uint32_t n, uint64_t* d_capacity, uint64_t* d_out_off, uint64_t* total, void* cuda_stream) {
+    static const lzb_options defaults = {0, 0, 0, 0, {0, 0, 0, 0}, 0, 0};
+    if (!ctx || (fmt != LZB_FMT_LZMA && fmt != LZB_FMT_LZMA2) || !d_in_off || (n && !d_in)) return LZB_RC_BAD_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);  // K2 writes the context's scratch items
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CUDA_TRY(ctx, ctx->d_items.ensure(std::max<size_t>(n, 1) * sizeof(LzbItem)));
+    CUDA_TRY(ctx, ctx->d_scan.ensure(std::max<size_t>(n, 1) * sizeof(LzbScan)));
+    uint64_t* cap = d_capacity;
+    if (!cap) {
+        CUDA_TRY(ctx, ctx->d_cap.ensure(std::max<size_t>(n, 1) * 8));
+        cap = ctx->d_cap.as<uint64_t>();
+    }
+    if (n) {
+        lzb_scan_kernel<<<(n + 127) / 128, 128, 0, s>>>(fmt, opt ? *opt : defaults, d_in, d_in_off, nullptr, n,
+                                                        ctx->d_items.as<LzbItem>(), ctx->d_scan.as<LzbScan>(), 0, cap);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    if (d_out_off) {
+        lzb_layout_kernel<<<1, 1024, 0, s>>>(cap, n, d_out_off);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    if (total) {
+        *total = 0;
+        if (d_out_off) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(total, d_out_off + n, 8, cudaMemcpyDeviceToHost, s));
+        }
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    }
+    return LZB_RC_OK;
+}
+
+// ---- CUDA IPC: a blob in one process's HBM, mapped into the other ranks of the node (NVLink peer access) ----
+extern "C" int lzb_ipc_export(lzb_ctx* ctx, const void* d_ptr, uint64_t bytes, lzb_ipc_handle* h) {
+    if (!ctx || !d_ptr || !h) return LZB_RC_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(h->handle), "lzb_ipc_handle::handle is a cudaIpcMemHandle_t");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    // the handle names the whole allocation; find its base through the driver entry point (no libcuda link dependency)
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(ctx, cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (!fn || ((range_fn)fn)(&base, &size, (unsigned long long)(uintptr_t)d_ptr) != 0) {
+        snprintf(ctx->err, sizeof(ctx->err), "cuMemGetAddressRange failed for %p", d_ptr);
+        return LZB_RC_CUDA;
+    }
+    cudaIpcMemHandle_t mh;
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&mh, (void*)(uintptr_t)base));
+    memcpy(h->handle, &mh, sizeof mh);
+    h->offset = (uint64_t)(uintptr_t)d_ptr - base;
+    h->bytes = bytes;
+    return LZB_RC_OK;
+}
+
+extern "C" int lzb_ipc_open(lzb_ctx* ctx, const lzb_ipc_handle* h, void** d_ptr) {
+    if (!ctx || !h || !d_ptr) return LZB_RC_BAD_ARG;
+    *d_ptr = nullptr;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, h->handle, sizeof mh);
+    void* base = nullptr;
+    CUDA_TRY(ctx, cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        ctx->ipc_open.push_back({(uint8_t*)base + h->offset, base});
+    }
+    *d_ptr = (uint8_t*)base + h->offset;
+    return LZB_RC_OK;
+}
+
+extern "C" int lzb_ipc_close(lzb_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return LZB_RC_BAD_ARG;
+    void* base = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        for (size_t i = 0; i < ctx->ipc_open.size(); i++)
+            if (ctx->ipc_open[i].first == d_ptr) {
+                base = ctx->ipc_open[i].second;
+                ctx->ipc_open.erase(ctx->ipc_open.begin() + i);
+                break;
+            }
+    }
+    if (!base) return LZB_RC_BAD_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaIpcCloseMemHandle(base));
+    return LZB_RC_OK;
+}
+
+// Scatter + decode + gather for one rank's stream range as ONE launch: see include/lzma_b200.h.
+extern "C" int lzb_decode_batch_peer(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* src_in,
+                                     const uint64_t* in_off, uint32_t n, uint8_t* dst_out, const uint64_t* out_off,
+                                     uint64_t* out_len, uint64_t* consumed, lzb_status* st) {
+    if (!ctx || !in_off || !out_off || (fmt != LZB_FMT_LZMA && fmt != LZB_FMT_LZMA2)) return LZB_RC_BAD_ARG;
+    if (n == 0) return LZB_RC_OK;
+    if (!src_in || !dst_out || ((uintptr_t)dst_out & 15)) return LZB_RC_BAD_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    Trace trace;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t in_lo = in_off[0], in_hi = in_off[n], out_lo = out_off[0], out_hi = out_off[n];
+    const uint64_t in_bytes = in_hi - in_lo;
+    // local staging keeps the 16-byte congruence of the remote offsets (and the 4-byte congruence K2 / K1 rely on)
+    const uint64_t lead = ((uintptr_t)src_in + in_lo) & 15;
+    CUDA_TRY(ctx, ctx->d_in.ensure(in_bytes + 256));
+    CUDA_TRY(ctx, ctx->d_out.ensure((out_hi - out_lo) + 64));
+    uint8_t* d_in0 = ctx->d_in.as<uint8_t>() + lead;
+    uint8_t* d_out0 = ctx->d_out.as<uint8_t>() + (out_lo & 15);
+    if (!ctx->peer_batch) {
+        ctx->peer_batch = new lzb_batch();
+        ctx->peer_batch->ctx = ctx;
+    }
+    lzb_batch* b = ctx->peer_batch;
+    // K1 addresses its blobs as base + offset: hand it bases that put offset in_lo / out_lo on the local copies.  Their low
+    // four bits: d_in0 - in_lo == src_in (mod 16) by the choice of `lead`; K2 reads the remote blob in place.
+    const uint8_t* in_base = d_in0 - in_lo;
+    uint8_t* out_base = d_out0 - out_lo;
+    const uint8_t* scan_base = src_in;
+    // batch_prepare_into wants 16-byte aligned bases: fold the misalignment of src_in into shifted offset arrays
+    std::vector<uint64_t> in_adj;
+    const uint64_t mis = (uintptr_t)src_in & 15;
+    if (mis) {
+        in_adj.assign(in_off, in_off + n + 1);
+        for (auto& v : in_adj) v += mis;
+        in_off = in_adj.data();
+        scan_base -= mis;
+        in_base -= mis;
+    }
+    int rc = batch_prepare_into(ctx, fmt, opt, in_base, in_off, n, out_base, out_off, b, false,
+                                (uint64_t)(uintptr_t)dst_out, scan_base, /*take_lock=*/false);
+    if (rc != LZB_RC_OK) return rc;
+    bool all_mirrored = true;
+    for (uint32_t i = 0; i < n; i++)
+        if (b->items[i].kind != LZB_ITEM_PRESET && (out_off[i] & 15)) all_mirrored = false;
+    trace.plan = trace.now();
+    // the input follows behind the gate; small shards are not worth the chunking
+    const unsigned long long* d_gate = nullptr;
+    std::function<int()> upload;
+    CopyJoin join{nullptr};
+    if (in_bytes >= 2 * LZB_GATE_CHUNK && !getenv("LZB_NO_GATE")) {
+        join.s = ctx->copy_stream;
+        if ((rc = arm_gate(ctx, src_in + (in_off[0] - mis), lead, in_off[0], in_bytes, &upload, &d_gate))) return rc;
+    } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, src_in + (in_off[0] - mis), in_bytes, cudaMemcpyDefault, ctx->stream));
+    }
+    cudaStream_t s = ctx->stream;
+    rc = launch_plan(ctx, s, b->plan, b->d_items.as<LzbItem>(), b->d_order.as<uint32_t>(), in_base, out_base,
+                     b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>(), /*mirror=*/true, d_gate, &upload,
+                     &b->d_matchws, &b->d_litws);
+    if (rc != LZB_RC_OK) return rc;
+    trace.launched = trace.now();
+    std::vector<LzbResult> res(n);
+    CUDA_TRY(ctx, cudaMemcpyAsync(res.data(), b->d_results.p, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if ((rc = batch_redo(b, s, res, true))) return rc;
+    if (out_hi > out_lo && !all_mirrored)  // some stream's region was not 16-byte aligned: plain copy of the whole range
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst_out + out_lo, d_out0, out_hi - out_lo, cudaMemcpyDefault, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    lzb_options o = {};
+    o.allow_incomplete = b->allow_incomplete;
+    for (uint32_t i = 0; i < n; i++) {
+        if (lzb::lenient_eof(fmt, &o, &res[i])) res[i].code = LZB_OK, res[i].sink_len = res[i].out_len;
+        if (st) lzb::status_from_result(res[i], &st[i]);
+        if (out_len) out_len[i] = res[i].sink_len;
+        if (consumed) consumed[i] = b->items[i].hdr_len + res[i].consumed;
+    }
+    if (trace.on)
+        fprintf(stderr, "lzb_trace peer n=%u in=%llu gated=%d planned=%.3f launched=%.3f end=%.3f ms\n", n,
+                (unsigned long long)in_bytes, d_gate != nullptr, trace.plan, trace.launched, trace.now());
+    return LZB_RC_OK;
+}
+
+// ---- one process, several devices ----
+struct lzb_multi {
+    std::vector<lzb_ctx*> ctxs;
+    char err[400] = {0};
+};
+
+extern "C" int lzb_create_multi(lzb_multi** out, const int* dev_ids, int n_dev) {
+    if (!out) return LZB_RC_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return LZB_RC_NO_DEVICE;
+    std::vector<int> ids;
+    if (!dev_ids || n_dev <= 0)
+        for (int d = 0; d < count; d++) ids.push_back(d);
+    else
+        ids.assign(dev_ids, dev_ids + n_dev);
+    lzb_multi* m = new lzb_multi();
+    for (int d : ids) {
+        lzb_ctx* c = nullptr;
+        int rc = (d < 0 || d >= count) ? LZB_RC_BAD_ARG : lzb_create(&c, d);
+        if (rc != LZB_RC_OK) {
+            lzb_destroy_multi(m);
+            return rc;
+        }
+        m->ctxs.push_back(c);
+    }
+    *out = m;
+    return LZB_RC_OK;
+}
+
+extern "C" void lzb_destroy_multi(lzb_multi* m) {
+    if (!m) return;
+    for (lzb_ctx* c : m->ctxs) lzb_destroy(c);
+    delete m;
+}
+
+extern "C" int lzb_multi_device_count(const lzb_multi* m) { return m ? (int)m->ctxs.size() : 0; }
+extern "C" lzb_ctx* lzb_multi_ctx(lzb_multi* m, int k) { return m && k >= 0 && k < (int)m->ctxs.size() ? m->ctxs[k] : nullptr; }
+extern "C" const char* lzb_multi_last_error(const lzb_multi* m) { return m ? m->err : "null multi"; }
+
+extern "C" int lzb_decode_batch_multi(lzb_multi* m, int fmt, const lzb_options* opt, const uint8_t* in, const uint64_t* in_off,
+                                      uint32_t n, uint8_t* out, const uint64_t* out_off, uint64_t* out_len,
+                                      uint64_t* consumed, lzb_status* st, uint32_t* split) {
+    if (!m || m->ctxs.empty() || !in_off || !out_off || !out_len || !consumed || !st) return LZB_RC_BAD_ARG;
+    const uint32_t nd = (uint32_t)m->ctxs.size();
+    // contiguous stream ranges with equal shares of the compressed bytes (decode time is proportional to decisions, for
+    // which the compressed length is the cheap proxy); contiguous, so every device's call is a plain sub-range of the
+    // caller's arrays and its uploads / page stores touch one slice of the caller's buffers
+    std::vector<uint32_t> cut(nd + 1, n);
+    cut[0] = 0;
+    const uint64_t base = n ? in_off[0] : 0, total = n ? in_off[n] - in_off[0] : 0;
+    for (uint32_t k = 1; k < nd; k++) {
+        const uint64_t target = base + (total / nd) * k + (total % nd) * k / nd;
+        uint32_t c = (uint32_t)(std::lower_bound(in_off, in_off + n + 1, target) - in_off);
+        cut[k] = std::min(std::max(c, cut[k - 1]), n);
+    }
+    if (split) memcpy(split, cut.data(), (nd + 1) * sizeof(uint32_t));
+    std::vector<int> rcs(nd, LZB_RC_OK);
+    std::vector<std::thread> th;
+    for (uint32_t k = 0; k < nd; k++) {
+        const uint32_t lo = cut[k], cnt = cut[k + 1] - cut[k];
+        if (!cnt) continue;
+        th.emplace_back([=, &rcs]() {
+            rcs[k] = lzb_decode_batch(m->ctxs[k], fmt, opt, in, in_off + lo, cnt, out, out_off + lo, out_len + lo,
+                                      consumed + lo, st + lo);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (uint32_t k = 0; k < nd; k++)
+        if (rcs[k] != LZB_RC_OK) {
+            snprintf(m->err, sizeof m->err, "device %d: %s", m->ctxs[k]->device, m->ctxs[k]->err);
+            return rcs[k];
+        }
+    return LZB_RC_OK;
 }
 
 extern "C" int lzb_decompress_alloc(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* in, size_t in_len,

@@ -137,7 +137,8 @@ LZB_DEFINE_K1(lzb_decode_biglit_kernel, true, true, 1, false)
 // ------------------------------------------------------------------------------------------------
 extern "C" __global__ void lzb_scan_kernel(int fmt, lzb_options opt, const uint8_t* __restrict__ in_blob,
                                            const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ out_off,
-                                           uint32_t n, LzbItem* items, LzbScan* scan) {
+                                           uint32_t n, LzbItem* items, LzbScan* scan, uint64_t mirror_base,
+                                           uint64_t* capacity) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint8_t* p = in_blob + in_off[i];
@@ -255,8 +256,45 @@ extern "C" __global__ void lzb_scan_kernel(int fmt, lzb_options opt, const uint8
         it.kind = LZB_ITEM_PRESET;
         it.preset_code = LZB_E_UNSUPPORTED;
     }
+    // mirror_base: device-visible address of offset 0 of a second copy of the output blob (pinned host memory or a
+    // peer GPU's blob); the mirror variants of K1 store finished pages there (16-byte vectors: both copies aligned)
+    if (mirror_base && it.kind != LZB_ITEM_PRESET && (it.out_off & 15) == 0) it.host_out = mirror_base + it.out_off;
     items[i] = it;
     scan[i] = sc;
+    if (capacity) {  // lzb_scan's rule for the raw formats (lzb::scan_capacity)
+        const uint64_t bound = len * 16384 + (1u << 20);
+        uint64_t c;
+        if (fmt == LZB_FMT_LZMA)
+            c = it.kind == LZB_ITEM_PRESET ? 0 : ((sc.flags & 1) && sc.unpacked <= bound) ? sc.unpacked + 288 : len * 8 + 65536;
+        else
+            c = sc.unpacked < bound ? sc.unpacked : bound;
+        capacity[i] = c;
+    }
+}
+
+// Output layout on the device: out_off = exclusive prefix sum of the capacities rounded up to 16 bytes (n + 1 entries).
+// One CTA; every thread sums a contiguous slice, the slice totals are scanned in shared memory.
+extern "C" __global__ void __launch_bounds__(1024) lzb_layout_kernel(const uint64_t* __restrict__ capacity, uint32_t n,
+                                                                     uint64_t* out_off) {
+    __shared__ uint64_t part[1024];
+    const uint32_t t = threadIdx.x, per = (n + 1023u) / 1024u;
+    const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
+    uint64_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += (capacity[i] + 15ull) & ~15ull;
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan of the slice totals
+        const uint64_t v = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint64_t run = t ? part[t - 1] : 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        out_off[i] = run;
+        run += (capacity[i] + 15ull) & ~15ull;
+    }
+    if (t == 1023) out_off[n] = part[1023];
 }
 
 // ------------------------------------------------------------------------------------------------
