@@ -28,6 +28,10 @@ class CompressOptions(C.Structure):  # lzb_compress_options
                 ("value", C.c_uint64)]
 
 
+class IpcHandle(C.Structure):  # lzb_ipc_handle
+    _fields_ = [("handle", C.c_uint8 * 64), ("offset", C.c_uint64), ("bytes", C.c_uint64)]
+
+
 class Status(C.Structure):  # lzb_status
     _fields_ = [("code", C.c_int32), ("kind", C.c_int32), ("a0", C.c_uint64), ("a1", C.c_uint64), ("a2", C.c_uint64)]
 
@@ -39,7 +43,10 @@ assert STATUS_DTYPE.itemsize == C.sizeof(Status)
 EXPORTS = ["lzb_create", "lzb_destroy", "lzb_last_error", "lzb_abi_version", "lzb_scan", "lzb_decode_batch",
            "lzb_decode_batch_device", "lzb_batch_prepare", "lzb_batch_launch", "lzb_batch_collect", "lzb_batch_destroy",
            "lzb_batch_kernels_per_launch", "lzb_decompress_alloc", "lzb_free", "lzb_crc_device", "lzb_format_error",
-           "lzb_encode_bound", "lzb_encode_batch", "lzb_encode_batch_device"]
+           "lzb_encode_bound", "lzb_encode_batch", "lzb_encode_batch_device",
+           "lzb_scan_device", "lzb_batch_prepare_device", "lzb_create_multi", "lzb_destroy_multi", "lzb_multi_device_count",
+           "lzb_multi_ctx", "lzb_multi_last_error", "lzb_decode_batch_multi", "lzb_ipc_export", "lzb_ipc_open",
+           "lzb_ipc_close", "lzb_decode_batch_peer"]
 
 _lib = None
 
@@ -90,6 +97,21 @@ def bind(path):
         lib.lzb_encode_batch.argtypes = [vp, C.c_int, C.POINTER(CompressOptions), vp, u64p, C.c_uint32, vp, u64p, u64p, vp]
         lib.lzb_encode_batch_device.argtypes = [vp, C.c_int, C.POINTER(CompressOptions), vp, u64p, C.c_uint32, vp, u64p,
                                                 u64p, vp, vp]
+    if hasattr(lib, "lzb_decode_batch_peer"):  # ABI v2
+        lib.lzb_scan_device.argtypes = [vp, C.c_int, C.POINTER(Options), vp, vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint64), vp]
+        lib.lzb_batch_prepare_device.argtypes = [vp, C.c_int, C.POINTER(Options), vp, vp, C.c_uint32, vp, vp, C.POINTER(vp)]
+        lib.lzb_create_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+        lib.lzb_destroy_multi.argtypes = [vp]
+        lib.lzb_multi_device_count.argtypes = [vp]
+        lib.lzb_multi_ctx.argtypes = [vp, C.c_int]
+        lib.lzb_multi_ctx.restype = vp
+        lib.lzb_multi_last_error.argtypes = [vp]
+        lib.lzb_multi_last_error.restype = C.c_char_p
+        lib.lzb_decode_batch_multi.argtypes = [vp, C.c_int, C.POINTER(Options), vp, u64p, C.c_uint32, vp, u64p, u64p, u64p, vp, vp]
+        lib.lzb_ipc_export.argtypes = [vp, vp, C.c_uint64, C.POINTER(IpcHandle)]
+        lib.lzb_ipc_open.argtypes = [vp, C.POINTER(IpcHandle), C.POINTER(vp)]
+        lib.lzb_ipc_close.argtypes = [vp, vp]
+        lib.lzb_decode_batch_peer.argtypes = [vp, C.c_int, C.POINTER(Options), vp, u64p, C.c_uint32, vp, u64p, u64p, u64p, vp]
     return lib
 
 

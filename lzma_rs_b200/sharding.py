@@ -175,7 +175,13 @@ def decode_sharded_tensors(decode_fn, blob, in_off, caps, src=0, group=None):
             a, b = int(in_all[cuts[r]]), int(in_all[cuts[r + 1]])
             if r != src and b > a:
                 reqs.append(dist.isend(blob[a:b], dst=r, group=group))
-        shard, shard_base, out_base = blob, 0, 0  # the source decodes straight out of / into the full blobs
+        # the source decodes straight out of / into the full blobs.  The kernels read whole aligned words: when the
+        # source's own range reaches the end of `blob` without 16 bytes of slack behind it, decode a padded copy instead
+        shard, shard_base, out_base = blob, 0, 0
+        if in_hi > in_lo and in_hi + 16 > blob.numel():
+            shard = torch.zeros(in_hi - in_lo + 16, dtype=torch.uint8, device=dev)
+            shard[:in_hi - in_lo] = blob[in_lo:in_hi]
+            shard_base = in_lo
     else:
         shard = torch.zeros(in_hi - in_lo + 16, dtype=torch.uint8, device=dev)
         if in_hi > in_lo:

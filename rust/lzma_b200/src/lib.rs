@@ -2,6 +2,10 @@
 //! of `include/lzma_b200.h`.  Replace `use lzma_rs::{lzma_decompress, lzma2_decompress, xz_decompress}` with
 //! `use lzma_b200::{...}`; `decompress::{Options, UnpackedSize}` and `error::{Error, Result}` keep their shapes.
 //!
+//! Besides the one-shot functions there is a batch form of each (`*_decompress_batch(&[&[u8]])`, the call the benchmark
+//! drives), a slice form that reports `consumed` (`decompress_slice`), and `set_devices` to spread batches over several
+//! GPUs of the node.
+//!
 //! NOT COMPILED in the build image (no Rust toolchain there) -- see INTEGRATION.md.
 use std::io;
 use std::os::raw::{c_char, c_int, c_void};
@@ -87,8 +91,26 @@ struct LzbCompressOptions {
 struct LzbCtx {
     _private: [u8; 0],
 }
+#[repr(C)]
+struct LzbMulti {
+    _private: [u8; 0],
+}
 extern "C" {
     fn lzb_create(ctx: *mut *mut LzbCtx, device: c_int) -> c_int;
+    fn lzb_create_multi(m: *mut *mut LzbMulti, dev_ids: *const c_int, n_dev: c_int) -> c_int;
+    fn lzb_multi_ctx(m: *mut LzbMulti, k: c_int) -> *mut LzbCtx;
+    fn lzb_scan(
+        ctx: *mut LzbCtx, fmt: c_int, opt: *const LzbOptions, input: *const u8, in_off: *const u64, n: u32,
+        capacity: *mut u64,
+    ) -> c_int;
+    fn lzb_decode_batch(
+        ctx: *mut LzbCtx, fmt: c_int, opt: *const LzbOptions, input: *const u8, in_off: *const u64, n: u32, out: *mut u8,
+        out_off: *const u64, out_len: *mut u64, consumed: *mut u64, st: *mut LzbStatus,
+    ) -> c_int;
+    fn lzb_decode_batch_multi(
+        m: *mut LzbMulti, fmt: c_int, opt: *const LzbOptions, input: *const u8, in_off: *const u64, n: u32, out: *mut u8,
+        out_off: *const u64, out_len: *mut u64, consumed: *mut u64, st: *mut LzbStatus, split: *mut u32,
+    ) -> c_int;
     fn lzb_decompress_alloc(
         ctx: *mut LzbCtx, fmt: c_int, opt: *const LzbOptions, input: *const u8, in_len: usize, out: *mut *mut u8,
         out_len: *mut usize, consumed: *mut usize, st: *mut LzbStatus,
@@ -105,11 +127,33 @@ const FMT_LZMA: c_int = 0;
 const FMT_LZMA2: c_int = 1;
 const FMT_XZ: c_int = 2;
 
-struct Ctx(*mut LzbCtx);
+/// The process-wide engine: one context on the current device, or (after `set_devices`) one per listed device.
+struct Ctx {
+    one: *mut LzbCtx,
+    multi: *mut LzbMulti, // null unless set_devices() was called with more than one device
+}
 unsafe impl Send for Ctx {}
 static CTX: Mutex<Option<Ctx>> = Mutex::new(None);
 
-fn with_ctx<T>(f: impl FnOnce(*mut LzbCtx) -> T) -> io::Result<T> {
+/// Use these CUDA devices for the `*_batch` functions (host batches are split into contiguous stream ranges with equal
+/// compressed bytes, every device uploads and decodes its own range: `lzb_decode_batch_multi`).  Call before the first
+/// decode; an empty slice = every visible device.  The single-stream functions use the first device.
+pub fn set_devices(devices: &[i32]) -> io::Result<()> {
+    let mut g = CTX.lock().unwrap();
+    if g.is_some() {
+        return Err(io::Error::new(io::ErrorKind::Other, "lzma_b200: set_devices() must precede the first decode"));
+    }
+    let mut m: *mut LzbMulti = std::ptr::null_mut();
+    let ids: Vec<c_int> = devices.iter().map(|&d| d as c_int).collect();
+    let rc = unsafe { lzb_create_multi(&mut m, if ids.is_empty() { std::ptr::null() } else { ids.as_ptr() }, ids.len() as c_int) };
+    if rc != 0 {
+        return Err(io::Error::new(io::ErrorKind::Other, format!("lzb_create_multi failed ({})", rc)));
+    }
+    *g = Some(Ctx { one: unsafe { lzb_multi_ctx(m, 0) }, multi: m });
+    Ok(())
+}
+
+fn with_engine<T>(f: impl FnOnce(&Ctx) -> T) -> io::Result<T> {
     let mut g = CTX.lock().unwrap();
     if g.is_none() {
         let mut p: *mut LzbCtx = std::ptr::null_mut();
@@ -117,9 +161,13 @@ fn with_ctx<T>(f: impl FnOnce(*mut LzbCtx) -> T) -> io::Result<T> {
         if rc != 0 {
             return Err(io::Error::new(io::ErrorKind::Other, format!("lzb_create failed ({}): no CUDA device", rc)));
         }
-        *g = Some(Ctx(p));
+        *g = Some(Ctx { one: p, multi: std::ptr::null_mut() });
     }
-    Ok(f(g.as_ref().unwrap().0))
+    Ok(f(g.as_ref().unwrap()))
+}
+
+fn with_ctx<T>(f: impl FnOnce(*mut LzbCtx) -> T) -> io::Result<T> {
+    with_engine(|e| f(e.one))
 }
 
 fn to_error(st: &LzbStatus) -> error::Error {
@@ -138,31 +186,225 @@ fn to_error(st: &LzbStatus) -> error::Error {
     }
 }
 
-fn run<R: io::BufRead, W: io::Write>(fmt: c_int, opt: &LzbOptions, input: &mut R, output: &mut W) -> error::Result<()> {
-    // The batch decoder wants the whole stream: buffer the reader, then give back what was not consumed.
-    let mut buf = Vec::new();
-    input.read_to_end(&mut buf)?;
+/// One decode of `data` (a complete stream, or a prefix of one).  Returns (status, output, consumed).
+fn decode_slice(fmt: c_int, opt: &LzbOptions, data: &[u8]) -> error::Result<(LzbStatus, Vec<u8>, usize)> {
     let mut out: *mut u8 = std::ptr::null_mut();
     let (mut out_len, mut consumed) = (0usize, 0usize);
     let mut st = LzbStatus::default();
     let rc = with_ctx(|c| unsafe {
-        lzb_decompress_alloc(c, fmt, opt, buf.as_ptr(), buf.len(), &mut out, &mut out_len, &mut consumed, &mut st)
+        lzb_decompress_alloc(c, fmt, opt, data.as_ptr(), data.len(), &mut out, &mut out_len, &mut consumed, &mut st)
     })?;
     if rc != 0 {
         return Err(error::Error::IoError(io::Error::new(io::ErrorKind::Other, format!("lzma_b200 call failed: {}", rc))));
     }
-    // like the reference, partial output reaches the sink even when the stream then fails
-    let res = if out_len > 0 { output.write_all(unsafe { std::slice::from_raw_parts(out, out_len) }) } else { Ok(()) };
+    let v = if out_len > 0 { unsafe { std::slice::from_raw_parts(out, out_len) }.to_vec() } else { Vec::new() };
     unsafe { lzb_free(out as *mut c_void) };
-    res?;
+    Ok((st, v, consumed))
+}
+
+/// Slice form of the three entry points: decodes the stream at the start of `data` and returns the output together with
+/// the number of input bytes the reference would have consumed (`lzma_rs` leaves the rest of its reader unread:
+/// src/decode/lzma2.rs:59-68, src/decode/lzma.rs:442-445).
+pub fn decompress_slice(fmt: Format, data: &[u8], opts: &decompress::Options) -> error::Result<(Vec<u8>, usize)> {
+    let (st, out, consumed) = decode_slice(fmt as c_int, &options(opts), data)?;
     if st.code != 0 {
         return Err(to_error(&st));
     }
-    // NOTE: a `&[u8]` / `Cursor` caller that needs the reference's "trailing bytes stay unread" behaviour should use
-    // `decompress_slice`, which returns `consumed`; a generic BufRead cannot be un-read.
-    let _ = consumed;
+    Ok((out, consumed))
+}
+/// Stream formats = the reference's three entry points.
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+#[repr(i32)]
+pub enum Format {
+    Lzma = 0,
+    Lzma2 = 1,
+    Xz = 2,
+}
+
+/// Status codes that mean "the decoder ran out of input" (include/lzma_b200.h): the stream may simply continue
+/// behind what the reader's buffer showed us.
+fn ran_out_of_input(st: &LzbStatus) -> bool {
+    matches!(st.code, 1 | 2 | 4 | 12 | 14 | 15 | 16 | 19 | 20)
+}
+
+/// End of a raw LZMA2 stream inside `buf` (index behind its 0x00 control byte) if the chunk headers seen so far reach it;
+/// `None` = more bytes are needed.  Framing only (lzma2.rs:59-78, 128-136, 204-207); malformed framing ends the walk
+/// where the reference's error would.
+fn lzma2_extent(buf: &[u8]) -> Option<usize> {
+    let mut q = 0usize;
+    loop {
+        let status = *buf.get(q)?;
+        q += 1;
+        if status == 0 {
+            return Some(q);
+        }
+        if status == 1 || status == 2 {
+            let n = ((*buf.get(q)? as usize) << 8 | *buf.get(q + 1)? as usize) + 1;
+            q += 2 + n;
+        } else if status < 0x80 {
+            return Some(q); // invalid control byte: the reference fails here
+        } else {
+            let packed = ((*buf.get(q + 2)? as usize) << 8 | *buf.get(q + 3)? as usize) + 1;
+            q += 4 + if status >= 0xC0 { 1 } else { 0 } + packed;
+        }
+        if q > buf.len() {
+            return None;
+        }
+    }
+}
+
+fn run<R: io::BufRead, W: io::Write>(fmt: c_int, opt: &LzbOptions, input: &mut R, output: &mut W) -> error::Result<()> {
+    // The batch decoder wants the whole stream, the reference reads only as much of its BufRead as the stream needs.
+    // 1) Decode what the reader's buffer shows (`fill_buf` does not consume).  For in-memory readers (`&[u8]`, `Cursor`)
+    //    that is everything: the decode is final and exactly `consumed` bytes are taken, trailing bytes stay unread like
+    //    in the reference.
+    // 2) A streaming reader whose buffer ends inside the stream: LZMA2 is read up to the end its chunk headers give
+    //    (exact for well-formed framing); .xz takes the rest of the reader (the reference rejects trailing data anyway,
+    //    xz.rs:88-92); .lzma takes the rest of the reader too -- the one documented deviation: its compressed length
+    //    is only known by decoding it.
+    let first: Vec<u8> = input.fill_buf()?.to_vec(); // a copy: the borrow of `input` must end before consume()
+    let (st, out, consumed) = decode_slice(fmt, opt, &first)?;
+    let (st, out) = if !ran_out_of_input(&st) {
+        // success, or an error the reference would raise on the same bytes: partial output still reaches the sink
+        input.consume(consumed.min(first.len()));
+        (st, out)
+    } else {
+        let mut buf = first;
+        let n = buf.len();
+        input.consume(n);
+        if fmt == FMT_LZMA2 {
+            loop {
+                if let Some(end) = lzma2_extent(&buf) {
+                    debug_assert!(end <= buf.len());
+                    break;
+                }
+                let more: Vec<u8> = input.fill_buf()?.to_vec();
+                if more.is_empty() {
+                    break; // truncated stream: the decode below reports the reference's error
+                }
+                // take only up to the end of the stream if it lies inside this refill
+                let have = buf.len();
+                buf.extend_from_slice(&more);
+                let take = match lzma2_extent(&buf) {
+                    Some(end) => end - have,
+                    None => more.len(),
+                };
+                buf.truncate(have + take);
+                input.consume(take);
+            }
+        } else {
+            input.read_to_end(&mut buf)?;
+        }
+        let (st, out, _consumed) = decode_slice(fmt, opt, &buf)?;
+        (st, out)
+    };
+    // like the reference, partial output reaches the sink even when the stream then fails
+    if !out.is_empty() {
+        output.write_all(&out)?;
+    }
+    if st.code != 0 {
+        return Err(to_error(&st));
+    }
     output.flush()?;
     Ok(())
+}
+
+/// Batch form of an entry point: n independent streams in one launch (what `bench.py` drives through the same C call).
+/// Element i is what `f(&mut inputs[i], &mut Vec::new())` of the one-shot function returns, with the decoded bytes.
+fn decode_many(fmt: c_int, opt: &LzbOptions, inputs: &[&[u8]]) -> Vec<error::Result<Vec<u8>>> {
+    let n = inputs.len();
+    if n == 0 {
+        return Vec::new();
+    }
+    let fail = |msg: String| -> Vec<error::Result<Vec<u8>>> {
+        (0..n).map(|_| Err(error::Error::IoError(io::Error::new(io::ErrorKind::Other, msg.clone())))).collect()
+    };
+    let mut in_off = Vec::with_capacity(n + 1);
+    let mut blob = Vec::with_capacity(inputs.iter().map(|s| s.len()).sum::<usize>() + 16);
+    in_off.push(0u64);
+    for s in inputs {
+        blob.extend_from_slice(s);
+        in_off.push(blob.len() as u64);
+    }
+    blob.extend_from_slice(&[0u8; 16]);
+    let mut cap = vec![0u64; n];
+    let rc = match with_ctx(|c| unsafe { lzb_scan(c, fmt, opt, blob.as_ptr(), in_off.as_ptr(), n as u32, cap.as_mut_ptr()) }) {
+        Ok(rc) => rc,
+        Err(e) => return fail(e.to_string()),
+    };
+    if rc != 0 {
+        return fail(format!("lzb_scan failed: {}", rc));
+    }
+    let mut pending: Vec<usize> = (0..n).collect();
+    let mut results: Vec<Option<error::Result<Vec<u8>>>> = (0..n).map(|_| None).collect();
+    // streams whose size the headers do not give (end-marker .lzma) may report LZB_E_CAPACITY: rerun those, larger
+    while !pending.is_empty() {
+        let m = pending.len();
+        let mut sub_in = Vec::with_capacity(m + 1);
+        let mut sub_blob = Vec::new();
+        let whole = m == n;
+        if !whole {
+            sub_in.push(0u64);
+            for &i in &pending {
+                sub_blob.extend_from_slice(inputs[i]);
+                sub_in.push(sub_blob.len() as u64);
+            }
+            sub_blob.extend_from_slice(&[0u8; 16]);
+        }
+        let (src, src_off): (&[u8], &[u64]) = if whole { (&blob, &in_off) } else { (&sub_blob, &sub_in) };
+        let mut out_off = vec![0u64; m + 1];
+        for (k, &i) in pending.iter().enumerate() {
+            out_off[k + 1] = out_off[k] + ((cap[i] + 15) & !15);
+        }
+        let mut out = vec![0u8; out_off[m] as usize + 16];
+        let (mut out_len, mut consumed, mut st) = (vec![0u64; m], vec![0u64; m], vec![LzbStatus::default(); m]);
+        let rc = with_engine(|e| unsafe {
+            if e.multi.is_null() {
+                lzb_decode_batch(e.one, fmt, opt, src.as_ptr(), src_off.as_ptr(), m as u32, out.as_mut_ptr(), out_off.as_ptr(),
+                                 out_len.as_mut_ptr(), consumed.as_mut_ptr(), st.as_mut_ptr())
+            } else {
+                lzb_decode_batch_multi(e.multi, fmt, opt, src.as_ptr(), src_off.as_ptr(), m as u32, out.as_mut_ptr(),
+                                       out_off.as_ptr(), out_len.as_mut_ptr(), consumed.as_mut_ptr(), st.as_mut_ptr(),
+                                       std::ptr::null_mut())
+            }
+        });
+        match rc {
+            Ok(0) => {}
+            Ok(rc) => return fail(format!("lzb_decode_batch failed: {}", rc)),
+            Err(e) => return fail(e.to_string()),
+        }
+        let mut again = Vec::new();
+        for (k, &i) in pending.iter().enumerate() {
+            if st[k].code == -1 && cap[i] < 0xFFFF_F000 {
+                cap[i] = (cap[i] * 2).max(st[k].a0 + 65536).min(0xFFFF_F000);
+                again.push(i);
+                continue;
+            }
+            results[i] = Some(if st[k].code == 0 {
+                Ok(out[out_off[k] as usize..(out_off[k] + out_len[k]) as usize].to_vec())
+            } else {
+                Err(to_error(&st[k]))
+            });
+        }
+        pending = again;
+    }
+    results.into_iter().map(|r| r.unwrap()).collect()
+}
+/// `lzma_decompress` over a batch of independent `.lzma` streams.
+pub fn lzma_decompress_batch(inputs: &[&[u8]]) -> Vec<error::Result<Vec<u8>>> {
+    decode_many(FMT_LZMA, &LzbOptions::default(), inputs)
+}
+/// `lzma_decompress_with_options` over a batch.
+pub fn lzma_decompress_batch_with_options(inputs: &[&[u8]], opts: &decompress::Options) -> Vec<error::Result<Vec<u8>>> {
+    decode_many(FMT_LZMA, &options(opts), inputs)
+}
+/// `lzma2_decompress` over a batch of independent raw LZMA2 streams (the benchmarked call).
+pub fn lzma2_decompress_batch(inputs: &[&[u8]]) -> Vec<error::Result<Vec<u8>>> {
+    decode_many(FMT_LZMA2, &LzbOptions::default(), inputs)
+}
+/// `xz_decompress` over a batch of `.xz` files.
+pub fn xz_decompress_batch(inputs: &[&[u8]]) -> Vec<error::Result<Vec<u8>>> {
+    decode_many(FMT_XZ, &LzbOptions::default(), inputs)
 }
 
 fn options(o: &decompress::Options) -> LzbOptions {

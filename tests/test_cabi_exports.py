@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = _native.load()
     for name in _declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.lzb_abi_version() == 1
+    assert lib.lzb_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -1,0 +1,243 @@
+"""GPU tier, C ABI v2: device-side sizing/layout, the peer decode (scatter + decode + gather in one
+launch; exercised here on one GPU with same-device and pinned-host "remote" blobs), the one-process multi-device entry
+point (two contexts on the same GPU), and the second-pass redo of the device path.  All against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import corpus
+import oracle_py as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lzma_rs_b200 import Context
+    c = Context()
+    yield c
+    c.close()
+
+
+def _mixed_batch(n, seed, lo=2_000, hi=150_000):
+    rng = np.random.default_rng(seed)
+    base_plain = [corpus.mixed_text(seed * 1000 + i, int(rng.integers(lo, hi))) for i in range(min(n, 64))]
+    base = [corpus.raw_lzma2(p, dict_size=1 << 20) for p in base_plain]
+    return [base[i % len(base)] for i in range(n)], [base_plain[i % len(base)] for i in range(n)]
+
+
+def underconsumed_lclp4_stream():
+    """An LZMA2 stream whose first chunk declares more packed bytes than the range decoder needs; the reference does not
+    skip them (lzma2.rs:189-192) but parses them as the next chunk -- here a chunk with lc = 4, which the framing scan
+    (skipping `packed` bytes) never sees."""
+    e1 = corpus.LzmaEncoder(3, 0, 2)
+    for b in b"first chunk, lc = 3":
+        e1.literal(b)
+    n1 = len(e1.hist)
+    e2 = corpus.LzmaEncoder(4, 0, 2)
+    for b in b"hidden chunk with lc = 4 behind the range coder's last byte":
+        e2.literal(b)
+    e2.match(9, 5)
+    n2 = len(e2.hist)
+    hidden = corpus.lzma2_chunk(e2.finish(), n2, 0xE0, corpus.props_byte(4, 0, 2))
+    return corpus.lzma2_chunk(e1.finish() + hidden + b"\0", n1, 0xE0, corpus.props_byte(3, 0, 2)) + b"\0"
+
+
+def test_scan_device_sizes_and_layout(ctx):
+    """A device-resident batch is sized, laid out and decoded without its sizes ever visiting the host (only the total,
+    to allocate the output blob): lzb_scan_device -> lzb_batch_prepare_device -> launch -> collect."""
+    import torch
+    from lzma_rs_b200 import _native
+    lib = _native.load()
+    streams, plains = _mixed_batch(300, 21)
+    streams += [b"", b"\x00", streams[0][:50], corpus.stored_lzma2(b"stored bytes " * 999)]
+    plains += [None] * 3 + [b"stored bytes " * 999]
+    n = len(streams)
+    blob, in_off = _native.pack_streams(streams)
+    d_in = torch.from_numpy(blob).cuda()
+    d_in_off = torch.from_numpy(in_off.astype(np.int64)).cuda()
+    d_cap = torch.zeros(n, dtype=torch.int64, device="cuda")
+    d_out_off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    total = C.c_uint64(0)
+    opt = _native.make_options()
+    rc = lib.lzb_scan_device(ctx.handle, 1, C.byref(opt), d_in.data_ptr(), d_in_off.data_ptr(), n, d_cap.data_ptr(),
+                             d_out_off.data_ptr(), C.byref(total), None)
+    assert rc == 0, ctx.last_error()
+    # same capacities as the host-side lzb_scan, and the layout is their 16-byte aligned exclusive prefix sum
+    host_cap = np.zeros(n, dtype=np.uint64)
+    assert lib.lzb_scan(ctx.handle, 1, C.byref(opt), blob.ctypes.data, in_off.ctypes.data, n, host_cap.ctypes.data) == 0
+    cap = d_cap.cpu().numpy().astype(np.uint64)
+    assert (cap == host_cap).all()
+    off = d_out_off.cpu().numpy().astype(np.uint64)
+    want_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum((cap + np.uint64(15)) // np.uint64(16) * np.uint64(16), out=want_off[1:])
+    assert (off == want_off).all() and total.value == int(want_off[-1])
+    d_out = torch.zeros(total.value + 16, dtype=torch.uint8, device="cuda")
+    batch = C.c_void_p()
+    rc = lib.lzb_batch_prepare_device(ctx.handle, 1, C.byref(opt), d_in.data_ptr(), d_in_off.data_ptr(), n, d_out.data_ptr(),
+                                      d_out_off.data_ptr(), C.byref(batch))
+    assert rc == 0, ctx.last_error()
+    assert lib.lzb_batch_launch(batch, None) == 0
+    out_len, cons = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+    st = np.zeros(n, dtype=_native.STATUS_DTYPE)
+    assert lib.lzb_batch_collect(batch, None, out_len.ctypes.data, cons.ctypes.data, st.ctypes.data) == 0
+    lib.lzb_batch_destroy(batch)
+    host = d_out.cpu().numpy()
+    for i in range(n):
+        ref = oracle.lzma2_decompress(streams[i])
+        got = host[int(off[i]):int(off[i]) + int(out_len[i])].tobytes()
+        assert got == ref.out, i
+        disp = "" if st[i]["code"] == 0 else _native.format_status(lib, st[i])
+        assert disp == ref.display, (i, disp, ref.display)
+        if plains[i] is not None:
+            assert got == plains[i]
+    # .lzma headers on the device: known size, end-marker (heuristic capacity), header errors
+    lz = [corpus.lzma_alone_known_size(plains[0]), corpus.lzma_alone(plains[1]), b"\x5d\x00", bytes([225]) + b"\0" * 12]
+    blob, in_off = _native.pack_streams(lz)
+    d_in = torch.from_numpy(blob).cuda()
+    d_in_off = torch.from_numpy(in_off.astype(np.int64)).cuda()
+    d_cap = torch.zeros(len(lz), dtype=torch.int64, device="cuda")
+    rc = lib.lzb_scan_device(ctx.handle, 0, C.byref(opt), d_in.data_ptr(), d_in_off.data_ptr(), len(lz), d_cap.data_ptr(),
+                             None, None, None)
+    assert rc == 0
+    host_cap = np.zeros(len(lz), dtype=np.uint64)
+    assert lib.lzb_scan(ctx.handle, 0, C.byref(opt), blob.ctypes.data, in_off.ctypes.data, len(lz), host_cap.ctypes.data) == 0
+    torch.cuda.synchronize()
+    assert (d_cap.cpu().numpy().astype(np.uint64) == host_cap).all()
+
+
+@pytest.mark.parametrize("where", ["device", "pinned_host"])
+def test_peer_decode_one_launch(ctx, where):
+    """lzb_decode_batch_peer: compressed bytes pulled from a blob that is NOT the context's staging memory (another
+    device allocation / pinned host memory) behind the input gate, output pages stored to the destination blob by K1.
+    A stream range that starts in the middle of both blobs, error streams mixed in, > 16 MiB so that the gate is armed."""
+    import torch
+    from lzma_rs_b200 import _native
+    lib = _native.load()
+    streams, plains = _mixed_batch(700, 33, 20_000, 120_000)
+    streams[5] = streams[5][:len(streams[5]) // 2]
+    streams[333] = b"\x55" + streams[333][1:]
+    streams[400] = underconsumed_lclp4_stream()
+    n = len(streams)
+    assert sum(len(s) for s in streams) > 20 << 20
+    refs = [oracle.lzma2_decompress(s) for s in streams]
+    blob, in_off = _native.pack_streams(streams)
+    caps = np.array([max(len(p), len(r.out)) for p, r in zip(plains, refs)], dtype=np.uint64)
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum((caps + np.uint64(15)) // np.uint64(16) * np.uint64(16), out=out_off[1:])
+    if where == "device":
+        src = torch.from_numpy(blob).cuda()
+        dst = torch.full((int(out_off[-1]) + 16,), 0xEE, dtype=torch.uint8, device="cuda")
+    else:
+        src = torch.from_numpy(blob).pin_memory()
+        dst = torch.full((int(out_off[-1]) + 16,), 0xEE, dtype=torch.uint8).pin_memory()
+    opt = _native.make_options()
+    lo, hi = 37, n - 11  # a rank's range: offsets are relative to the WHOLE blobs
+    m = hi - lo
+    out_len, cons = np.zeros(m, dtype=np.uint64), np.zeros(m, dtype=np.uint64)
+    st = np.zeros(m, dtype=_native.STATUS_DTYPE)
+    sub_in, sub_out = np.ascontiguousarray(in_off[lo:hi + 1]), np.ascontiguousarray(out_off[lo:hi + 1])
+    rc = lib.lzb_decode_batch_peer(ctx.handle, 1, C.byref(opt), src.data_ptr(), sub_in.ctypes.data, m, dst.data_ptr(),
+                                   sub_out.ctypes.data, out_len.ctypes.data, cons.ctypes.data, st.ctypes.data)
+    assert rc == 0, ctx.last_error()
+    torch.cuda.synchronize()
+    host = dst.cpu().numpy()
+    assert (host[:int(out_off[lo])] == 0xEE).all() and (host[int(out_off[hi]):] == 0xEE).all(), "wrote outside its range"
+    for k in range(m):
+        i = lo + k
+        got = host[int(out_off[i]):int(out_off[i]) + int(out_len[k])].tobytes()
+        disp = "" if st[k]["code"] == 0 else _native.format_status(lib, st[k])
+        assert disp == refs[i].display, (i, disp, refs[i].display)
+        assert got == refs[i].out, i
+        if refs[i].ok:
+            assert int(cons[k]) == refs[i].consumed
+
+
+def test_multi_device_entry_point(ctx):
+    """lzb_create_multi / lzb_decode_batch_multi: the host batch is split into contiguous stream ranges with equal
+    compressed bytes, one thread and one context per listed device (here the same GPU twice and three times)."""
+    import torch
+    from lzma_rs_b200 import _native
+    lib = _native.load()
+    streams, plains = _mixed_batch(500, 44, 5_000, 90_000)
+    streams[77] = streams[77][:100]
+    n = len(streams)
+    refs = [oracle.lzma2_decompress(s) for s in streams]
+    blob, in_off = _native.pack_streams(streams)
+    caps = np.array([len(p) for p in plains], dtype=np.uint64)
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum((caps + np.uint64(15)) // np.uint64(16) * np.uint64(16), out=out_off[1:])
+    h_in = torch.from_numpy(blob).pin_memory()
+    opt = _native.make_options()
+    for devs in ([0, 0], [0, 0, 0], None):
+        m = C.c_void_p()
+        if devs is None:
+            rc = lib.lzb_create_multi(C.byref(m), None, 0)
+        else:
+            arr = (C.c_int * len(devs))(*devs)
+            rc = lib.lzb_create_multi(C.byref(m), arr, len(devs))
+        assert rc == 0
+        nd = lib.lzb_multi_device_count(m)
+        assert nd == (len(devs) if devs else torch.cuda.device_count())
+        h_out = torch.full((int(out_off[-1]) + 16,), 0xEE, dtype=torch.uint8).pin_memory()
+        out_len, cons = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        st = np.zeros(n, dtype=_native.STATUS_DTYPE)
+        split = np.zeros(nd + 1, dtype=np.uint32)
+        rc = lib.lzb_decode_batch_multi(m, 1, C.byref(opt), h_in.data_ptr(), in_off.ctypes.data, n, h_out.data_ptr(),
+                                        out_off.ctypes.data, out_len.ctypes.data, cons.ctypes.data, st.ctypes.data,
+                                        split.ctypes.data)
+        assert rc == 0, lib.lzb_multi_last_error(m)
+        assert split[0] == 0 and split[-1] == n and (np.diff(split.astype(np.int64)) >= 0).all()
+        if nd > 1:  # equal shares of the compressed bytes, to within one stream
+            share = np.diff(in_off[split.astype(np.int64)].astype(np.int64))
+            assert share.max() - share.min() <= 2 * max(len(s) for s in streams)
+        hv = h_out.numpy()
+        for i in range(n):
+            got = hv[int(out_off[i]):int(out_off[i]) + int(out_len[i])].tobytes()
+            disp = "" if st[i]["code"] == 0 else _native.format_status(lib, st[i])
+            assert disp == refs[i].display and got == refs[i].out, i
+        lib.lzb_destroy_multi(m)
+
+
+def test_device_path_second_pass(ctx):
+    """a stream whose later chunk (hidden from the framing scan behind an under-consumed chunk) needs larger
+    lc+lp than the scan saw is decoded like the reference on the DEVICE entry points too (second pass at lc+lp = 4)."""
+    import gpu_util
+    s = underconsumed_lclp4_stream()
+    ref = oracle.lzma2_decompress(s)
+    assert ref.ok and b"hidden chunk" in ref.out
+    filler, fp = _mixed_batch(40, 55)
+    streams = filler[:20] + [s] + filler[20:]
+    caps = [len(p) for p in fp[:20]] + [len(ref.out)] + [len(p) for p in fp[20:]]
+    b = gpu_util.DeviceBatch(ctx, 1, streams, caps).decode()
+    assert b.st[20]["code"] == 0, b.display(20)
+    assert b.output(20) == ref.out and int(b.consumed[20]) == ref.consumed
+    for i in (0, 19, 21, 40):
+        assert b.st[i]["code"] == 0 and b.output(i) == (fp[:20] + [ref.out] + fp[20:])[i]
+    r = gpu_util.host_decode(ctx, 1, [s], {})[0]
+    assert r.ok and r.data == ref.out
+
+
+def test_cpp_multi_client(ctx, tmp_path):
+    """tests/cpp/multi_check.cpp: a compiled C++ client of lzb_create_multi / lzb_decode_batch_multi (pageable buffers)."""
+    import os
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "multi_check"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "multi_check.cpp"), "-L" + os.path.join(root, "lzma_rs_b200"),
+                           "-llzma_b200", "-Wl,-rpath," + os.path.join(root, "lzma_rs_b200"), "-o", str(exe)])
+    plain = corpus.mixed_text(4242, 180_000)
+    (tmp_path / "s.lzma2").write_bytes(corpus.raw_lzma2(plain, dict_size=1 << 20))
+    (tmp_path / "s.plain").write_bytes(plain)
+    for devs in ["0,0", "all", "0,0,0,0"]:
+        r = subprocess.run([str(exe), devs, str(tmp_path / "s.lzma2"), str(tmp_path / "s.plain"), "301"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, (devs, r.stdout, r.stderr)
+        nd = {"0,0": 2, "0,0,0,0": 4}.get(devs, torch.cuda.device_count())
+        assert r.stdout.startswith(f"devices {nd} split 0 "), r.stdout
