@@ -112,10 +112,11 @@ LZB_DEV uint32_t rc_step(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np) {
         "setp.ge.u32 p, %3, bound;\n\t"
         "sub.u32 rb, %2, bound;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
-        "selp.u32 kk, 31, 2048, p;\n\t"
         "selp.u32 %2, rb, bound, p;\n\t"
         "@p sub.u32 %3, %3, bound;\n\t"
-        "mad.lo.u32 %1, %4, %5, kk;\n\t}"
+        "mad.lo.u32 kk, %4, %5, 2048;\n\t"      // 2048 - p ...
+        "@p add.u32 kk, kk, -2017;\n\t"         // ... or 31 - p: no register spent on the constant 31
+        "mov.u32 %1, kk;\n\t}"
         : "=r"(bit), "=r"(t), "+r"(d.range), "+r"(d.code)
         : "r"(pv), "r"(kc.m1));
 #else
@@ -146,11 +147,12 @@ LZB_DEV uint32_t rc_step_tree(Dec& d, const LzbKC& kc, uint32_t pv, uint32_t& np
         "setp.ge.u32 p, %3, bound;\n\t"
         "sub.u32 rb, %2, bound;\n\t"
         "selp.u32 xx, %7, %6, p;\n\t"
-        "selp.u32 kk, 31, 2048, p;\n\t"
         "selp.u32 %2, rb, bound, p;\n\t"
         "@p sub.u32 %3, %3, bound;\n\t"
         "mad.lo.u32 %0, %5, %8, xx;\n\t"
-        "mad.lo.u32 %1, %4, %9, kk;\n\t}"
+        "mad.lo.u32 kk, %4, %9, 2048;\n\t"
+        "@p add.u32 kk, kk, -2017;\n\t"
+        "mov.u32 %1, kk;\n\t}"
         : "=r"(child), "=r"(t), "+r"(d.range), "+r"(d.code)
         : "r"(pv), "r"(node), "r"(x0), "r"(x1), "r"(kc.two), "r"(kc.m1));
 #else
@@ -184,6 +186,10 @@ struct TabPtr {
         TabPtr t = {b + off};
         return t;
     }
+    LZB_MEM TabPtr at_bytes(uint32_t boff) const {
+        TabPtr t = {b + (boff >> 1)};
+        return t;
+    }
 };
 #ifdef __CUDACC__
 struct TabSm {
@@ -211,6 +217,10 @@ struct TabSm {
     LZB_MEM uint32_t node_index(const LzbKC&, uint32_t node) const { return (node - a) >> 1; }
     LZB_MEM TabSm at(const LzbKC& kc, uint32_t off) const {
         TabSm t = {off * kc.two + a};
+        return t;
+    }
+    LZB_MEM TabSm at_bytes(uint32_t boff) const {
+        TabSm t = {boff + a};
         return t;
     }
 };
@@ -380,6 +390,38 @@ LZB_DEV void fill_tables(uint16_t* T, uint32_t n_u16, int lane) {
     } while (0)
 #endif
 
+// End of a literal (lzma.rs:299-307): limit checks, the byte, the state transition; STATE_EXPR = the new state.
+#if LZB_R2_CHECKS
+#define LZB_LIT_CHECKS                                                              \
+    if (LZB_UNLIKELY((d.p > d.lim) | (opos >= lit_limit))) {                        \
+        if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);                                  \
+        if (opos >= mem_stop) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);               \
+        FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);                                \
+    }
+#else
+#define LZB_LIT_CHECKS                                                              \
+    if (LZB_UNLIKELY(d.p > d.lim)) FAIL(LZB_E_IO_EOF, 0, 0);                        \
+    if (LZB_UNLIKELY(opos >= lit_limit)) {                                          \
+        if (LZB_UNLIKELY(opos >= mem_stop)) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0); \
+        FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);                                \
+    }
+#endif
+#if LZB_R2_STATE
+#define LZB_LIT_STATE(STATE_EXPR) state = (STATE_EXPR);
+#else  // 0,0,0,0,1,2,3,4,5,6,4,5 as packed nibbles
+#define LZB_LIT_STATE(STATE_EXPR) state = (uint32_t)(0x546543210000ull >> (state * 4)) & 0xFu;
+#endif
+#define LZB_LIT_TAIL(STATE_EXPR)                        \
+    {                                                   \
+        LZB_LIT_CHECKS                                  \
+        prev_byte = sym & 0xFFu;                        \
+        if (lane == 0) out[opos] = (uint8_t)prev_byte;  \
+        opos += 1;                                      \
+        LZB_LIT_STATE(STATE_EXPR)                       \
+        mb_valid = false;                               \
+        continue;                                       \
+    }
+
 // Warp copy of n bytes src -> dst (arbitrary, independent alignments; regions do not overlap): a few head bytes
 // bring dst to a 4-byte boundary, the body stores aligned 32-bit words assembled from two aligned source words with
 // a funnel shift (128 B per warp instruction instead of 32), the tail goes byte-wise.  SRC_CONST: the source is the
@@ -497,8 +539,19 @@ LZB_DEV void mirror_to_host(const uint8_t* out, uint8_t* hout, uint32_t from, ui
 template <bool LIT_GLOBAL, bool MIRROR, int WIDE, class MainTab, class PlainTab, class MatchedTab>
 LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t* __restrict__ in_blob,
                                   uint8_t* out_blob, uint16_t* T, uint16_t* gws, const MainTab tab,
-                                  const PlainTab plain, const MatchedTab matched, const LzbKC kc, uint32_t tab_lclp,
+                                  const PlainTab plain, const MatchedTab matched, const LzbKC kc_in, uint32_t tab_lclp,
                                   LzbResult* res, int lane) {
+#if defined(__CUDACC__) && defined(LZB_R2_PINKC)
+    // (experiment) multipliers pinned in registers instead of re-read from the constant bank at every use site
+    LzbKC kcp = kc_in;
+    kcp.two = kc_in.two + (tab_lclp >> 30);  // + 0, opaque to ptxas: a plain parameter load would be rematerialised
+    kcp.m1 = kc_in.m1 - (tab_lclp >> 30);
+    LZB_KEEP(kcp.two);
+    LZB_KEEP(kcp.m1);
+    const LzbKC& kc = kcp;
+#else
+    const LzbKC& kc = kc_in;
+#endif
     Dec d;
     const bool is_lzma1 = itp->kind == LZB_ITEM_LZMA;
     const uint32_t p0 = (uint32_t)(itp->in_off & 3ull);
@@ -651,6 +704,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 #if LZB_R2_STATE
         uint32_t row_mask = (1u << (lc + lp)) - 1;
         LZB_KEEP(row_mask);
+        uint32_t plain_row_bytes = plain_stride * 2u;  // pinned: row address = one multiply-add
+        LZB_KEEP(plain_row_bytes);
 #endif
         LZB_KEEP(pb_mask);
         LZB_KEEP(lp_mask);
@@ -675,15 +730,28 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
             // register, so the root of the plain literal tree is fetched while is_match is being decoded.
 #if LZB_R2_STATE
             // ((len & lp_mask) << lc) + (prev_byte >> (8 - lc)) as one shift of len:prev_byte
+#ifdef __CUDACC__
+            const uint32_t lit_row = (__byte_perm(prev_byte, len, 0x6540) >> lit_shift) & row_mask;  // len : prev_byte
+#else
             const uint32_t lit_row = (((len << 8) | prev_byte) >> lit_shift) & row_mask;
+#endif
 #else
             const uint32_t lit_row = ((len & lp_mask) << lc) + (prev_byte >> lit_shift);
 #endif
+#if LZB_R2_STATE
+            const PlainTab probs = plain.at_bytes(lit_row * plain_row_bytes);
+#else
             const PlainTab probs = plain.at(kc, lit_row * plain_stride);
+#endif
             const uint32_t i_is_match = T_IS_MATCH + (state << 4) + pos_state;
             const uint32_t p_is_match = tab.ld16(kc, i_is_match);
+#if LZB_R2_STATE
+            // (unconditional: after a match the value is simply not used -- cheaper than the predicate and the zero)
+            const uint32_t lit_pv = probs.ldn(kc, probs.root(kc));
+#else
             uint32_t lit_pv = 0;
             if (state < 7) lit_pv = probs.ldn(kc, probs.root(kc));
+#endif
             uint32_t np_im;
             const uint32_t is_lz = rc_step(d, kc, p_is_match, np_im);
             tab.st16(kc, i_is_match, np_im);
@@ -728,31 +796,11 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                         rc_normalize(d);
                     }
                     sym = probs.node_index(kc, node);
-                }
-#if LZB_R2_CHECKS
-                if (LZB_UNLIKELY((d.p > d.lim) | (opos >= lit_limit))) {
-                    if (d.p > d.lim) FAIL(LZB_E_IO_EOF, 0, 0);
-                    if (opos >= mem_stop) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
-                    FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);
-                }
-#else
-                if (LZB_UNLIKELY(d.p > d.lim)) FAIL(LZB_E_IO_EOF, 0, 0);
-                if (LZB_UNLIKELY(opos >= lit_limit)) {
-                    if (LZB_UNLIKELY(opos >= mem_stop)) FAIL(LZB_E_MEMLIMIT, itp->memlimit, 0);
-                    FAIL(LZB_E_CAPACITY, (uint64_t)opos + 1, 0);
-                }
-#endif
-                prev_byte = sym & 0xFFu;
-                if (lane == 0) out[opos] = (uint8_t)prev_byte;
-                opos += 1;
-                // state after a literal (lzma.rs:299-305): 0,0,0,0,1,2,3,4,5,6,4,5
 #if LZB_R2_STATE
-                state = state < 10 ? (state > 3 ? state - 3 : 0u) : state - 6;
-#else
-                state = (uint32_t)(0x546543210000ull >> (state * 4)) & 0xFu;
+                    LZB_LIT_TAIL(state > 3 ? state - 3 : 0u)  // 0..3 -> 0; 4,5,6 -> 1,2,3  (own copy: no join with the matched path)
 #endif
-                mb_valid = false;
-                continue;
+                }
+                LZB_LIT_TAIL(state < 10 ? state - 3 : state - 6)  // 7,8,9 -> 4,5,6; 10,11 -> 4,5
             }
 
             // ---- LZ, lzma.rs:309-390

@@ -29,17 +29,17 @@ struct LzbCrcRange {
                                     LzbResult*, unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long, \
                                     const LzbKC, const unsigned long long*)
 LZB_K1_PROTO(lzb_decode_kernel);
-LZB_K1_PROTO(lzb_decode_mirror_kernel);
 LZB_K1_PROTO(lzb_decode_fill_kernel);
-LZB_K1_PROTO(lzb_decode_fill_mirror_kernel);
 LZB_K1_PROTO(lzb_decode_copy_kernel);
-LZB_K1_PROTO(lzb_decode_copy_mirror_kernel);
 LZB_K1_PROTO(lzb_decode_sched_kernel);
-LZB_K1_PROTO(lzb_decode_sched_mirror_kernel);
 LZB_K1_PROTO(lzb_decode_sched_fill_kernel);
-LZB_K1_PROTO(lzb_decode_sched_fill_mirror_kernel);
 LZB_K1_PROTO(lzb_decode_sched_copy_kernel);
-LZB_K1_PROTO(lzb_decode_sched_copy_mirror_kernel);
+LZB_K1_PROTO(lzb_decode_drain_kernel);
+LZB_K1_PROTO(lzb_decode_drain_fill_kernel);
+LZB_K1_PROTO(lzb_decode_drain_copy_kernel);
+LZB_K1_PROTO(lzb_decode_mirror_kernel);
+LZB_K1_PROTO(lzb_decode_mirror_fill_kernel);
+LZB_K1_PROTO(lzb_decode_mirror_copy_kernel);
 LZB_K1_PROTO(lzb_decode_biglit_kernel);
 extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, const uint64_t*, const uint64_t*, uint32_t,
                                            LzbItem*, LzbScan*, uint64_t, uint64_t*);
@@ -90,7 +90,13 @@ struct lzb_ctx {
     // on `stream`; after each chunk the offset reached is copied from h_marks to d_gate[0] (see input_arrived())
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t gate_ready = nullptr;
-    unsigned long long* h_marks = nullptr;  // pinned: [0..2] initial gate words, [8..] one watermark per chunk
+    unsigned long long* h_marks = nullptr;  // pinned: [0..3] initial gate words, [8..] one watermark per chunk
+    // drain mode of the host API (multi-round batches): K1 publishes one "done" word per stream into h_done (pinned), the
+    // host polls them and the copy engine moves finished streams to the caller's buffer on drain_stream
+    cudaStream_t drain_stream = nullptr;
+    cudaEvent_t kernels_done = nullptr;
+    unsigned int* h_done = nullptr;
+    size_t h_done_cap = 0;
     // lzb_decode_batch_device keeps ONE batch object alive between calls: its device buffers are reused instead of
     // paying six cudaMalloc / cudaFree (each a device synchronisation) per call
     struct lzb_batch* oneshot = nullptr;
@@ -133,17 +139,19 @@ struct LaunchCfg {
     uint32_t lclp, warp_bytes, warps, grid;
 };
 
-// K1 variants: [sched][mirror][lean | fill | copy] (+ the lc+lp > 4 kernel).  Their dynamic shared-memory limit is raised
+// K1 variants: [plain | sched | drain | mirror][lean | fill | copy] (+ the lc+lp > 4 kernel); drain and mirror are the
+// host-I/O forms (input gate; done words / page stores) and always take a static prefix like sched.  Their dynamic
+// shared-memory limit is raised
 // once per device in lzb_create, so launches never touch function attributes (several threads may launch prepared
 // batches of one context at the same time).
 typedef void (*k1_t)(const LzbItem*, const uint32_t*, uint32_t, uint32_t, const uint8_t*, uint8_t*, LzbResult*,
                      unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long, const LzbKC,
                      const unsigned long long*);
 const k1_t k1_variants[13] = {
-    lzb_decode_kernel,              lzb_decode_fill_kernel,              lzb_decode_copy_kernel,
-    lzb_decode_mirror_kernel,       lzb_decode_fill_mirror_kernel,       lzb_decode_copy_mirror_kernel,
-    lzb_decode_sched_kernel,        lzb_decode_sched_fill_kernel,        lzb_decode_sched_copy_kernel,
-    lzb_decode_sched_mirror_kernel, lzb_decode_sched_fill_mirror_kernel, lzb_decode_sched_copy_mirror_kernel,
+    lzb_decode_kernel,        lzb_decode_fill_kernel,        lzb_decode_copy_kernel,
+    lzb_decode_sched_kernel,  lzb_decode_sched_fill_kernel,  lzb_decode_sched_copy_kernel,
+    lzb_decode_drain_kernel,  lzb_decode_drain_fill_kernel,  lzb_decode_drain_copy_kernel,
+    lzb_decode_mirror_kernel, lzb_decode_mirror_fill_kernel, lzb_decode_mirror_copy_kernel,
     lzb_decode_biglit_kernel};
 
 LaunchCfg decode_config(const lzb_ctx* ctx, uint32_t n, uint32_t lclp) {
@@ -174,10 +182,12 @@ struct DecodePlan {
     uint32_t parked = 0;          // warps the placement keeps out of the launch
     uint64_t big_stride_u16 = 0;  // workspace u16 per warp
     int wide = 0;                 // K1 variant: 0 lean, 1 word-wide run fills, 2 vector stored-chunk copies
+    bool host_io = false;         // launch with the host-I/O kernels (input gate; done words or page stores)
 };
 
 void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lzma2_lclp_hint, uint64_t stored_bytes,
-               DecodePlan* p, bool route_stored = true) {
+               DecodePlan* p, bool route_stored = true, bool host_io = false) {
+    p->host_io = host_io;
     uint32_t lclp_small = 0, lclp_big = 0;
     // stored-chunk-only streams whose output fits go to the copy kernel (not with a host mirror: that kernel does not
     // stream pages to the host); everything below plans K1 for the rest
@@ -233,6 +243,18 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
             p->cfg_small.grid = sp.grid;
         }
     }
+    if (host_io && !p->n_static && p->n_small) {
+        // the host-I/O kernels exist in the static-prefix form only (lzb_kernels.cu): without a placement plan, hand the
+        // head of the queue out round-robin over the CTAs, which is what the dynamic queue does in effect
+        const uint32_t grid = p->cfg_small.grid, warps = p->cfg_small.warps, ns = grid * warps;
+        std::vector<uint32_t> order(ns, LZB_ORDER_PARK);
+        for (uint32_t c = 0; c < grid; c++)
+            for (uint32_t w = 0; w < warps; w++)
+                if ((uint64_t)w * grid + c < p->n_small) order[c * warps + w] = p->order_small[w * grid + c];
+        if (p->n_small > ns) order.insert(order.end(), p->order_small.begin() + ns, p->order_small.end());
+        p->order_small.swap(order);
+        p->n_static = ns;
+    }
     if (!p->order_big.empty()) {
         LaunchCfg& c = p->cfg_big;
         c.lclp = lclp_big;
@@ -276,14 +298,12 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         // per-warp global workspace for the matched-literal columns (L2-resident: 8 KiB per warp at lc+lp = 3)
         const uint64_t mstride = lzb_matched_u16(c.lclp);
         CUDA_TRY(ctx, matchws.ensure((size_t)c.grid * c.warps * mstride * 2));
-        // variants: [sched][mirror][lean | fill | copy]; mirror = host API with a pinned output buffer (finished pages
-        // streamed to the host); sched = the launch carries a placement plan (lzb_sched.h)
         const k1_t* kernels = k1_variants;
-        const int v = (p.n_static ? 6 : 0) + (mirror ? 3 : 0) + p.wide;
+        const int v = (p.host_io ? (mirror ? 9 : 6) : p.n_static ? 3 : 0) + p.wide;
         if (int rc = fire()) return rc;
         kernels[v]<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, p.n_static, d_in_base, d_out_base, d_results,
                                                       d_counter, c.lclp, c.warp_bytes, matchws.as<uint16_t>(), mstride, kc,
-                                                      mirror ? d_gate : nullptr);
+                                                      d_gate);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     if (nb) {
@@ -293,8 +313,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         if (int rc = fire()) return rc;
         lzb_decode_biglit_kernel<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order + ns, nb, 0u, d_in_base, d_out_base,
                                                                     d_results, d_counter + 1, c.lclp, c.warp_bytes,
-                                                                    litws.as<uint16_t>(), p.big_stride_u16, kc,
-                                                                    mirror ? d_gate : nullptr);
+                                                                    litws.as<uint16_t>(), p.big_stride_u16, kc, d_gate);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     if (nst) {
@@ -312,6 +331,100 @@ int upload_order(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, DevBuf& d_or
         CUDA_TRY(ctx, cudaMemcpyAsync(d_order.as<uint32_t>() + ns + nb, p.order_stored.data(), nst * 4, cudaMemcpyHostToDevice, s));
     if (ns) CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, p.order_small.data(), ns * 4, cudaMemcpyHostToDevice, s));
     if (nb) CUDA_TRY(ctx, cudaMemcpyAsync(d_order.as<uint32_t>() + ns, p.order_big.data(), nb * 4, cudaMemcpyHostToDevice, s));
+    return LZB_RC_OK;
+}
+
+// Arms K1's input gate for a blob of `in_bytes` bytes at `src` (pinned host memory, or a peer GPU's memory) that goes to
+// ctx->d_in + lead: the gate words are uploaded on ctx->stream, and `*upload` becomes the closure that enqueues the
+// chunked copy (+ one watermark update per chunk) on ctx->copy_stream.  The closure is run by launch_plan right before
+// the first K1 launch is enqueued.
+int arm_gate(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_lo, uint64_t in_bytes,
+             std::function<int()>* upload, const unsigned long long** d_gate) {
+    uint64_t chunk = LZB_GATE_CHUNK;
+    while ((lead + in_bytes + chunk - 1) / chunk > LZB_GATE_MAX_CHUNKS) chunk *= 2;
+    CUDA_TRY(ctx, ctx->d_gate.ensure(64));
+    unsigned long long* hm = ctx->h_marks;
+    hm[0] = 0;                                      // watermark: device offset reached so far
+    hm[1] = (unsigned long long)(lead - in_lo);     // device offset = blob offset + this (mod 2^64)
+    hm[2] = (unsigned long long)(lead + in_bytes);  // device offset of the end of the blob
+    hm[3] = 0;                                      // no done words (set_done_words)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, hm, 32, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->gate_ready, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gate_ready, 0));
+    *upload = [=]() -> int {
+        uint32_t k = 0;
+        for (uint64_t lo = lead; lo < lead + in_bytes; k++) {  // chunk boundaries at device offsets k * chunk
+            const uint64_t hi = std::min<uint64_t>((lo / chunk + 1) * chunk, lead + in_bytes);
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + lo, src + (lo - lead), hi - lo, cudaMemcpyDefault,
+                                          ctx->copy_stream));
+            hm[8 + k] = hi;
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, &hm[8 + k], 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            lo = hi;
+        }
+        return LZB_RC_OK;
+    };
+    *d_gate = ctx->d_gate.as<unsigned long long>();
+    return LZB_RC_OK;
+}
+
+// Drain mode: n zeroed done words in pinned host memory, their address in gate[3].  *d_gate may still be null (input
+// already on the device): then a gate that is open from the start is set up.
+int set_done_words(lzb_ctx* ctx, uint32_t n, const unsigned long long** d_gate) {
+    if (n > ctx->h_done_cap) {
+        if (ctx->h_done) cudaFreeHost(ctx->h_done);
+        ctx->h_done = nullptr;
+        ctx->h_done_cap = 0;
+        const size_t want = (size_t)n + n / 4 + 1024;
+        CUDA_TRY(ctx, cudaHostAlloc((void**)&ctx->h_done, want * sizeof(unsigned int), cudaHostAllocDefault));
+        ctx->h_done_cap = want;
+    }
+    memset(ctx->h_done, 0, (size_t)n * sizeof(unsigned int));
+    unsigned long long* hm = ctx->h_marks;
+    CUDA_TRY(ctx, ctx->d_gate.ensure(64));
+    if (!*d_gate) {
+        hm[0] = ~0ull;  // everything has arrived
+        hm[1] = hm[2] = 0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, hm, 24, cudaMemcpyHostToDevice, ctx->stream));
+        *d_gate = ctx->d_gate.as<unsigned long long>();
+    }
+    hm[4] = (unsigned long long)(uintptr_t)ctx->h_done;  // UVA: pinned host memory has the same address on the device
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.as<unsigned long long>() + 3, &hm[4], 8, cudaMemcpyHostToDevice, ctx->stream));
+    return LZB_RC_OK;
+}
+
+// Drain mode, host side: while the kernels recorded in ctx->kernels_done run, poll the done words in schedule order and
+// let the copy engine move every finished stream from the device blob to `dst_base` (same offsets; pinned host memory
+// or a peer GPU).  `order` is the launch's queue (may hold LZB_ORDER_PARK); copied[i] is set for every stream moved.
+// Streams complete roughly in queue order, so a sliding window over the queue is enough.  Returns after the kernels
+// have finished and every published stream has been enqueued; the caller handles the rest (kernels without done words)
+// and synchronises ctx->drain_stream.
+int drain_finished(lzb_ctx* ctx, const std::vector<uint32_t>& order, const LzbItem* items, const uint8_t* d_out_base,
+                   uint8_t* dst_base, std::vector<uint8_t>& copied, uint32_t window) {
+    volatile unsigned int* done = ctx->h_done;
+    size_t frontier = 0;
+    auto sweep = [&](size_t hi) -> int {
+        int moved = 0;
+        for (size_t k = frontier; k < hi; k++) {
+            const uint32_t i = order[k];
+            if (i == LZB_ORDER_PARK || copied[i]) continue;
+            const unsigned int f = done[i];
+            if (!f) continue;
+            copied[i] = 1;
+            moved++;
+            if (f > 1 && !(items[i].flags & LZB_ITEM_F_OUT_SCRATCH))
+                CUDA_TRY(ctx, cudaMemcpyAsync(dst_base + items[i].out_off, d_out_base + items[i].out_off, f - 1,
+                                              cudaMemcpyDefault, ctx->drain_stream));
+        }
+        while (frontier < order.size() && (order[frontier] == LZB_ORDER_PARK || copied[order[frontier]])) frontier++;
+        return moved;
+    };
+    for (;;) {
+        const bool finished = cudaEventQuery(ctx->kernels_done) == cudaSuccess;
+        const int moved = sweep(finished ? order.size() : std::min(order.size(), frontier + window));
+        if (moved < 0) return moved;
+        if (finished) break;
+        if (!moved) std::this_thread::sleep_for(std::chrono::microseconds(40));
+    }
     return LZB_RC_OK;
 }
 
@@ -427,13 +540,19 @@ class CudaExecutor : public lzb::Executor {
     int run(const LzbItem* items, uint32_t n, uint32_t lclp_hint, uint64_t stored_bytes, LzbResult* results) {
         lzb_ctx* ctx = ctx_;
         DecodePlan plan;
-        make_plan(ctx, items, n, lclp_hint, stored_bytes, &plan, /*route_stored=*/hmirror_ == nullptr);
+        // Output to a pinned host buffer, two forms.  Up to two rounds of streams: K1's mirror variants store finished
+        // 4 KiB pages to the host buffer themselves (all streams end together, nothing else could overlap the transfer).
+        // More rounds: drain mode -- the plain kernels publish a done word per stream and the copy engine moves finished
+        // streams while later rounds decode (the kernel never stores across PCIe).
+        const bool drain = hmirror_ != nullptr && n > 2u * (uint32_t)ctx->sm_count * LZB_MAX_WARPS && !getenv("LZB_NO_DRAIN");
+        const bool mirror = hmirror_ != nullptr && !drain;
+        make_plan(ctx, items, n, lclp_hint, stored_bytes, &plan, /*route_stored=*/!mirror, /*host_io=*/hmirror_ != nullptr);
         CUDA_TRY(ctx, ctx->d_items.ensure(n * sizeof(LzbItem)));
         CUDA_TRY(ctx, ctx->d_results.ensure(n * sizeof(LzbResult)));
         CUDA_TRY(ctx, ctx->d_counter.ensure(64));
         const LzbItem* up = items;
         std::vector<LzbItem> patched;
-        if (hmirror_) {  // the mirror copies 16-byte vectors: both copies of a stream's region must be 16-byte aligned
+        if (mirror) {  // the mirror copies 16-byte vectors: both copies of a stream's region must be 16-byte aligned
             patched.assign(items, items + n);
             for (auto& it : patched) {
                 if (it.flags & LZB_ITEM_F_OUT_SCRATCH) continue;  // intermediate result of a filter chain
@@ -455,10 +574,21 @@ class CudaExecutor : public lzb::Executor {
             cudaEventCreate(&ev1);
             cudaEventRecord(ev0, s_);
         }
+        const unsigned long long* gate = gate_;
+        if (drain && (rc = set_done_words(ctx, n, &gate)) != LZB_RC_OK) return rc;
         rc = launch_plan(ctx, s_, plan, ctx->d_items.as<LzbItem>(), ctx->d_order.as<uint32_t>(), in_, out_,
-                         ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>(), hmirror_ != nullptr, gate_,
+                         ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>(), mirror, gate,
                          &before_first_kernel);
         if (rc != LZB_RC_OK) return rc;
+        std::vector<uint8_t> copied;
+        if (drain) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->kernels_done, s_));
+            copied.assign(n, 0);
+            std::vector<uint32_t> queue(plan.order_small);
+            queue.insert(queue.end(), plan.order_big.begin(), plan.order_big.end());
+            rc = drain_finished(ctx, queue, items, out_, hmirror_, copied, 4u * (uint32_t)ctx->sm_count * LZB_MAX_WARPS);
+            if (rc != LZB_RC_OK) return rc;
+        }
         if (tr) {
             cudaEventRecord(ev1, s_);
             trace->launched = trace->now();
@@ -466,6 +596,13 @@ class CudaExecutor : public lzb::Executor {
         if (tr) trace->uploaded = trace->now();
         CUDA_TRY(ctx, cudaMemcpyAsync(results, ctx->d_results.p, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s_));
         CUDA_TRY(ctx, cudaStreamSynchronize(s_));
+        if (drain) {  // what carried no done word (streams of the stored-chunk copy kernel), then wait for the copy engine
+            for (uint32_t i = 0; i < n; i++)
+                if (!copied[i] && results[i].out_len && !(items[i].flags & LZB_ITEM_F_OUT_SCRATCH))
+                    CUDA_TRY(ctx, cudaMemcpyAsync(hmirror_ + items[i].out_off, out_ + items[i].out_off, results[i].out_len,
+                                                  cudaMemcpyDefault, ctx->drain_stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->drain_stream));
+        }
         if (tr) {
             trace->synced = trace->now();
             float ms = 0;
@@ -485,38 +622,6 @@ class CudaExecutor : public lzb::Executor {
     bool unmirrored_ = false;
     std::vector<void*> scratch_;
 };
-
-// Arms K1's input gate for a blob of `in_bytes` bytes at `src` (pinned host memory, or a peer GPU's memory) that goes to
-// ctx->d_in + lead: the gate words are uploaded on ctx->stream, and `*upload` becomes the closure that enqueues the
-// chunked copy (+ one watermark update per chunk) on ctx->copy_stream.  The closure is run by launch_plan right before
-// the first K1 launch is enqueued.
-int arm_gate(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_lo, uint64_t in_bytes,
-             std::function<int()>* upload, const unsigned long long** d_gate) {
-    uint64_t chunk = LZB_GATE_CHUNK;
-    while ((lead + in_bytes + chunk - 1) / chunk > LZB_GATE_MAX_CHUNKS) chunk *= 2;
-    CUDA_TRY(ctx, ctx->d_gate.ensure(64));
-    unsigned long long* hm = ctx->h_marks;
-    hm[0] = 0;                                      // watermark: device offset reached so far
-    hm[1] = (unsigned long long)(lead - in_lo);     // device offset = blob offset + this (mod 2^64)
-    hm[2] = (unsigned long long)(lead + in_bytes);  // device offset of the end of the blob
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, hm, 24, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->gate_ready, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gate_ready, 0));
-    *upload = [=]() -> int {
-        uint32_t k = 0;
-        for (uint64_t lo = lead; lo < lead + in_bytes; k++) {  // chunk boundaries at device offsets k * chunk
-            const uint64_t hi = std::min<uint64_t>((lo / chunk + 1) * chunk, lead + in_bytes);
-            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + lo, src + (lo - lead), hi - lo, cudaMemcpyDefault,
-                                          ctx->copy_stream));
-            hm[8 + k] = hi;
-            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, &hm[8 + k], 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-            lo = hi;
-        }
-        return LZB_RC_OK;
-    };
-    *d_gate = ctx->d_gate.as<unsigned long long>();
-    return LZB_RC_OK;
-}
 
 struct CopyJoin {  // no exit path may leave copies in flight into ctx->d_in
     cudaStream_t s;
@@ -546,6 +651,8 @@ extern "C" int lzb_create(lzb_ctx** out, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->drain_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->kernels_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->gate_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaHostAlloc((void**)&ctx->h_marks, (8 + LZB_GATE_MAX_CHUNKS) * sizeof(unsigned long long), cudaHostAllocDefault) !=
             cudaSuccess) {
@@ -568,6 +675,7 @@ extern "C" void lzb_destroy(lzb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->drain_stream) cudaStreamSynchronize(ctx->drain_stream);
     if (ctx->oneshot) {
         lzb_batch_destroy(ctx->oneshot);
         ctx->oneshot = nullptr;
@@ -583,8 +691,11 @@ extern "C" void lzb_destroy(lzb_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->drain_stream) cudaStreamDestroy(ctx->drain_stream);
     if (ctx->gate_ready) cudaEventDestroy(ctx->gate_ready);
+    if (ctx->kernels_done) cudaEventDestroy(ctx->kernels_done);
     if (ctx->h_marks) cudaFreeHost(ctx->h_marks);
+    if (ctx->h_done) cudaFreeHost(ctx->h_done);
     delete ctx;
 }
 
@@ -673,6 +784,7 @@ struct lzb_batch {
     DecodePlan plan;
     uint32_t lclp_hint = 0;
     uint64_t stored_bytes = 0;
+    bool host_io = false;
     DevBuf d_redo_items, d_redo_results, d_redo_order, d_redo_counter;  // second pass of lzb_batch_collect (rare)
 };
 
@@ -682,7 +794,8 @@ struct lzb_batch {
 // (nullptr = d_in; lzb_decode_batch_peer scans the remote copy while d_in is still being filled).
 static int batch_prepare_into(lzb_ctx* ctx, int fmt, const lzb_options* opt, const uint8_t* d_in, const uint64_t* in_off,
                               uint32_t n, uint8_t* d_out, const uint64_t* out_off, lzb_batch* b, bool dev_offsets = false,
-                              uint64_t mirror_base = 0, const uint8_t* scan_in = nullptr, bool take_lock = true) {
+                              uint64_t mirror_base = 0, const uint8_t* scan_in = nullptr, bool take_lock = true,
+                              bool host_io = false) {
     static const lzb_options defaults = {0, 0, 0, 0, {0, 0, 0, 0}, 0, 0};
     if (!ctx || !in_off || !out_off || (fmt != LZB_FMT_LZMA && fmt != LZB_FMT_LZMA2) || n == 0 || !d_in || !d_out)
         return LZB_RC_BAD_ARG;
@@ -733,7 +846,8 @@ static int batch_prepare_into(lzb_ctx* ctx, int fmt, const lzb_options* opt, con
     }
     b->lclp_hint = lclp;
     b->stored_bytes = stored_bytes;
-    make_plan(ctx, b->items.data(), n, lclp, stored_bytes, &b->plan, /*route_stored=*/mirror_base == 0);
+    make_plan(ctx, b->items.data(), n, lclp, stored_bytes, &b->plan, /*route_stored=*/mirror_base == 0, host_io);
+    b->host_io = host_io;
     if (upload_order(ctx, s, b->plan, b->d_order) != LZB_RC_OK) return fail(LZB_RC_CUDA);
     B_TRY(cudaStreamSynchronize(s));
     return LZB_RC_OK;
@@ -759,7 +873,7 @@ static int batch_redo(lzb_batch* b, cudaStream_t s, std::vector<LzbResult>& res,
     std::vector<LzbItem> sub(m);
     for (uint32_t k = 0; k < m; k++) sub[k] = b->items[redo[k]];
     DecodePlan plan;
-    make_plan(ctx, sub.data(), m, 4, b->stored_bytes, &plan, /*route_stored=*/!mirror);
+    make_plan(ctx, sub.data(), m, 4, b->stored_bytes, &plan, /*route_stored=*/!mirror, b->host_io);
     CUDA_TRY(ctx, b->d_redo_items.ensure(m * sizeof(LzbItem)));
     CUDA_TRY(ctx, b->d_redo_results.ensure(m * sizeof(LzbResult)));
     CUDA_TRY(ctx, b->d_redo_counter.ensure(64));
@@ -1007,12 +1121,16 @@ extern "C" int lzb_decode_batch_peer(lzb_ctx* ctx, int fmt, const lzb_options* o
         scan_base -= mis;
         in_base -= mis;
     }
+    // same two forms as the host API (CudaExecutor::run): page stores by K1 for up to two rounds of streams, done words +
+    // copy engine (peer-to-peer over NVLink) beyond
+    const bool drain = n > 2u * (uint32_t)ctx->sm_count * LZB_MAX_WARPS && !getenv("LZB_NO_DRAIN");
     int rc = batch_prepare_into(ctx, fmt, opt, in_base, in_off, n, out_base, out_off, b, false,
-                                (uint64_t)(uintptr_t)dst_out, scan_base, /*take_lock=*/false);
+                                drain ? 0 : (uint64_t)(uintptr_t)dst_out, scan_base, /*take_lock=*/false, /*host_io=*/true);
     if (rc != LZB_RC_OK) return rc;
     bool all_mirrored = true;
     for (uint32_t i = 0; i < n; i++)
         if (b->items[i].kind != LZB_ITEM_PRESET && (out_off[i] & 15)) all_mirrored = false;
+    if (drain) all_mirrored = true;  // the copy engine has no alignment needs
     trace.plan = trace.now();
     // the input follows behind the gate; small shards are not worth the chunking
     const unsigned long long* d_gate = nullptr;
@@ -1025,15 +1143,35 @@ extern "C" int lzb_decode_batch_peer(lzb_ctx* ctx, int fmt, const lzb_options* o
         CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, src_in + (in_off[0] - mis), in_bytes, cudaMemcpyDefault, ctx->stream));
     }
     cudaStream_t s = ctx->stream;
+    if (drain && (rc = set_done_words(ctx, n, &d_gate)) != LZB_RC_OK) return rc;
     rc = launch_plan(ctx, s, b->plan, b->d_items.as<LzbItem>(), b->d_order.as<uint32_t>(), in_base, out_base,
-                     b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>(), /*mirror=*/true, d_gate, &upload,
+                     b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>(), /*mirror=*/!drain, d_gate, &upload,
                      &b->d_matchws, &b->d_litws);
     if (rc != LZB_RC_OK) return rc;
     trace.launched = trace.now();
+    std::vector<uint8_t> copied;
+    if (drain) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->kernels_done, s));
+        copied.assign(n, 0);
+        std::vector<uint32_t> queue(b->plan.order_small);
+        queue.insert(queue.end(), b->plan.order_big.begin(), b->plan.order_big.end());
+        rc = drain_finished(ctx, queue, b->items.data(), out_base, dst_out, copied, 4u * (uint32_t)ctx->sm_count * LZB_MAX_WARPS);
+        if (rc != LZB_RC_OK) return rc;
+    }
     std::vector<LzbResult> res(n);
     CUDA_TRY(ctx, cudaMemcpyAsync(res.data(), b->d_results.p, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    if ((rc = batch_redo(b, s, res, true))) return rc;
+    const std::vector<LzbResult> first_pass(res);
+    if ((rc = batch_redo(b, s, res, !drain))) return rc;
+    if (drain) {  // streams without a done word (stored-chunk kernel) and streams the second pass decoded again
+        for (uint32_t i = 0; i < n; i++) {
+            const bool redone = first_pass[i].code != res[i].code || first_pass[i].out_len != res[i].out_len;
+            if ((!copied[i] || redone) && res[i].out_len)
+                CUDA_TRY(ctx, cudaMemcpyAsync(dst_out + b->items[i].out_off, out_base + b->items[i].out_off, res[i].out_len,
+                                              cudaMemcpyDefault, ctx->drain_stream));
+        }
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->drain_stream));
+    }
     if (out_hi > out_lo && !all_mirrored)  // some stream's region was not 16-byte aligned: plain copy of the whole range
         CUDA_TRY(ctx, cudaMemcpyAsync(dst_out + out_lo, d_out0, out_hi - out_lo, cudaMemcpyDefault, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));

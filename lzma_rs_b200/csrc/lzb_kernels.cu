@@ -33,9 +33,14 @@
 // device offset reached so far to gate[0].  A warp starts a stream once every 128-byte line the stream touches has
 // arrived (whole lines: K1 reads the blob through the non-coherent path, so a line must never be fetched before all of
 // it is there).  gate[1] = device offset minus blob offset, gate[2] = device offset of the end of the blob.
+// gate[3] (0 = none): device-visible address of one 32-bit "done" word per stream in pinned host memory.  When a stream
+// is finished its warp publishes out_len + 1 there (after a system-scope fence by every lane that stored output); the
+// host polls these words and lets the COPY ENGINE move each finished stream to the caller's buffer (pinned host memory
+// or a peer GPU) while the kernel keeps decoding -- the multi-round form of the host API: the kernel itself then never
+// stores across PCIe (measured on the north-star batch: the page-mirroring variant runs 16 % slower than the plain one).
 // Returns false if the bytes did not arrive within 5 s (LZB_E_INPUT_TIMEOUT: the host then waits for the upload and
 // decodes the stream again; it keeps a stalled copy from hanging the GPU).
-__device__ __noinline__ bool input_arrived(const LzbItem* it, const unsigned long long* gate) {
+__device__ __forceinline__ bool input_arrived(const LzbItem* it, const unsigned long long* gate) {
     if (it->kind == LZB_ITEM_PRESET || (it->flags & LZB_ITEM_F_IN_FROM_OUT)) return true;
     unsigned long long need = (it->in_off + it->in_len + gate[1] + 127ull) & ~127ull;
     if (need > gate[2]) need = gate[2];
@@ -53,7 +58,11 @@ __device__ __noinline__ bool input_arrived(const LzbItem* it, const unsigned lon
     return true;
 }
 
-template <bool LIT_GLOBAL, bool MIRROR, int WIDE, bool SCHED>
+// GATE: host-API launches (input gate + done words compiled in).  They always use the SCHED form: in the plain-queue form
+// any code around decode_item that depends on the stream index makes ptxas treat the loop's exits as divergent and wrap
+// every branch of the bit loop in BSSY / BSYNC pairs (10 -> 78 in the kernel, +20 % instructions; tools/check_sass.py
+// counts them) -- the host gives launches without a placement plan a trivial static prefix instead (launch_plan).
+template <bool LIT_GLOBAL, bool MIRROR, int WIDE, bool SCHED, bool GATE>
 __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order,
                                             uint32_t n_items, uint32_t n_static, const uint8_t* __restrict__ in_blob,
                                             uint8_t* out_blob, LzbResult* results, unsigned int* counter, uint32_t tab_lclp,
@@ -82,7 +91,11 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
         if (slot >= n_items) break;
         const uint32_t idx = order[slot];
         if (SCHED && idx == LZB_ORDER_PARK) break;
-        if (MIRROR && gate && !input_arrived(items + idx, gate)) {  // host API: the input blob is still being uploaded
+        // host API: the input blob may still be on its way.  The verdict of the (called) wait is re-broadcast from lane 0:
+        // a call's return value counts as divergent for the compiler, and a divergent `continue` here would put
+        // reconvergence barriers (BSSY / BSYNC) around every branch of the bit loop below -- that, not the page stores, is
+        // what made the round-1 mirror kernels 16 % slower than the plain ones (profiles/r02_e2e_timeline.md).
+        if (GATE && gate && !__shfl_sync(FULL_MASK, (int)input_arrived(items + idx, gate), 0)) {
             if (lane == 0) {
                 LzbResult r = {};
                 r.code = LZB_E_INPUT_TIMEOUT;
@@ -99,6 +112,15 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
             decode_item<false, MIRROR, WIDE>(items + idx, in_blob, out_blob, T, gws, tab, plain, matched, kc, tab_lclp, results + idx, lane);
         }
         __syncwarp();
+        if (GATE && gate) {
+            const unsigned long long done = gate[3];
+            if (done) {
+                __threadfence_system();  // this lane's output stores, before the word that releases them to the copy engine
+                __syncwarp();
+                if (lane == 0)
+                    reinterpret_cast<volatile unsigned int*>(done)[idx] = (unsigned int)results[idx].out_len + 1u;
+            }
+        }
     }
 }
 
@@ -108,29 +130,32 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
         uint32_t tab_lclp, uint32_t warp_smem_bytes, uint16_t *ws, unsigned long long ws_stride_u16,                 \
         const __grid_constant__ LzbKC kc, const unsigned long long *gate
 #define LZB_KERNEL_PASS items, order, n_items, n_static, in_blob, out_blob, results, counter, tab_lclp, warp_smem_bytes, ws, ws_stride_u16, kc, gate
-#define LZB_DEFINE_K1(NAME, LIT_GLOBAL, MIRROR, WIDE, SCHED)                                               \
+#define LZB_DEFINE_K1(NAME, LIT_GLOBAL, MIRROR, WIDE, SCHED, GATE)                                         \
     extern "C" __global__ void __launch_bounds__(LZB_MAX_WARPS * 32, 1) NAME(LZB_KERNEL_ARGS) {          \
-        decode_loop<LIT_GLOBAL, MIRROR, WIDE, SCHED>(LZB_KERNEL_PASS);                                    \
+        decode_loop<LIT_GLOBAL, MIRROR, WIDE, SCHED, GATE>(LZB_KERNEL_PASS);                              \
     }
 
-// MIRROR: host-API variant, finished output pages are mirrored into the caller's pinned host buffer.
-// WIDE  : 0 lean; 1 ("fill") word-wide run fills for batches that expand > 16x; 2 ("copy") 16-byte vector copies of
-//         stored chunks for batches that are mostly stored chunks.  Selected by the host from the framing scan.
-// SCHED : launch with a placement plan (above).
-LZB_DEFINE_K1(lzb_decode_kernel, false, false, 0, false)
-LZB_DEFINE_K1(lzb_decode_mirror_kernel, false, true, 0, false)
-LZB_DEFINE_K1(lzb_decode_fill_kernel, false, false, 1, false)
-LZB_DEFINE_K1(lzb_decode_fill_mirror_kernel, false, true, 1, false)
-LZB_DEFINE_K1(lzb_decode_copy_kernel, false, false, 2, false)
-LZB_DEFINE_K1(lzb_decode_copy_mirror_kernel, false, true, 2, false)
-LZB_DEFINE_K1(lzb_decode_sched_kernel, false, false, 0, true)
-LZB_DEFINE_K1(lzb_decode_sched_mirror_kernel, false, true, 0, true)
-LZB_DEFINE_K1(lzb_decode_sched_fill_kernel, false, false, 1, true)
-LZB_DEFINE_K1(lzb_decode_sched_fill_mirror_kernel, false, true, 1, true)
-LZB_DEFINE_K1(lzb_decode_sched_copy_kernel, false, false, 2, true)
-LZB_DEFINE_K1(lzb_decode_sched_copy_mirror_kernel, false, true, 2, true)
+// Device-resident batches (lzb_batch_* / lzb_decode_batch_device): no host I/O code at all.
+//   WIDE : 0 lean; 1 ("fill") word-wide run fills for batches that expand > 16x; 2 ("copy") 16-byte vector copies of
+//          stored chunks for batches that are mostly stored chunks.  Selected by the host from the framing scan.
+//   SCHED: launch with a placement plan (above).
+LZB_DEFINE_K1(lzb_decode_kernel, false, false, 0, false, false)
+LZB_DEFINE_K1(lzb_decode_fill_kernel, false, false, 1, false, false)
+LZB_DEFINE_K1(lzb_decode_copy_kernel, false, false, 2, false, false)
+LZB_DEFINE_K1(lzb_decode_sched_kernel, false, false, 0, true, false)
+LZB_DEFINE_K1(lzb_decode_sched_fill_kernel, false, false, 1, true, false)
+LZB_DEFINE_K1(lzb_decode_sched_copy_kernel, false, false, 2, true, false)
+// Host API / peer form (input gate, output leaves the device while the kernel runs), always in the SCHED form:
+//   "drain"  done word per finished stream, the copy engine moves it (batches of more than two rounds)
+//   "mirror" K1 stores finished 4 KiB pages to the destination itself (up to two rounds: all streams end together)
+LZB_DEFINE_K1(lzb_decode_drain_kernel, false, false, 0, true, true)
+LZB_DEFINE_K1(lzb_decode_drain_fill_kernel, false, false, 1, true, true)
+LZB_DEFINE_K1(lzb_decode_drain_copy_kernel, false, false, 2, true, true)
+LZB_DEFINE_K1(lzb_decode_mirror_kernel, false, true, 0, true, true)
+LZB_DEFINE_K1(lzb_decode_mirror_fill_kernel, false, true, 1, true, true)
+LZB_DEFINE_K1(lzb_decode_mirror_copy_kernel, false, true, 2, true, true)
 // .lzma streams with lc+lp > 4: literal table in a per-warp global workspace (ws + warp_id * ws_stride_u16).
-LZB_DEFINE_K1(lzb_decode_biglit_kernel, true, true, 1, false)
+LZB_DEFINE_K1(lzb_decode_biglit_kernel, true, true, 1, false, true)
 
 // ------------------------------------------------------------------------------------------------
 // K2: per-stream scan -> work items (+ size summary).  One thread per stream.

@@ -241,3 +241,53 @@ def test_cpp_multi_client(ctx, tmp_path):
         assert r.returncode == 0, (devs, r.stdout, r.stderr)
         nd = {"0,0": 2, "0,0,0,0": 4}.get(devs, torch.cuda.device_count())
         assert r.stdout.startswith(f"devices {nd} split 0 "), r.stdout
+
+
+def test_drain_mode_many_streams(ctx):
+    """More than two rounds of streams with a pinned output: the plain kernels publish a done word per stream and the copy
+    engine moves finished streams while later rounds decode (host API and peer form).  Error streams, stored-chunk-only
+    streams (copy kernel, no done words), an unaligned output layout and the second-pass stream are mixed in."""
+    import gpu_util
+    import torch
+    from lzma_rs_b200 import _native
+    lib = _native.load()
+    rng = np.random.default_rng(77)
+    base_plain = [corpus.mixed_text(9100 + i, int(rng.integers(1_000, 9_000))) for i in range(96)]
+    base = [corpus.raw_lzma2(p, dict_size=1 << 16) for p in base_plain]
+    n = 9100
+    streams = [base[i % 96] for i in range(n)]
+    plains = [base_plain[i % 96] for i in range(n)]
+    streams[11] = streams[11][:40]
+    streams[5000] = b"\x33" + streams[5000][1:]
+    streams[9000] = underconsumed_lclp4_stream()
+    for i in (100, 4000, 9099):
+        plains[i] = bytes([i & 0xFF]) * 70_001
+        streams[i] = corpus.stored_lzma2(plains[i])
+    special = {11, 5000, 9000}
+    refs = {i: oracle.lzma2_decompress(streams[i]) for i in special}
+    caps = [len(refs[i].out) + 64 if i in special else len(plains[i]) for i in range(n)]
+    # host API, pinned buffers, 16-byte aligned layout
+    outs, out_len, consumed, st = gpu_util.host_decode_pinned(ctx, 1, streams, caps)
+    for i in range(n):
+        if i in special:
+            disp = "" if st[i]["code"] == 0 else _native.format_status(lib, st[i])
+            assert disp == refs[i].display and outs[i] == refs[i].out, i
+        else:
+            assert st[i]["code"] == 0 and outs[i] == plains[i] and int(consumed[i]) == len(streams[i]), i
+    # peer form into a device blob whose stream regions are NOT 16-byte aligned (tight layout)
+    blob, in_off = _native.pack_streams(streams)
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(np.asarray(caps, dtype=np.uint64), out=out_off[1:])
+    src = torch.from_numpy(blob).cuda()
+    dst = torch.full((int(out_off[-1]) + 16,), 0xEE, dtype=torch.uint8, device="cuda")
+    opt = _native.make_options()
+    ol, cs = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+    st2 = np.zeros(n, dtype=_native.STATUS_DTYPE)
+    rc = lib.lzb_decode_batch_peer(ctx.handle, 1, C.byref(opt), src.data_ptr(), in_off.ctypes.data, n, dst.data_ptr(),
+                                   out_off.ctypes.data, ol.ctypes.data, cs.ctypes.data, st2.ctypes.data)
+    assert rc == 0, ctx.last_error()
+    torch.cuda.synchronize()
+    host = dst.cpu().numpy()
+    assert (st2["code"] == st["code"]).all() and (ol == out_len).all()
+    for i in range(n):
+        assert host[int(out_off[i]):int(out_off[i]) + int(ol[i])].tobytes() == outs[i], i

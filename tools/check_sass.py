@@ -7,10 +7,19 @@ single pipe per SM sub-partition then throttles the kernel (measured on B200: C3
 65 %, math_pipe_throttle 12 % -> 22 %; profiles/r01_uniform_flip.md).  The flip shows in the static opcode mix, so the
 build checks it:   python tools/check_sass.py lzma_rs_b200/liblzma_b200.so [max_share]
 prints size / registers-independent uniform-op share per decode kernel and exits 1 if any exceeds max_share (0.12).
+
+Second guard (round 2): reconvergence barriers.  K1's control flow is warp-uniform; when ptxas's divergence analysis
+loses that (a called function's result or stream-index dependent code around decode_item in the plain-queue loop), it
+wraps every branch of the bit loop in BSSY / BSYNC pairs: 10 -> 78 barriers and +20 % instructions in the kernel
+(round-1's non-sched mirror kernel had 87).  More than MAX_BSSY (32) in a decode kernel fails the build; the lc+lp > 4
+kernel (rare path, literal table in global memory) is exempt.
 """
 import re
 import subprocess
 import sys
+
+
+MAX_BSSY = 32
 
 
 def kernels(lib):
@@ -38,9 +47,14 @@ def main():
         ops = [o for o in ops if o != "NOP"]
         u = sum(1 for o in ops if o.startswith("U") or o in ("R2UR", "S2UR", "LDCU", "VOTEU"))
         share = u / max(1, len(ops))
+        bssy = sum(1 for o in ops if o == "BSSY")
         flag = "" if share <= limit else "   <-- uniform-datapath flip"
+        if bssy > MAX_BSSY and "biglit" not in name:
+            flag += "   <-- reconvergence barriers in the bit loop"
+            bad += 1
         bad += share > limit
-        print(f"{name:34s} {len(ops):5d} instructions ({len(ops) * 16 / 1024:5.1f} KB)  uniform-datapath ops {100 * share:5.1f} %{flag}")
+        print(f"{name:34s} {len(ops):5d} instructions ({len(ops) * 16 / 1024:5.1f} KB)  uniform-datapath ops {100 * share:5.1f} %"
+              f"  BSSY {bssy:3d}{flag}")
     return 1 if bad else 0
 
 
