@@ -559,6 +559,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
         ((itp->flags & LZB_ITEM_F_IN_FROM_OUT) ? (const uint8_t*)out_blob : in_blob) + (itp->in_off - p0);
     const uint32_t stream_lim = p0 + (uint32_t)itp->in_len;
     uint8_t* out = out_blob + itp->out_off;
+    // (pinning this pointer in a register pair with an opaque asm was tried: ptxas then loses the address space (generic
+    // ST instead of STG) and the warp-uniformity of everything derived from it -- 76 BSSY pairs in the bit loop)
     const uint32_t cap = (uint32_t)LZB_MIN(itp->out_cap, (uint64_t)0xFFFFF000u);
     const uint32_t tab_u16 = LIT_GLOBAL ? (uint32_t)T_LIT : T_LIT + (0x100u << tab_lclp);
     const uint32_t plain_stride = LIT_GLOBAL ? 0x300u : 0x100u, matched_stride = LIT_GLOBAL ? 0x300u : 0x200u;

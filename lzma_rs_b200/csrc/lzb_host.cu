@@ -95,6 +95,7 @@ struct lzb_ctx {
     // host polls them and the copy engine moves finished streams to the caller's buffer on drain_stream
     cudaStream_t drain_stream = nullptr;
     cudaEvent_t kernels_done = nullptr;
+    cudaEvent_t upload_done = nullptr;  // recorded on copy_stream behind the last chunk of a gated upload
     unsigned int* h_done = nullptr;
     size_t h_done_cap = 0;
     // lzb_decode_batch_device keeps ONE batch object alive between calls: its device buffers are reused instead of
@@ -113,6 +114,7 @@ struct lzb_ctx {
 };
 #define LZB_GATE_CHUNK (8ull << 20)  // upload granularity of the gated host path
 #define LZB_GATE_MAX_CHUNKS 56
+#define LZB_GATE_MARKS 4096          // watermark values of one queue-order upload (h_marks[8 ..])
 
 #define CUDA_TRY(ctx, call)                                                                         \
     do {                                                                                            \
@@ -273,7 +275,7 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
 int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem* d_items, const uint32_t* d_order,
                 const uint8_t* d_in_base, uint8_t* d_out_base, LzbResult* d_results, unsigned int* d_counter,
                 bool mirror = false, const unsigned long long* d_gate = nullptr,
-                std::function<int()>* before_first_kernel = nullptr, DevBuf* own_matchws = nullptr,
+                std::function<int(int)>* upload = nullptr, int* upload_phase = nullptr, DevBuf* own_matchws = nullptr,
                 DevBuf* own_litws = nullptr) {
     // per-warp workspaces: the ctx's own for the host API (calls are serialised by ctx->mu), the batch's own for prepared
     // device batches, which may be in flight on different streams at the same time
@@ -283,11 +285,10 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
     // everything small this launch needs has been enqueued: now the gated upload of the input blob may occupy the copy
     // engine.  It is enqueued BEFORE the kernel so that a launch that blocks the host (profilers, compute-sanitizer,
     // CUDA_LAUNCH_BLOCKING) cannot wait for bytes nobody has sent yet.
-    auto fire = [&]() -> int {
-        if (!before_first_kernel || !*before_first_kernel) return LZB_RC_OK;
-        int rc = (*before_first_kernel)();
-        *before_first_kernel = nullptr;
-        return rc;
+    auto fire = [&]() -> int {  // phase 0 of the gated upload; the caller runs phase 1 behind the launches (upload_rest)
+        if (!upload || !*upload || !upload_phase || *upload_phase != 0) return LZB_RC_OK;
+        *upload_phase = 1;
+        return (*upload)(0);
     };
     const uint32_t ns = (uint32_t)p.order_small.size(), nb = (uint32_t)p.order_big.size();
     const uint32_t nst = (uint32_t)p.order_stored.size();
@@ -318,10 +319,19 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
     }
     if (nst) {
         if (int rc = fire()) return rc;
+        // the stored-chunk copy kernel has no input gate: it starts behind the last chunk of an upload still in flight
+        if (d_gate) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->upload_done, 0));
         lzb_stored_decode_kernel<<<nst, 256, 0, s>>>(d_items, d_order + ns + nb, d_in_base, d_out_base, d_results);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     return LZB_RC_OK;
+}
+
+// Phase 1 of a gated upload whose phase 0 ran inside launch_plan.
+int upload_rest(std::function<int(int)>* upload, int* upload_phase) {
+    if (!upload || !*upload || !upload_phase || *upload_phase != 1) return LZB_RC_OK;
+    *upload_phase = 2;
+    return (*upload)(1);
 }
 
 int upload_order(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, DevBuf& d_order) {
@@ -339,7 +349,7 @@ int upload_order(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, DevBuf& d_or
 // chunked copy (+ one watermark update per chunk) on ctx->copy_stream.  The closure is run by launch_plan right before
 // the first K1 launch is enqueued.
 int arm_gate(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_lo, uint64_t in_bytes,
-             std::function<int()>* upload, const unsigned long long** d_gate) {
+             std::function<int(int)>* upload, const unsigned long long** d_gate) {
     uint64_t chunk = LZB_GATE_CHUNK;
     while ((lead + in_bytes + chunk - 1) / chunk > LZB_GATE_MAX_CHUNKS) chunk *= 2;
     CUDA_TRY(ctx, ctx->d_gate.ensure(64));
@@ -348,10 +358,12 @@ int arm_gate(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_lo, ui
     hm[1] = (unsigned long long)(lead - in_lo);     // device offset = blob offset + this (mod 2^64)
     hm[2] = (unsigned long long)(lead + in_bytes);  // device offset of the end of the blob
     hm[3] = 0;                                      // no done words (set_done_words)
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, hm, 32, cudaMemcpyHostToDevice, ctx->stream));
+    hm[4] = 0;                                      // the watermark counts bytes (arm_gate_queue: queue positions)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, hm, 40, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->gate_ready, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gate_ready, 0));
-    *upload = [=]() -> int {
+    *upload = [=](int phase) -> int {  // phase 0: before the first kernel launch (everything); phase 1: behind it (nothing)
+        if (phase) return LZB_RC_OK;
         uint32_t k = 0;
         for (uint64_t lo = lead; lo < lead + in_bytes; k++) {  // chunk boundaries at device offsets k * chunk
             const uint64_t hi = std::min<uint64_t>((lo / chunk + 1) * chunk, lead + in_bytes);
@@ -361,9 +373,62 @@ int arm_gate(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_lo, ui
             CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, &hm[8 + k], 8, cudaMemcpyHostToDevice, ctx->copy_stream));
             lo = hi;
         }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy_stream));
         return LZB_RC_OK;
     };
     *d_gate = ctx->d_gate.as<unsigned long long>();
+    return LZB_RC_OK;
+}
+
+// Queue-order form of the gated upload (raw formats, one work item per stream): re-arms the gate armed by arm_gate so that
+// the watermark counts positions of `queue` (the launch's order array; LZB_ORDER_PARK entries count), and replaces the
+// upload closure.  Every stream is one copy of whole 128-byte lines of the device blob (K1 reads its input through the
+// non-coherent path: a line must be complete before anything on it is read; neighbours share their boundary lines, which
+// are simply copied twice with the same bytes).  Phase 0 (before the kernel launch) enqueues the head of the queue, so
+// that the launch is not held up by ~10^5 driver calls; phase 1 (behind the launch) the rest, then `tail` (streams that
+// are not in K1's queue: the stored-chunk copy kernel's).
+int arm_gate_queue(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_lo, uint64_t in_bytes,
+                   const LzbItem* items, const std::vector<uint32_t>& queue, const std::vector<uint32_t>& tail,
+                   std::function<int(int)>* upload) {
+    unsigned long long* hm = ctx->h_marks;
+    hm[6] = 1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.as<unsigned long long>() + 4, &hm[6], 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->gate_ready, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gate_ready, 0));
+    const size_t npos = queue.size();
+    const size_t head = std::min<size_t>(npos, 768);
+    // a watermark update every `step` positions: at most LZB_GATE_MARKS of them
+    const size_t step = std::max<size_t>(16, (npos + LZB_GATE_MARKS - 2) / (LZB_GATE_MARKS - 1));
+    std::vector<uint32_t> q(queue), t(tail);
+    *upload = [=](int phase) -> int {
+        auto copy_stream_of = [&](uint32_t i) -> int {
+            const LzbItem& it = items[i];
+            if (it.kind == LZB_ITEM_PRESET || (it.flags & LZB_ITEM_F_IN_FROM_OUT) || !it.in_len) return LZB_RC_OK;
+            // device offsets of the stream (items carry blob offsets; hdr_len bytes in front belong to it too)
+            uint64_t lo = lead + (it.in_off - it.hdr_len - in_lo), hi = lead + (it.in_off + it.in_len - in_lo);
+            lo = std::max<uint64_t>(lead, lo & ~127ull);
+            hi = std::min<uint64_t>(lead + in_bytes, (hi + 127ull) & ~127ull);
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + lo, src + (lo - lead), hi - lo, cudaMemcpyDefault,
+                                          ctx->copy_stream));
+            return LZB_RC_OK;
+        };
+        const size_t from = phase ? head : 0, to = phase ? npos : head;
+        for (size_t k = from; k < to; k++) {
+            if (q[k] != LZB_ORDER_PARK)
+                if (int rc = copy_stream_of(q[k])) return rc;
+            if ((k + 1) % step == 0 || k + 1 == npos) {
+                unsigned long long* mark = &hm[8 + (k + step) / step];  // one pinned word per update, never reused
+                *mark = k + 1;
+                CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, mark, 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
+        }
+        if (phase ? head < npos : head == npos) {  // the last phase that has work
+            for (uint32_t i : t)
+                if (int rc = copy_stream_of(i)) return rc;
+            CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy_stream));
+        }
+        return LZB_RC_OK;
+    };
     return LZB_RC_OK;
 }
 
@@ -383,12 +448,12 @@ int set_done_words(lzb_ctx* ctx, uint32_t n, const unsigned long long** d_gate) 
     CUDA_TRY(ctx, ctx->d_gate.ensure(64));
     if (!*d_gate) {
         hm[0] = ~0ull;  // everything has arrived
-        hm[1] = hm[2] = 0;
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, hm, 24, cudaMemcpyHostToDevice, ctx->stream));
+        hm[1] = hm[2] = hm[3] = hm[4] = 0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, hm, 40, cudaMemcpyHostToDevice, ctx->stream));
         *d_gate = ctx->d_gate.as<unsigned long long>();
     }
-    hm[4] = (unsigned long long)(uintptr_t)ctx->h_done;  // UVA: pinned host memory has the same address on the device
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.as<unsigned long long>() + 3, &hm[4], 8, cudaMemcpyHostToDevice, ctx->stream));
+    hm[5] = (unsigned long long)(uintptr_t)ctx->h_done;  // UVA: pinned host memory has the same address on the device
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.as<unsigned long long>() + 3, &hm[5], 8, cudaMemcpyHostToDevice, ctx->stream));
     return LZB_RC_OK;
 }
 
@@ -436,10 +501,16 @@ class CudaExecutor : public lzb::Executor {
     CudaExecutor(lzb_ctx* ctx, cudaStream_t s, const uint8_t* d_in_base, uint8_t* d_out_base, uint8_t* host_mirror = nullptr,
                  const unsigned long long* d_gate = nullptr)
         : ctx_(ctx), s_(s), in_(d_in_base), out_(d_out_base), hmirror_(host_mirror), gate_(d_gate) {}
-    // Runs once, right before the first K1 launch is enqueued (after the small uploads of the plan, which must not queue
-    // behind it on the copy engine): the gated upload of the input blob.
-    std::function<int()> before_first_kernel;
+    // The gated upload of the input blob.  Phase 0 runs right before the first K1 launch is enqueued (after the small
+    // uploads of the plan, which must not queue behind it on the copy engine), phase 1 behind the launch.
+    std::function<int(int)> before_first_kernel;
+    int upload_phase = 0;
     cudaStream_t copy_stream = nullptr;  // where that upload runs
+    // set for the raw formats (one work item per stream): the upload may follow the launch's queue instead of the blob
+    struct QueueUpload {
+        const uint8_t* src = nullptr;  // first byte of the blob in the caller's memory
+        uint64_t lead = 0, in_lo = 0, in_bytes = 0;
+    } queue_upload;
     Trace* trace = nullptr;
     bool all_mirrored() const { return hmirror_ != nullptr && !unmirrored_; }
 
@@ -540,11 +611,15 @@ class CudaExecutor : public lzb::Executor {
     int run(const LzbItem* items, uint32_t n, uint32_t lclp_hint, uint64_t stored_bytes, LzbResult* results) {
         lzb_ctx* ctx = ctx_;
         DecodePlan plan;
-        // Output to a pinned host buffer, two forms.  Up to two rounds of streams: K1's mirror variants store finished
-        // 4 KiB pages to the host buffer themselves (all streams end together, nothing else could overlap the transfer).
-        // More rounds: drain mode -- the plain kernels publish a done word per stream and the copy engine moves finished
-        // streams while later rounds decode (the kernel never stores across PCIe).
-        const bool drain = hmirror_ != nullptr && n > 2u * (uint32_t)ctx->sm_count * LZB_MAX_WARPS && !getenv("LZB_NO_DRAIN");
+        // Output to a pinned host buffer, two forms.  One round of streams (every stream resident from the start): K1's
+        // mirror variants store finished 4 KiB pages to the host buffer themselves (all streams end together, nothing else
+        // could overlap the transfer).  More than one round: drain mode -- the plain kernels publish a done word per
+        // stream and the copy engine moves finished streams while later ones decode (the kernel never stores across PCIe;
+        // DESIGN.md section 5).  LZB_DRAIN_ROUNDS overrides the threshold (in rounds; experiments).
+        const char* dr = getenv("LZB_DRAIN_ROUNDS");
+        const double drain_rounds = dr ? atof(dr) : 1.0;
+        const bool drain = hmirror_ != nullptr && !getenv("LZB_NO_DRAIN") &&
+                           (double)n > drain_rounds * (double)ctx->sm_count * LZB_MAX_WARPS;
         const bool mirror = hmirror_ != nullptr && !drain;
         make_plan(ctx, items, n, lclp_hint, stored_bytes, &plan, /*route_stored=*/!mirror, /*host_io=*/hmirror_ != nullptr);
         CUDA_TRY(ctx, ctx->d_items.ensure(n * sizeof(LzbItem)));
@@ -575,11 +650,17 @@ class CudaExecutor : public lzb::Executor {
             cudaEventRecord(ev0, s_);
         }
         const unsigned long long* gate = gate_;
+        if (gate_ && upload_phase == 0 && queue_upload.src && plan.order_big.empty() && !getenv("LZB_GATE_BYTES")) {
+            rc = arm_gate_queue(ctx, queue_upload.src, queue_upload.lead, queue_upload.in_lo, queue_upload.in_bytes, items,
+                                plan.order_small, plan.order_stored, &before_first_kernel);
+            if (rc != LZB_RC_OK) return rc;
+        }
         if (drain && (rc = set_done_words(ctx, n, &gate)) != LZB_RC_OK) return rc;
         rc = launch_plan(ctx, s_, plan, ctx->d_items.as<LzbItem>(), ctx->d_order.as<uint32_t>(), in_, out_,
                          ctx->d_results.as<LzbResult>(), ctx->d_counter.as<unsigned int>(), mirror, gate,
-                         &before_first_kernel);
+                         &before_first_kernel, &upload_phase);
         if (rc != LZB_RC_OK) return rc;
+        if ((rc = upload_rest(&before_first_kernel, &upload_phase)) != LZB_RC_OK) return rc;
         std::vector<uint8_t> copied;
         if (drain) {
             CUDA_TRY(ctx, cudaEventRecord(ctx->kernels_done, s_));
@@ -603,6 +684,14 @@ class CudaExecutor : public lzb::Executor {
                                                   cudaMemcpyDefault, ctx->drain_stream));
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->drain_stream));
         }
+        if (gate_ && upload_phase == 2 && !gate_opened_) {
+            // later launches of this call (second passes, chained .xz stages) use other queues: the upload has been
+            // consumed by the kernel that just finished; open the gate for good
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            ctx->h_marks[7] = ~0ull;
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, &ctx->h_marks[7], 8, cudaMemcpyHostToDevice, s_));
+            gate_opened_ = true;
+        }
         if (tr) {
             trace->synced = trace->now();
             float ms = 0;
@@ -620,6 +709,7 @@ class CudaExecutor : public lzb::Executor {
     uint8_t* hmirror_;
     const unsigned long long* gate_;
     bool unmirrored_ = false;
+    bool gate_opened_ = false;
     std::vector<void*> scratch_;
 };
 
@@ -653,8 +743,9 @@ extern "C" int lzb_create(lzb_ctx** out, int device) {
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->drain_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->kernels_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->upload_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->gate_ready, cudaEventDisableTiming) != cudaSuccess ||
-        cudaHostAlloc((void**)&ctx->h_marks, (8 + LZB_GATE_MAX_CHUNKS) * sizeof(unsigned long long), cudaHostAllocDefault) !=
+        cudaHostAlloc((void**)&ctx->h_marks, (8 + LZB_GATE_MARKS + 8) * sizeof(unsigned long long), cudaHostAllocDefault) !=
             cudaSuccess) {
         lzb_destroy(ctx);
         return LZB_RC_CUDA;
@@ -694,6 +785,7 @@ extern "C" void lzb_destroy(lzb_ctx* ctx) {
     if (ctx->drain_stream) cudaStreamDestroy(ctx->drain_stream);
     if (ctx->gate_ready) cudaEventDestroy(ctx->gate_ready);
     if (ctx->kernels_done) cudaEventDestroy(ctx->kernels_done);
+    if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
     if (ctx->h_marks) cudaFreeHost(ctx->h_marks);
     if (ctx->h_done) cudaFreeHost(ctx->h_done);
     delete ctx;
@@ -739,7 +831,7 @@ extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, c
     // follows in chunks on the copy stream: every warp waits only for its own stream's bytes (input_arrived() in
     // lzb_kernels.cu), so the upload overlaps the decode.  Otherwise: one copy, in stream order before the kernel.
     const unsigned long long* d_gate = nullptr;
-    std::function<int()> upload;
+    std::function<int(int)> upload;
     CopyJoin join{nullptr};
     const uint64_t in_bytes = in_hi - in_lo, lead = in_lo & 15;
     if (host_mirror && in_bytes >= 2 * LZB_GATE_CHUNK && !getenv("LZB_NO_GATE")) {
@@ -751,6 +843,20 @@ extern "C" int lzb_decode_batch(lzb_ctx* ctx, int fmt, const lzb_options* opt, c
     CudaExecutor ex(ctx, ctx->stream, d_in0 - in_lo, d_out0 - out_lo, host_mirror, d_gate);
     ex.before_first_kernel = upload;
     ex.copy_stream = upload ? ctx->copy_stream : nullptr;
+    bool in_pinned = false;  // one copy per stream only pays from page-locked memory (pageable copies are staged)
+    {
+        cudaPointerAttributes ia;
+        if (cudaPointerGetAttributes(&ia, in) == cudaSuccess)
+            in_pinned = ia.type == cudaMemoryTypeHost || ia.type == cudaMemoryTypeDevice || ia.type == cudaMemoryTypeManaged;
+        else
+            cudaGetLastError();
+    }
+    if (upload && in_pinned && fmt != LZB_FMT_XZ) {  // .xz: blocks are re-planned from the bytes, the whole blob must arrive
+        ex.queue_upload.src = in + in_lo;
+        ex.queue_upload.lead = lead;
+        ex.queue_upload.in_lo = in_lo;
+        ex.queue_upload.in_bytes = in_bytes;
+    }
     ex.trace = &trace;
     const double t_enq = trace.now();
     std::vector<lzb::StreamOut> outs(n);
@@ -881,7 +987,7 @@ static int batch_redo(lzb_batch* b, cudaStream_t s, std::vector<LzbResult>& res,
     if (int rc = upload_order(ctx, s, plan, b->d_redo_order)) return rc;
     if (int rc = launch_plan(ctx, s, plan, b->d_redo_items.as<LzbItem>(), b->d_redo_order.as<uint32_t>(), b->d_in, b->d_out,
                              b->d_redo_results.as<LzbResult>(), b->d_redo_counter.as<unsigned int>(), mirror, nullptr,
-                             nullptr, &b->d_matchws, &b->d_litws))
+                             nullptr, nullptr, &b->d_matchws, &b->d_litws))
         return rc;
     std::vector<LzbResult> subres(m);
     CUDA_TRY(ctx, cudaMemcpyAsync(subres.data(), b->d_redo_results.p, m * sizeof(LzbResult), cudaMemcpyDeviceToHost, s));
@@ -915,8 +1021,8 @@ extern "C" int lzb_batch_launch(lzb_batch* b, void* cuda_stream) {
     // a caller driving several GPUs from one thread may have another device current
     if (cudaSetDevice(b->ctx->device) != cudaSuccess) return LZB_RC_CUDA;
     return launch_plan(b->ctx, s, b->plan, b->d_items.as<LzbItem>(), b->d_order.as<uint32_t>(), b->d_in, b->d_out,
-                       b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>(), false, nullptr, nullptr, &b->d_matchws,
-                       &b->d_litws);
+                       b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>(), false, nullptr, nullptr, nullptr,
+                       &b->d_matchws, &b->d_litws);
 }
 
 extern "C" int lzb_batch_kernels_per_launch(const lzb_batch* b) {
@@ -1123,7 +1229,8 @@ extern "C" int lzb_decode_batch_peer(lzb_ctx* ctx, int fmt, const lzb_options* o
     }
     // same two forms as the host API (CudaExecutor::run): page stores by K1 for up to two rounds of streams, done words +
     // copy engine (peer-to-peer over NVLink) beyond
-    const bool drain = n > 2u * (uint32_t)ctx->sm_count * LZB_MAX_WARPS && !getenv("LZB_NO_DRAIN");
+    const char* dr = getenv("LZB_DRAIN_ROUNDS");
+    const bool drain = !getenv("LZB_NO_DRAIN") && (double)n > (dr ? atof(dr) : 1.0) * (double)ctx->sm_count * LZB_MAX_WARPS;
     int rc = batch_prepare_into(ctx, fmt, opt, in_base, in_off, n, out_base, out_off, b, false,
                                 drain ? 0 : (uint64_t)(uintptr_t)dst_out, scan_base, /*take_lock=*/false, /*host_io=*/true);
     if (rc != LZB_RC_OK) return rc;
@@ -1134,11 +1241,16 @@ extern "C" int lzb_decode_batch_peer(lzb_ctx* ctx, int fmt, const lzb_options* o
     trace.plan = trace.now();
     // the input follows behind the gate; small shards are not worth the chunking
     const unsigned long long* d_gate = nullptr;
-    std::function<int()> upload;
+    std::function<int(int)> upload;
+    int upload_phase = 0;
     CopyJoin join{nullptr};
     if (in_bytes >= 2 * LZB_GATE_CHUNK && !getenv("LZB_NO_GATE")) {
         join.s = ctx->copy_stream;
         if ((rc = arm_gate(ctx, src_in + (in_off[0] - mis), lead, in_off[0], in_bytes, &upload, &d_gate))) return rc;
+        if (b->plan.order_big.empty() && !getenv("LZB_GATE_BYTES") &&
+            (rc = arm_gate_queue(ctx, src_in + (in_off[0] - mis), lead, in_off[0], in_bytes, b->items.data(), b->plan.order_small,
+                                 b->plan.order_stored, &upload)))
+            return rc;
     } else {
         CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, src_in + (in_off[0] - mis), in_bytes, cudaMemcpyDefault, ctx->stream));
     }
@@ -1146,8 +1258,9 @@ extern "C" int lzb_decode_batch_peer(lzb_ctx* ctx, int fmt, const lzb_options* o
     if (drain && (rc = set_done_words(ctx, n, &d_gate)) != LZB_RC_OK) return rc;
     rc = launch_plan(ctx, s, b->plan, b->d_items.as<LzbItem>(), b->d_order.as<uint32_t>(), in_base, out_base,
                      b->d_results.as<LzbResult>(), b->d_counter.as<unsigned int>(), /*mirror=*/!drain, d_gate, &upload,
-                     &b->d_matchws, &b->d_litws);
+                     &upload_phase, &b->d_matchws, &b->d_litws);
     if (rc != LZB_RC_OK) return rc;
+    if ((rc = upload_rest(&upload, &upload_phase)) != LZB_RC_OK) return rc;
     trace.launched = trace.now();
     std::vector<uint8_t> copied;
     if (drain) {

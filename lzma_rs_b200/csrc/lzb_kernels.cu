@@ -40,10 +40,15 @@
 // stores across PCIe (measured on the north-star batch: the page-mirroring variant runs 16 % slower than the plain one).
 // Returns false if the bytes did not arrive within 5 s (LZB_E_INPUT_TIMEOUT: the host then waits for the upload and
 // decodes the stream again; it keeps a stalled copy from hanging the GPU).
-__device__ __forceinline__ bool input_arrived(const LzbItem* it, const unsigned long long* gate) {
+// gate[4] != 0: the upload follows the launch's QUEUE instead of the blob (one copy per stream, whole 128-byte lines, in
+// the order the warps will ask for them), and the watermark counts queue positions: the stream at position `slot` is
+// there once gate[0] > slot.  The static prefix -- the first stream of every warp -- then arrives first and in order,
+// instead of wherever its bytes happen to lie in the blob.
+__device__ __forceinline__ bool input_arrived(const LzbItem* it, const unsigned long long* gate, unsigned int slot) {
     if (it->kind == LZB_ITEM_PRESET || (it->flags & LZB_ITEM_F_IN_FROM_OUT)) return true;
     unsigned long long need = (it->in_off + it->in_len + gate[1] + 127ull) & ~127ull;
     if (need > gate[2]) need = gate[2];
+    if (gate[4]) need = (unsigned long long)slot + 1ull;
     const volatile unsigned long long* wm = gate;
     if (*wm < need) {
         unsigned long long t0, t1;
@@ -95,7 +100,7 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
         // a call's return value counts as divergent for the compiler, and a divergent `continue` here would put
         // reconvergence barriers (BSSY / BSYNC) around every branch of the bit loop below -- that, not the page stores, is
         // what made the round-1 mirror kernels 16 % slower than the plain ones (profiles/r02_e2e_timeline.md).
-        if (GATE && gate && !__shfl_sync(FULL_MASK, (int)input_arrived(items + idx, gate), 0)) {
+        if (GATE && gate && !__shfl_sync(FULL_MASK, (int)input_arrived(items + idx, gate, slot), 0)) {
             if (lane == 0) {
                 LzbResult r = {};
                 r.code = LZB_E_INPUT_TIMEOUT;

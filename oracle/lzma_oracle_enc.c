@@ -6,10 +6,14 @@
  * `lzma2_compress` / `xz_compress` emit stored chunks only (src/encode/lzma2.rs, src/encode/xz.rs).  Input is a byte
  * slice (what the reference's tests pass: &[u8] / Cursor), output a malloc'ed buffer.
  *
- * PARITY UNPINNED: the reference's tests hold no golden *compressed* vectors -- they only round-trip
- * (tests/lzma.rs:16-28, tests/lzma2.rs, tests/xz.rs:30-52).  This restatement is checked the same way (its output
- * decodes to the input with the decode oracle and with liblzma) plus one indirect known answer: half of
- * lzma_compress(small.txt) decodes to small.txt[..26] (src/decode/stream.rs:474-499).
+ * PARITY: pinned on the one golden COMPRESSED vector the reference holds that its own encoder produced -- the 23 bytes
+ * of tests/lzma.rs:197-207 (decompress_empty_world) = src/decode/stream.rs:393,444 are exactly lzma_compress(b"")
+ * (header, end marker, flush; tests/test_oracle_encoders.py::test_encoder_known_answer_empty_world) -- and on the
+ * indirect known answer of src/decode/stream.rs:474-499 (half of lzma_compress(small.txt) decodes to small.txt[..26]).
+ * Everything else the reference's tests do on the compress side is a round trip (tests/lzma.rs:16-28, tests/lzma2.rs,
+ * tests/xz.rs:30-52); the restatement is checked the same way (its output decodes to the input with the decode oracle
+ * and with liblzma, at every chunk-size edge).  No golden vector exists for literal payloads or for the stored-chunk
+ * formats: for those the pin is the round trip through two independent decoders.
  */
 #include <stdlib.h>
 #include <string.h>

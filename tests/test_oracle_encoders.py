@@ -37,6 +37,24 @@ def test_encoders_round_trip(i):
     assert lib.lzb_encode_bound(0, None, len(d)) >= len(oracle.lzma_compress(d))
 
 
+# The one golden COMPRESSED vector the reference holds whose producer is its own encoder: tests/lzma.rs:197-207
+# (decompress_empty_world) and src/decode/stream.rs:393,444 use the exact bytes lzma_compress emits for empty input --
+# 13-byte header with unknown size, the end marker (is_match=1, is_rep=0, len = 2 via choice=0 + 3-bit tree, pos_slot 63,
+# 26 direct bits, 4 align bits, all ones) and the 5-byte flush.  It pins the header writer, the range encoder's carry /
+# shift_low / flush logic and every probability model the marker touches.
+EMPTY_WORLD = b"\x5d\x00\x00\x80\x00\xff\xff\xff\xff\xff\xff\xff\xff\x00\x83\xff\xfb\xff\xff\xc0\x00\x00\x00"
+
+
+def test_encoder_known_answer_empty_world():
+    assert oracle.lzma_compress(b"") == EMPTY_WORLD
+    assert corpus.dumb_lzma(b"") == EMPTY_WORLD
+    # and the reference's hello-world vector (written by a real LZMA encoder, not by lzma_compress) still decodes
+    hello = (b"\x5d\x00\x00\x80\x00\xff\xff\xff\xff\xff\xff\xff\xff\x00\x24\x19\x49\x98\x6f\x10\x19\xc6\xd7\x31\xeb\x36"
+             b"\x50\xb2\x98\x48\xff\xfe\xa5\xb0\x00")
+    assert oracle.lzma_decompress(hello).out == b"Hello world\n"
+    assert oracle.lzma_compress(b"Hello world\n") != hello  # literals only: a different (longer) encoding of the same text
+
+
 def test_stream_known_answer():
     c = oracle.lzma_compress(SMALL)
     got = oracle.lzma_decompress(c[:len(c) // 2])  # truncated: error, but the window held 26 bytes (stream.rs:497-498)
