@@ -393,11 +393,7 @@ class Context:
         out_len = _np.zeros(n, dtype=_np.uint64)
         consumed = _np.zeros(n, dtype=_np.uint64)
         st = _np.zeros(n, dtype=_native.STATUS_DTYPE)
-        rc = self._lib.lzb_decode_batch(self._h, fmt, _C.byref(opt), blob.ctypes.data, in_off.ctypes.data, n,
-                                        out.ctypes.data, out_off.ctypes.data, out_len.ctypes.data,
-                                        consumed.ctypes.data, st.ctypes.data)
-        if rc != _native.RC_OK:
-            raise RuntimeError(f"lzb_decode_batch failed rc={rc}: {self.last_error()}")
+        self._decode_call(fmt, opt, blob, in_off, n, out, out_off, out_len, consumed, st)
         res = []
         for i in range(n):
             o = int(out_off[i])
@@ -405,6 +401,13 @@ class Context:
             disp = "" if st[i]["code"] == 0 else _native.format_status(self._lib, st[i])
             res.append(StreamResult(data, int(consumed[i]), st[i].copy(), disp))
         return res
+
+    def _decode_call(self, fmt, opt, blob, in_off, n, out, out_off, out_len, consumed, st):
+        rc = self._lib.lzb_decode_batch(self._h, fmt, _C.byref(opt), blob.ctypes.data, in_off.ctypes.data, n,
+                                        out.ctypes.data, out_off.ctypes.data, out_len.ctypes.data,
+                                        consumed.ctypes.data, st.ctypes.data)
+        if rc != _native.RC_OK:
+            raise RuntimeError(f"lzb_decode_batch failed rc={rc}: {self.last_error()}")
 
     def encode_batch(self, fmt, datas, options=None):
         """lzb_encode_batch: the reference's encoders over a batch (fmt 0: literal-only .lzma, 1: stored-chunk LZMA2,
@@ -449,7 +452,52 @@ class Context:
         return StreamResult(payload, consumed.value, row, disp)
 
 
+class MultiContext(Context):
+    """Several CUDA devices behind one handle (lzb_create_multi): `decode_batch` splits a host batch into contiguous
+    stream ranges with equal compressed bytes, every device uploads, decodes and returns its own range
+    (lzb_decode_batch_multi).  Everything else (single streams, encoders, scans) runs on the first device."""
+
+    def __init__(self, devices=None):
+        self._lib = _native.load()
+        m = _C.c_void_p()
+        if devices:
+            arr = (_C.c_int * len(devices))(*devices)
+            rc = self._lib.lzb_create_multi(_C.byref(m), arr, len(devices))
+        else:
+            rc = self._lib.lzb_create_multi(_C.byref(m), None, 0)
+        if rc != _native.RC_OK:
+            raise RuntimeError(f"lzb_create_multi failed (rc={rc}): no usable CUDA device -- lzma_rs_b200 has no CPU fallback")
+        self._m = m
+        self._h = _C.c_void_p(self._lib.lzb_multi_ctx(m, 0))
+        self.device_count = self._lib.lzb_multi_device_count(m)
+        self.last_split = None
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.lzb_destroy_multi(self._m)
+            self._m = self._h = None
+
+    def _decode_call(self, fmt, opt, blob, in_off, n, out, out_off, out_len, consumed, st):
+        split = _np.zeros(self.device_count + 1, dtype=_np.uint32)
+        rc = self._lib.lzb_decode_batch_multi(self._m, fmt, _C.byref(opt), blob.ctypes.data, in_off.ctypes.data, n,
+                                              out.ctypes.data, out_off.ctypes.data, out_len.ctypes.data,
+                                              consumed.ctypes.data, st.ctypes.data, split.ctypes.data)
+        self.last_split = split
+        if rc != _native.RC_OK:
+            raise RuntimeError(f"lzb_decode_batch_multi failed rc={rc}: {self._lib.lzb_multi_last_error(self._m).decode()}")
+
+
 _default_ctx = None
+
+
+def set_devices(devices=None):
+    """Spread the module-level `*_decompress_batch` calls over these CUDA devices (None / empty: every visible device).
+    Call before the first decode."""
+    global _default_ctx
+    if _default_ctx is not None:
+        raise RuntimeError("set_devices() must precede the first decode")
+    _default_ctx = MultiContext(devices)
+    return _default_ctx
 
 
 def _ctx():

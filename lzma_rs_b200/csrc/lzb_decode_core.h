@@ -935,8 +935,18 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                 } else {  // overlapping: the window replicates with period dist
                     // (identical index expressions on both sides: written as src[0] the compiler folds the load into the
                     // lane-dependent fill and loses the warp-uniformity of prev_byte downstream)
-                    prev_byte = src[i_last % dist];
-                    match_byte = src[i_next % dist];
+#if LZB_R2_COPY
+                    if (dist == 1) {
+                        // run of the previous byte (zero fills in real data; every symbol of BASELINE config 5): that
+                        // byte is already in a register -- it is the literal context -- so the next symbol's prev_byte /
+                        // match_byte need no memory round trip and no index reduced modulo dist
+                        match_byte = prev_byte;
+                    } else
+#endif
+                    {
+                        prev_byte = src[i_last % dist];
+                        match_byte = src[i_next % dist];
+                    }
                     if (WIDE == 1 && dist == 1) {  // run of one byte (BASELINE config 5): word-wide fill
                         warp_fill(dst, prev_byte, mlen, lane);
                     } else {

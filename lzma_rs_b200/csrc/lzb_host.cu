@@ -384,12 +384,17 @@ int arm_gate(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_lo, ui
 // the watermark counts positions of `queue` (the launch's order array; LZB_ORDER_PARK entries count), and replaces the
 // upload closure.  Every stream is one copy of whole 128-byte lines of the device blob (K1 reads its input through the
 // non-coherent path: a line must be complete before anything on it is read; neighbours share their boundary lines, which
-// are simply copied twice with the same bytes).  Phase 0 (before the kernel launch) enqueues the head of the queue, so
-// that the launch is not held up by ~10^5 driver calls; phase 1 (behind the launch) the rest, then `tail` (streams that
-// are not in K1's queue: the stored-chunk copy kernel's).
+// are simply copied twice with the same bytes).  Phase 0 (before the kernel launch) enqueues `tail` (streams that are not
+// in K1's queue: the stored-chunk copy kernel's, which has no gate and waits for ctx->upload_done -- that event has to be
+// recorded BEFORE the launch is enqueued, so these go first) and the head of the queue; phase 1 (behind the launch, so
+// that the launch is not held up by ~10^5 driver calls) the rest.  Returns 1 without touching the gate when the tail is
+// too large to go first (the caller keeps the blob-order upload).
 int arm_gate_queue(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_lo, uint64_t in_bytes,
                    const LzbItem* items, const std::vector<uint32_t>& queue, const std::vector<uint32_t>& tail,
                    std::function<int(int)>* upload) {
+    uint64_t tail_bytes = 0;
+    for (uint32_t i : tail) tail_bytes += items[i].in_len;
+    if (tail_bytes > (64ull << 20)) return 1;
     unsigned long long* hm = ctx->h_marks;
     hm[6] = 1;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.as<unsigned long long>() + 4, &hm[6], 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -412,6 +417,11 @@ int arm_gate_queue(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_
                                           ctx->copy_stream));
             return LZB_RC_OK;
         };
+        if (!phase) {
+            for (uint32_t i : t)
+                if (int rc = copy_stream_of(i)) return rc;
+            CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy_stream));
+        }
         const size_t from = phase ? head : 0, to = phase ? npos : head;
         for (size_t k = from; k < to; k++) {
             if (q[k] != LZB_ORDER_PARK)
@@ -421,11 +431,6 @@ int arm_gate_queue(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_
                 *mark = k + 1;
                 CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_gate.p, mark, 8, cudaMemcpyHostToDevice, ctx->copy_stream));
             }
-        }
-        if (phase ? head < npos : head == npos) {  // the last phase that has work
-            for (uint32_t i : t)
-                if (int rc = copy_stream_of(i)) return rc;
-            CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy_stream));
         }
         return LZB_RC_OK;
     };
@@ -653,7 +658,7 @@ class CudaExecutor : public lzb::Executor {
         if (gate_ && upload_phase == 0 && queue_upload.src && plan.order_big.empty() && !getenv("LZB_GATE_BYTES")) {
             rc = arm_gate_queue(ctx, queue_upload.src, queue_upload.lead, queue_upload.in_lo, queue_upload.in_bytes, items,
                                 plan.order_small, plan.order_stored, &before_first_kernel);
-            if (rc != LZB_RC_OK) return rc;
+            if (rc < 0) return rc;
         }
         if (drain && (rc = set_done_words(ctx, n, &gate)) != LZB_RC_OK) return rc;
         rc = launch_plan(ctx, s_, plan, ctx->d_items.as<LzbItem>(), ctx->d_order.as<uint32_t>(), in_, out_,
@@ -1249,7 +1254,7 @@ extern "C" int lzb_decode_batch_peer(lzb_ctx* ctx, int fmt, const lzb_options* o
         if ((rc = arm_gate(ctx, src_in + (in_off[0] - mis), lead, in_off[0], in_bytes, &upload, &d_gate))) return rc;
         if (b->plan.order_big.empty() && !getenv("LZB_GATE_BYTES") &&
             (rc = arm_gate_queue(ctx, src_in + (in_off[0] - mis), lead, in_off[0], in_bytes, b->items.data(), b->plan.order_small,
-                                 b->plan.order_stored, &upload)))
+                                 b->plan.order_stored, &upload)) < 0)
             return rc;
     } else {
         CUDA_TRY(ctx, cudaMemcpyAsync(d_in0, src_in + (in_off[0] - mis), in_bytes, cudaMemcpyDefault, ctx->stream));

@@ -9,6 +9,7 @@
 // is the error::Error variant.  Partial output is written before the throw, as in the reference.
 // Header-only; link with -llzma_b200.  There is no CPU fallback.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <istream>
 #include <iterator>
@@ -246,5 +247,88 @@ class Stream {
 };
 }  // namespace decompress
 inline void xz_decompress(std::istream& in, std::ostream& out) { detail::run(LZB_FMT_XZ, nullptr, in, out); }
+
+// ---- batch forms (n independent streams per call: what the benchmark drives) and several GPUs ----
+namespace batch {
+struct Input {
+    const uint8_t* data;
+    size_t size;
+};
+struct Result {
+    std::vector<uint8_t> data;  // what the reference would have written to its sink (also on error)
+    size_t consumed = 0;
+    lzb_status status{};
+    std::string error;  // "" or the reference's Display string
+    bool ok() const { return status.code == LZB_OK; }
+};
+namespace detail {
+inline lzb_multi*& multi() {
+    static lzb_multi* m = nullptr;
+    return m;
+}
+inline std::vector<Result> run(int fmt, const lzb_options* opt, const std::vector<Input>& in) {
+    const uint32_t n = (uint32_t)in.size();
+    std::vector<Result> res(n);
+    if (!n) return res;
+    std::vector<uint64_t> in_off(n + 1, 0), out_off(n + 1, 0), cap(n), out_len(n), consumed(n);
+    std::vector<uint8_t> blob;
+    for (uint32_t i = 0; i < n; i++) {
+        blob.insert(blob.end(), in[i].data, in[i].data + in[i].size);
+        in_off[i + 1] = blob.size();
+    }
+    blob.resize(blob.size() + 16);
+    lzb_ctx* c = multi() ? lzb_multi_ctx(multi(), 0) : lzma_rs::detail::ctx();
+    if (lzb_scan(c, fmt, opt, blob.data(), in_off.data(), n, cap.data()) != LZB_RC_OK) throw std::runtime_error("lzb_scan failed");
+    std::vector<uint32_t> pending(n);
+    for (uint32_t i = 0; i < n; i++) pending[i] = i;
+    while (!pending.empty()) {  // streams of unknown size that report LZB_E_CAPACITY are decoded again, larger
+        const uint32_t m = (uint32_t)pending.size();
+        std::vector<uint64_t> sin(m + 1, 0), sout(m + 1, 0), slen(m), scons(m);
+        std::vector<uint8_t> sblob;
+        for (uint32_t k = 0; k < m; k++) {
+            sblob.insert(sblob.end(), in[pending[k]].data, in[pending[k]].data + in[pending[k]].size);
+            sin[k + 1] = sblob.size();
+            sout[k + 1] = sout[k] + ((cap[pending[k]] + 15) & ~15ull);
+        }
+        sblob.resize(sblob.size() + 16);
+        std::vector<uint8_t> out(sout[m] + 16);
+        std::vector<lzb_status> st(m);
+        const int rc = multi() ? lzb_decode_batch_multi(multi(), fmt, opt, sblob.data(), sin.data(), m, out.data(), sout.data(),
+                                                        slen.data(), scons.data(), st.data(), nullptr)
+                               : lzb_decode_batch(c, fmt, opt, sblob.data(), sin.data(), m, out.data(), sout.data(), slen.data(),
+                                                  scons.data(), st.data());
+        if (rc != LZB_RC_OK) throw std::runtime_error(std::string("lzma_b200: ") + lzb_last_error(c));
+        std::vector<uint32_t> again;
+        for (uint32_t k = 0; k < m; k++) {
+            const uint32_t i = pending[k];
+            if (st[k].code == LZB_E_CAPACITY && cap[i] < 0xFFFFF000ull) {
+                cap[i] = std::min<uint64_t>(std::max<uint64_t>(cap[i] * 2, st[k].a0 + 65536), 0xFFFFF000ull);
+                again.push_back(i);
+                continue;
+            }
+            res[i].data.assign(out.begin() + sout[k], out.begin() + sout[k] + slen[k]);
+            res[i].consumed = scons[k];
+            res[i].status = st[k];
+            if (st[k].code != LZB_OK) {
+                char msg[512];
+                lzb_format_error(&st[k], msg, sizeof msg);
+                res[i].error = msg;
+            }
+        }
+        pending.swap(again);
+    }
+    return res;
+}
+}  // namespace detail
+// Spread the batch calls over these CUDA devices (empty = every visible device): lzb_create_multi.
+inline void set_devices(const std::vector<int>& devices) {
+    if (detail::multi()) lzb_destroy_multi(detail::multi());
+    if (lzb_create_multi(&detail::multi(), devices.empty() ? nullptr : devices.data(), (int)devices.size()) != LZB_RC_OK)
+        throw std::runtime_error("lzb_create_multi failed: no CUDA device (no CPU fallback)");
+}
+inline std::vector<Result> lzma_decompress_batch(const std::vector<Input>& in) { return detail::run(LZB_FMT_LZMA, nullptr, in); }
+inline std::vector<Result> lzma2_decompress_batch(const std::vector<Input>& in) { return detail::run(LZB_FMT_LZMA2, nullptr, in); }
+inline std::vector<Result> xz_decompress_batch(const std::vector<Input>& in) { return detail::run(LZB_FMT_XZ, nullptr, in); }
+}  // namespace batch
 
 }  // namespace lzma_rs

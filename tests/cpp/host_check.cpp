@@ -5,7 +5,9 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <iterator>
 #include <string>
+#include <vector>
 
 #include "lzma_rs_b200/host/lzma_rs.hpp"
 
@@ -23,6 +25,22 @@ int main(int argc, char** argv) {
             if (fmt == "rt-lzma") lzma_rs::lzma_decompress(packed, out);
             else if (fmt == "rt-lzma2") lzma_rs::lzma2_decompress(packed, out);
             else lzma_rs::xz_decompress(packed, out);
+            return 0;
+        }
+        if (fmt == "batch-lzma2") {  // batch form over two contexts (the same GPU twice): 7 copies, one of them truncated
+            std::vector<char> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+            std::vector<lzma_rs::batch::Input> ins(7, {reinterpret_cast<const uint8_t*>(buf.data()), buf.size()});
+            ins[3].size = buf.size() / 2;
+            lzma_rs::batch::set_devices({0, 0});
+            auto res = lzma_rs::batch::lzma2_decompress_batch(ins);
+            for (size_t i = 0; i < res.size(); i++) {
+                if (i == 3) {
+                    if (res[i].ok() || res[i].error != "io error: failed to fill whole buffer") return 5;
+                } else if (!res[i].ok() || res[i].consumed != buf.size() || res[i].data != res[0].data) {
+                    return 6;
+                }
+            }
+            out.write(reinterpret_cast<const char*>(res[0].data.data()), (std::streamsize)res[0].data.size());
             return 0;
         }
         if (fmt == "lzma") lzma_rs::lzma_decompress(in, out);

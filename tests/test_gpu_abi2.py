@@ -291,3 +291,22 @@ def test_drain_mode_many_streams(ctx):
     assert (st2["code"] == st["code"]).all() and (ol == out_len).all()
     for i in range(n):
         assert host[int(out_off[i]):int(out_off[i]) + int(ol[i])].tobytes() == outs[i], i
+
+
+def test_python_multi_context(ctx):
+    """lzma_rs_b200.MultiContext: the Python face of lzb_decode_batch_multi (same results as one context)."""
+    import lzma_rs_b200 as L
+    streams, plains = _mixed_batch(200, 66, 3_000, 60_000)
+    streams.append(streams[0][:33])
+    mc = L.MultiContext([0, 0, 0])
+    try:
+        got = mc.decode_batch(1, streams)
+        want = ctx.decode_batch(1, streams)
+        assert mc.device_count == 3 and mc.last_split[0] == 0 and mc.last_split[-1] == len(streams)
+        for g, w, p in zip(got, want, plains + [None]):
+            assert g.data == w.data and g.display == w.display and g.consumed == w.consumed
+            if p is not None:
+                assert g.ok and g.data == p
+        assert not got[-1].ok and got[-1].display == "io error: failed to fill whole buffer"
+    finally:
+        mc.close()

@@ -187,6 +187,10 @@ def test_cpp_host_mirror(ctx, golden, tmp_path):
         else:
             assert r.returncode == 0, (name, r.stderr)
     plain = corpus.mixed_text(31337, 150_000)
+    src, dst = tmp_path / "b.lzma2", tmp_path / "b.out"  # batch form + set_devices of the C++ mirror
+    src.write_bytes(corpus.raw_lzma2(plain, dict_size=1 << 20))
+    r = subprocess.run([str(exe), "batch-lzma2", str(src), str(dst)], capture_output=True, text=True)
+    assert r.returncode == 0 and dst.read_bytes() == plain, (r.returncode, r.stderr)
     for fmt in ("rt-lzma", "rt-lzma2", "rt-xz"):  # compress side of the C++ mirror: round trips
         src, dst = tmp_path / "plain.bin", tmp_path / "rt.bin"
         src.write_bytes(plain)
