@@ -936,10 +936,16 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     // (identical index expressions on both sides: written as src[0] the compiler folds the load into the
                     // lane-dependent fill and loses the warp-uniformity of prev_byte downstream)
 #if LZB_R2_COPY
+#ifdef LZB_FILL_SHORTCUT  // (experiment: the shortcut in the `fill` instantiation too, reconvergence barriers and all)
                     if (dist == 1) {
-                        // run of the previous byte (zero fills in real data; every symbol of BASELINE config 5): that
-                        // byte is already in a register -- it is the literal context -- so the next symbol's prev_byte /
-                        // match_byte need no memory round trip and no index reduced modulo dist
+#else
+                    if (WIDE != 1 && dist == 1) {
+#endif
+                        // run of the previous byte (zero fills in real data): that byte is already in a register -- it is
+                        // the literal context -- so the next symbol's prev_byte / match_byte need no memory round trip
+                        // and no index reduced modulo dist.  (Not in the `fill` instantiation: there the same shortcut
+                        // makes ptxas lose the warp-uniformity of prev_byte -- 85 BSSY pairs in the bit loop, whichever
+                        // way the fill value is produced; tools/check_sass.py.)
                         match_byte = prev_byte;
                     } else
 #endif
