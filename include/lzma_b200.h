@@ -242,6 +242,23 @@ int lzb_decode_batch_peer(lzb_ctx *ctx, int fmt, const lzb_options *opt, const u
                           uint32_t n, uint8_t *dst_out, const uint64_t *out_off, uint64_t *out_len, uint64_t *consumed,
                           lzb_status *st);
 
+/* ---- decompress::raw::{LzmaDecoder, Lzma2Decoder} (feature raw_decoder; src/decode/lzma.rs:597-648,
+ * src/decode/lzma2.rs:11-82): decoder OBJECTS whose DecoderState -- probabilities, state, rep[4], and for LZMA2 the
+ * properties of the last props reset -- survives from one decompress() call to the next until reset() is called; the
+ * output window does not (every call starts an empty one), exactly as in the reference.  The state lives in device
+ * memory; a call runs on a copy and commits it when the decode is over (so a capacity retry starts from the same state).
+ *   fmt = LZB_FMT_LZMA : lc/lp/pb/dict_size = LzmaParams (headerless payloads); the unpacked size of each call comes
+ *                        from opt (has_provided / provided = Option<u64>, as LzmaParams::unpacked_size / reset(Some(..)))
+ *   fmt = LZB_FMT_LZMA2: lc/lp/pb/dict_size ignored (DecoderState::new(0, 0, 0), lzma2.rs:24-34)
+ * After a call that ended in a decode error the reference's state is whatever the failing symbol left behind (its tests
+ * never reuse such a decoder); here a failed call commits nothing: the decoder is as it was before the call. */
+typedef struct lzb_raw lzb_raw;
+int lzb_raw_create(lzb_ctx *ctx, int fmt, uint32_t lc, uint32_t lp, uint32_t pb, uint32_t dict_size, lzb_raw **raw);
+int lzb_raw_reset(lzb_raw *raw); /* DecoderState::reset_state (lzma.rs:216-249) */
+int lzb_raw_decompress(lzb_raw *raw, const lzb_options *opt, const uint8_t *in, size_t in_len, uint8_t **out,
+                       size_t *out_len, size_t *consumed, lzb_status *st);
+void lzb_raw_destroy(lzb_raw *raw);
+
 /* Single-stream convenience for the Rust/C++ shim: scan + decode + (for end-marker .lzma) capacity
  * retry.  *out is malloc'ed by the library (free with lzb_free) and holds *out_len bytes -- on error
  * the reference's partial output.  Returns LZB_RC_*; *st has the decode status. */

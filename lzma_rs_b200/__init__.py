@@ -95,9 +95,8 @@ class decompress:  # namespace mirroring lzma_rs::decompress (src/decode/options
             return _native.make_options(self.unpacked_size.mode, self.unpacked_size.value, self.memlimit, self.allow_incomplete)
 
     class raw:  # namespace mirroring lzma_rs::decompress::raw (feature `raw_decoder`, src/lib.rs:29-35)
-        """Reusable raw decoders over the batch path.  The reference keeps a decoder's probability state between two
-        `decompress` calls unless `reset` is called in between; the GPU path decodes every stream from a fresh state,
-        so a second `decompress` without `reset()` raises instead of silently decoding something else."""
+        """Reusable raw decoders.  Like the reference's, a decoder keeps its probability state between two `decompress`
+        calls unless `reset` is called in between (the state lives in device memory: lzb_raw_* of the C ABI)."""
 
         class LzmaProperties:
             """LzmaProperties { lc, lp, pb } (src/decode/lzma.rs:41-66)."""
@@ -144,49 +143,53 @@ class decompress:  # namespace mirroring lzma_rs::decompress (src/decode/options
                 return cls(decompress.raw.LzmaProperties(lc, lp, pb), dict_size, size)
 
         class LzmaDecoder:
-            """raw::LzmaDecoder (src/decode/lzma.rs:597-648): `input` is a headerless LZMA stream."""
+            """raw::LzmaDecoder (src/decode/lzma.rs:597-648): `input` is a headerless LZMA stream.  Like the reference's,
+            the decoder keeps its DecoderState (probabilities, state, rep distances) from one `decompress` to the next
+            until `reset()`; every call starts an empty output window (lzb_raw_* in the C ABI)."""
 
             def __init__(self, params, memlimit=None, ctx=None):
                 params.properties.validate()
-                if params.dict_size < 0x1000:
-                    # LzmaParams::new does not clamp (only read_header does, lzma.rs:122-126); the GPU path's work item
-                    # is built from a header, which does
-                    raise error.InternalError("raw LzmaDecoder: dict_size < 4096 is not supported on the GPU path")
-                self.params, self.memlimit, self._ctx, self._used = params, memlimit, ctx, False
+                self.params, self.memlimit, self._ctx = params, memlimit, ctx
                 self._unpacked = params.unpacked_size
+                self._raw = None
+
+            def _handle(self):
+                if self._raw is None:
+                    pr = self.params.properties
+                    self._raw = (self._ctx or _ctx()).raw_new(_native.FMT_LZMA, pr.lc, pr.lp, pr.pb, self.params.dict_size)
+                return self._raw
 
             def reset(self, unpacked_size=...):
                 """reset(None) keeps the size; reset(Some(x)) replaces it (lzma.rs:620-627): pass nothing or x."""
                 if unpacked_size is not ...:
                     self._unpacked = unpacked_size
-                self._used = False
+                if self._raw is not None:
+                    self._raw.reset()
 
             def decompress(self, input, output=None):
-                if self._used:
-                    raise error.InternalError("raw LzmaDecoder: call reset() before decoding another stream")
-                self._used = True
-                pr = self.params.properties
-                head = bytes([(pr.pb * 5 + pr.lp) * 9 + pr.lc]) + self.params.dict_size.to_bytes(4, "little")
                 opts = decompress.Options(decompress.UnpackedSize.UseProvided(self._unpacked), self.memlimit)
                 data, reader = _read_all(input)
-                r = (self._ctx or _ctx()).decompress_one(_native.FMT_LZMA, head + data, opts)
-                return _deliver(r, len(data) + 5, 5, reader, output)
+                r = self._handle().decompress(data, opts)
+                return _deliver(r, len(data), 0, reader, output)
 
         class Lzma2Decoder:
-            """raw::Lzma2Decoder (src/decode/lzma2.rs:11-82)."""
+            """raw::Lzma2Decoder (src/decode/lzma2.rs:11-82); state kept between calls like the reference's."""
 
             def __init__(self, ctx=None):
-                self._ctx, self._used = ctx, False
+                self._ctx, self._raw = ctx, None
+
+            def _handle(self):
+                if self._raw is None:
+                    self._raw = (self._ctx or _ctx()).raw_new(_native.FMT_LZMA2, 0, 0, 0, 0)
+                return self._raw
 
             def reset(self):
-                self._used = False
+                if self._raw is not None:
+                    self._raw.reset()
 
             def decompress(self, input, output=None):
-                if self._used:
-                    raise error.InternalError("raw Lzma2Decoder: call reset() before decoding another stream")
-                self._used = True
                 data, reader = _read_all(input)
-                r = (self._ctx or _ctx()).decompress_one(_native.FMT_LZMA2, data, None)
+                r = self._handle().decompress(data, None)
                 return _deliver(r, len(data), 0, reader, output)
 
 
@@ -433,6 +436,10 @@ class Context:
             caps = _np.where(short, st["a0"], caps).astype(_np.uint64)
         return [out[int(out_off[i]):int(out_off[i]) + int(out_len[i])].tobytes() for i in range(n)]
 
+    def raw_new(self, fmt, lc, lp, pb, dict_size):
+        """A decompress::raw decoder object whose DecoderState lives on this context's device."""
+        return RawHandle(self, fmt, lc, lp, pb, dict_size)
+
     def decompress_one(self, fmt, data, options=None):
         """lzb_decompress_alloc: scan + decode (+ capacity retry for end-marker .lzma)."""
         opt = (options or decompress.Options())._native()
@@ -450,6 +457,50 @@ class Context:
         row["code"], row["kind"], row["a0"], row["a1"], row["a2"] = st.code, st.kind, st.a0, st.a1, st.a2
         disp = "" if st.code == 0 else _native.format_status(self._lib, st)
         return StreamResult(payload, consumed.value, row, disp)
+
+
+class RawHandle:
+    """One decompress::raw decoder object on the device (lzb_raw_create .. lzb_raw_destroy)."""
+
+    def __init__(self, ctx, fmt, lc, lp, pb, dict_size):
+        self._ctx, self._lib = ctx, ctx._lib
+        h = _C.c_void_p()
+        rc = self._lib.lzb_raw_create(ctx.handle, fmt, lc, lp, pb, dict_size, _C.byref(h))
+        if rc != _native.RC_OK:
+            raise error.InternalError(f"lzb_raw_create failed rc={rc}: {ctx.last_error()}")
+        self._h = h
+
+    def reset(self):
+        if self._lib.lzb_raw_reset(self._h) != _native.RC_OK:
+            raise RuntimeError(f"lzb_raw_reset failed: {self._ctx.last_error()}")
+
+    def decompress(self, data, options=None):
+        opt = (options or decompress.Options())._native()
+        buf = bytes(data)
+        out = _C.c_void_p()
+        out_len, consumed = _C.c_size_t(), _C.c_size_t()
+        st = _native.Status()
+        rc = self._lib.lzb_raw_decompress(self._h, _C.byref(opt), buf, len(buf), _C.byref(out), _C.byref(out_len),
+                                          _C.byref(consumed), _C.byref(st))
+        if rc != _native.RC_OK:
+            raise RuntimeError(f"lzb_raw_decompress failed rc={rc}: {self._ctx.last_error()}")
+        payload = _C.string_at(out, out_len.value) if out_len.value else b""
+        self._lib.lzb_free(out)
+        row = _np.zeros((), dtype=_native.STATUS_DTYPE)
+        row["code"], row["kind"], row["a0"], row["a1"], row["a2"] = st.code, st.kind, st.a0, st.a1, st.a2
+        disp = "" if st.code == 0 else _native.format_status(self._lib, st)
+        return StreamResult(payload, consumed.value, row, disp)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._ctx.handle:
+            self._lib.lzb_raw_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class MultiContext(Context):

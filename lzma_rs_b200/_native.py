@@ -46,7 +46,8 @@ EXPORTS = ["lzb_create", "lzb_destroy", "lzb_last_error", "lzb_abi_version", "lz
            "lzb_encode_bound", "lzb_encode_batch", "lzb_encode_batch_device",
            "lzb_scan_device", "lzb_batch_prepare_device", "lzb_create_multi", "lzb_destroy_multi", "lzb_multi_device_count",
            "lzb_multi_ctx", "lzb_multi_last_error", "lzb_decode_batch_multi", "lzb_ipc_export", "lzb_ipc_open",
-           "lzb_ipc_close", "lzb_decode_batch_peer"]
+           "lzb_ipc_close", "lzb_decode_batch_peer", "lzb_raw_create", "lzb_raw_reset", "lzb_raw_decompress",
+           "lzb_raw_destroy"]
 
 _lib = None
 
@@ -112,6 +113,11 @@ def bind(path):
         lib.lzb_ipc_open.argtypes = [vp, C.POINTER(IpcHandle), C.POINTER(vp)]
         lib.lzb_ipc_close.argtypes = [vp, vp]
         lib.lzb_decode_batch_peer.argtypes = [vp, C.c_int, C.POINTER(Options), vp, u64p, C.c_uint32, vp, u64p, u64p, u64p, vp]
+        lib.lzb_raw_create.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+        lib.lzb_raw_reset.argtypes = [vp]
+        lib.lzb_raw_decompress.argtypes = [vp, C.POINTER(Options), vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t),
+                                           C.POINTER(C.c_size_t), C.POINTER(Status)]
+        lib.lzb_raw_destroy.argtypes = [vp]
     return lib
 
 

@@ -536,7 +536,10 @@ LZB_DEV void mirror_to_host(const uint8_t* out, uint8_t* hout, uint32_t from, ui
 // WIDE  : 1 = word-wide run fills, 2 = 16-byte vector stored-chunk copies.  Kept out of the default instantiation (0)
 //         because K1 sits at the edge of the instruction cache: every extra path costs the common case 1-6 % even when
 //         it never executes (measured); the host selects the variant per batch from the framing scan.
-template <bool LIT_GLOBAL, bool MIRROR, int WIDE, class MainTab, class PlainTab, class MatchedTab>
+// CARRY : decompress::raw decoders -- the DecoderState a previous call left in an LzbCarry record (itp->host_out) is the
+//         starting point, and what this call leaves is written back (lzb_types.h).  LIT_GLOBAL form only: the record's
+//         literal area IS the kernel's literal workspace.
+template <bool LIT_GLOBAL, bool MIRROR, int WIDE, bool CARRY = false, class MainTab, class PlainTab, class MatchedTab>
 LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t* __restrict__ in_blob,
                                   uint8_t* out_blob, uint16_t* T, uint16_t* gws, const MainTab tab,
                                   const PlainTab plain, const MatchedTab matched, const LzbKC kc_in, uint32_t tab_lclp,
@@ -574,6 +577,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
     uint32_t lc = 0, lp = 0, pb = 0;
     uint32_t prev_byte = 0, match_byte = 0;
     bool mb_valid = false, tables_fresh = true;
+    bool carry_live = false;  // CARRY: the tables in shared memory are this decoder's state (written back at the end)
+    LzbCarry* const carry = CARRY ? reinterpret_cast<LzbCarry*>(itp->host_out) : nullptr;
     uint32_t dict_size = 0xFFFFFFFFu, mem_stop = 0xFFFFFFFFu;
     uint32_t target = 0;
     bool has_target = false;
@@ -612,9 +617,27 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
         target = (uint32_t)LZB_MIN(itp->unpacked, (uint64_t)0xFFFFFFFFu);  // sizes beyond the cap are never reached
         if (LZB_UNLIKELY(lc + lp > tab_lclp)) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
     }
-    fill_tables(T, tab_u16, lane);
-    // global part: the whole literal table (LIT_GLOBAL; .lzma props never change mid-stream) or the matched columns
-    fill_tables(gws, LIT_GLOBAL ? 0x300u << (lc + lp) : 0x200u << tab_lclp, lane);
+    if (CARRY && !carry->fresh) {  // continue from the state the previous decompress() call left
+        const uint16_t* saved = reinterpret_cast<const uint16_t*>(carry + 1);
+        for (uint32_t i = lane; i < (uint32_t)T_LIT; i += LZB_LANES) T[i] = saved[i];
+        LZB_SYNCWARP();
+        state = carry->state;
+        rep0 = carry->rep[0];
+        rep1 = carry->rep[1];
+        rep2 = carry->rep[2];
+        rep3 = carry->rep[3];
+        if (!is_lzma1) {
+            lc = carry->lc;
+            lp = carry->lp;
+            pb = carry->pb;
+        }
+        tables_fresh = false;
+    } else {
+        fill_tables(T, tab_u16, lane);
+        // global part: the whole literal table (LIT_GLOBAL; .lzma props never change mid-stream) or the matched columns
+        fill_tables(gws, LIT_GLOBAL ? 0x300u << (lc + lp) : 0x200u << tab_lclp, lane);
+    }
+    carry_live = CARRY;
 
     for (;;) {  // LZMA2 chunk loop (lzma2.rs:59-78); a .lzma stream is a single pass
         if (is_lzma1) {
@@ -673,7 +696,9 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                 if (LZB_UNLIKELY(lc + lp > tab_lclp)) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
                 if (!tables_fresh) {  // reset_state, lzma.rs:216-249
                     fill_tables(T, tab_u16, lane);
-                    fill_tables(gws, 0x200u << tab_lclp, lane);
+                    fill_tables(gws, LIT_GLOBAL ? 0x300u << (lc + lp) : 0x200u << tab_lclp, lane);
+                } else if (LIT_GLOBAL) {  // the table was initialised for the old lc+lp: cover the new one
+                    fill_tables(gws, 0x300u << (lc + lp), lane);
                 }
                 state = 0;
                 rep0 = rep1 = rep2 = rep3 = 0;
@@ -974,6 +999,21 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
 finish:
     LZB_SYNCWARP();
+    if (CARRY && carry_live) {  // what the next decompress() call of this decoder starts from
+        uint16_t* saved = reinterpret_cast<uint16_t*>(carry + 1);
+        for (uint32_t i = lane; i < (uint32_t)T_LIT; i += LZB_LANES) saved[i] = T[i];
+        if (lane == 0) {
+            carry->fresh = 0;
+            carry->state = state;
+            carry->rep[0] = rep0;
+            carry->rep[1] = rep1;
+            carry->rep[2] = rep2;
+            carry->rep[3] = rep3;
+            carry->lc = lc;
+            carry->lp = lp;
+            carry->pb = pb;
+        }
+    }
     if (MIRROR && hout && opos > mirrored) mirror_to_host(out, hout, mirrored, opos, lane);
     if (lane == 0) {
         uint64_t sink = opos;

@@ -44,6 +44,7 @@ LZB_K1_PROTO(lzb_decode_biglit_kernel);
 extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, const uint64_t*, const uint64_t*, uint32_t,
                                            LzbItem*, LzbScan*, uint64_t, uint64_t*);
 extern "C" __global__ void lzb_layout_kernel(const uint64_t*, uint32_t, uint64_t*);
+extern "C" __global__ void lzb_decode_carry_kernel(const LzbItem*, const uint8_t*, uint8_t*, LzbResult*, const LzbKC);
 extern "C" __global__ void lzb_crc_partial_kernel(const uint8_t*, const LzbCrcRange*, const uint32_t*, uint64_t,
                                                   uint32_t*, uint64_t*);
 extern "C" __global__ void lzb_stored_decode_kernel(const LzbItem*, const uint32_t*, const uint8_t*, uint8_t*, LzbResult*);
@@ -1420,6 +1421,148 @@ extern "C" int lzb_decompress_alloc(lzb_ctx* ctx, int fmt, const lzb_options* op
 }
 
 extern "C" void lzb_free(void* p) { free(p); }
+
+// ---- decompress::raw decoder objects: DecoderState kept in device memory between calls ----
+struct lzb_raw {
+    lzb_ctx* ctx = nullptr;
+    int fmt = 0;
+    uint32_t lc = 0, lp = 0, pb = 0, dict_size = 0, lclp_cap = 0;
+    DevBuf state[2];  // [cur]: the committed state; the other one is what the running call works on
+    int cur = 0;
+    DevBuf d_item, d_result;
+};
+
+static int raw_write_fresh(lzb_raw* r) {
+    lzb_ctx* ctx = r->ctx;
+    LzbCarry h = {};
+    h.fresh = 1;
+    h.lc = r->fmt == LZB_FMT_LZMA ? r->lc : 0;
+    h.lp = r->fmt == LZB_FMT_LZMA ? r->lp : 0;
+    h.pb = r->fmt == LZB_FMT_LZMA ? r->pb : 0;
+    h.lclp_cap = r->lclp_cap;
+    CUDA_TRY(ctx, cudaMemcpyAsync(r->state[r->cur].p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LZB_RC_OK;
+}
+
+extern "C" int lzb_raw_create(lzb_ctx* ctx, int fmt, uint32_t lc, uint32_t lp, uint32_t pb, uint32_t dict_size, lzb_raw** out) {
+    if (!out) return LZB_RC_BAD_ARG;
+    *out = nullptr;
+    if (!ctx || (fmt != LZB_FMT_LZMA && fmt != LZB_FMT_LZMA2)) return LZB_RC_BAD_ARG;
+    if (fmt == LZB_FMT_LZMA && (lc > 8 || lp > 4 || pb > 4 || dict_size == 0)) return LZB_RC_BAD_ARG;  // lzma.rs:62-66
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    lzb_raw* r = new lzb_raw();
+    r->ctx = ctx;
+    r->fmt = fmt;
+    r->lc = lc;
+    r->lp = lp;
+    r->pb = pb;
+    r->dict_size = dict_size;
+    r->lclp_cap = fmt == LZB_FMT_LZMA ? lc + lp : 4;  // LZMA2 chunks may switch to any lc + lp <= 4 (lzma2.rs:170-175)
+    const size_t bytes = (size_t)lzb_carry_bytes(r->lclp_cap);
+    int rc = LZB_RC_OK;
+    if (r->state[0].ensure(bytes) != cudaSuccess || r->state[1].ensure(bytes) != cudaSuccess ||
+        r->d_item.ensure(sizeof(LzbItem)) != cudaSuccess || r->d_result.ensure(sizeof(LzbResult)) != cudaSuccess)
+        rc = LZB_RC_OOM;
+    if (rc == LZB_RC_OK) rc = raw_write_fresh(r);
+    if (rc != LZB_RC_OK) {
+        lzb_raw_destroy(r);
+        return rc;
+    }
+    *out = r;
+    return LZB_RC_OK;
+}
+
+extern "C" int lzb_raw_reset(lzb_raw* r) {
+    if (!r) return LZB_RC_BAD_ARG;
+    std::lock_guard<std::mutex> lock(r->ctx->mu);
+    if (cudaSetDevice(r->ctx->device) != cudaSuccess) return LZB_RC_CUDA;
+    return raw_write_fresh(r);
+}
+
+extern "C" void lzb_raw_destroy(lzb_raw* r) {
+    if (!r) return;
+    if (r->ctx) cudaSetDevice(r->ctx->device);
+    r->state[0].release();
+    r->state[1].release();
+    r->d_item.release();
+    r->d_result.release();
+    delete r;
+}
+
+extern "C" int lzb_raw_decompress(lzb_raw* r, const lzb_options* opt, const uint8_t* in, size_t in_len, uint8_t** out,
+                                  size_t* out_len, size_t* consumed, lzb_status* st) {
+    if (!r || !out || !out_len || !consumed || !st || (in_len && !in)) return LZB_RC_BAD_ARG;
+    lzb_ctx* ctx = r->ctx;
+    *out = nullptr;
+    *out_len = *consumed = 0;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, ctx->d_in.ensure(in_len + 64));
+    if (in_len) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in.p, in, in_len, cudaMemcpyHostToDevice, s));
+    const uint64_t limit = 0xFFFFF000ull, bound = (uint64_t)in_len * 16384 + (1u << 20);
+    const bool sized = r->fmt == LZB_FMT_LZMA && opt && opt->has_provided;
+    uint64_t cap;
+    if (r->fmt == LZB_FMT_LZMA2) {
+        static const uint8_t empty = 0;
+        cap = std::min<uint64_t>(lzb::scan_lzma2(in ? in : &empty, in_len).unpacked, bound) + 16;
+    } else {
+        cap = sized && opt->provided <= bound ? opt->provided + 288 : (uint64_t)in_len * 8 + 65536;
+    }
+    const LzbKC kc = LZB_KC_INIT;
+    const int smem = ((int)T_LIT * 2 + 15) & ~15;
+    const size_t state_bytes = (size_t)lzb_carry_bytes(r->lclp_cap);
+    LzbResult res;
+    for (;;) {
+        cap = std::min(cap, limit);
+        CUDA_TRY(ctx, ctx->d_out.ensure(cap + 64));
+        const int work = 1 - r->cur;
+        CUDA_TRY(ctx, cudaMemcpyAsync(r->state[work].p, r->state[r->cur].p, state_bytes, cudaMemcpyDeviceToDevice, s));
+        LzbItem it = {};
+        it.in_off = 0;
+        it.in_len = in_len;
+        it.out_off = 0;
+        it.out_cap = cap;
+        it.unpacked = sized ? opt->provided : LZB_UNKNOWN_SIZE;
+        it.memlimit = opt && opt->has_memlimit ? opt->memlimit : ~0ull;
+        it.dict_size = r->dict_size;
+        it.kind = r->fmt == LZB_FMT_LZMA ? LZB_ITEM_LZMA : LZB_ITEM_LZMA2;
+        it.lc = (uint8_t)r->lc;
+        it.lp = (uint8_t)r->lp;
+        it.pb = (uint8_t)r->pb;
+        it.flags = LZB_ITEM_F_CARRY;
+        it.host_out = (uint64_t)(uintptr_t)r->state[work].p;
+        CUDA_TRY(ctx, cudaMemcpyAsync(r->d_item.p, &it, sizeof it, cudaMemcpyHostToDevice, s));
+        lzb_decode_carry_kernel<<<1, 32, smem, s>>>(r->d_item.as<LzbItem>(), ctx->d_in.as<uint8_t>(), ctx->d_out.as<uint8_t>(),
+                                                    r->d_result.as<LzbResult>(), kc);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaMemcpyAsync(&res, r->d_result.p, sizeof res, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        if (res.code == LZB_E_CAPACITY && cap < limit) {  // size unknown up front: same state, larger buffer
+            cap = std::max<uint64_t>(cap * 2, res.a0 + 65536);
+            continue;
+        }
+        if (res.code == LZB_OK) r->cur = work;  // commit; a failed call leaves the decoder as it was before the call
+        break;
+    }
+    lzb::status_from_result(res, st);
+    if (st->code == LZB_E_CAPACITY) {
+        st->code = LZB_E_UNSUPPORTED;
+        st->kind = LZB_KIND_INTERNAL;
+    }
+    uint8_t* buf = (uint8_t*)malloc((size_t)res.sink_len + 16);
+    if (!buf) return LZB_RC_OOM;
+    if (res.sink_len) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(buf, ctx->d_out.p, res.sink_len, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    }
+    *out = buf;
+    *out_len = (size_t)res.sink_len;
+    *consumed = (size_t)res.consumed;
+    return LZB_RC_OK;
+}
 
 extern "C" int lzb_crc_device(lzb_ctx* ctx, const uint8_t* d_data, const uint64_t* off, const uint64_t* len, uint32_t n,
                               uint32_t* crc32, uint64_t* crc64, void* cuda_stream) {

@@ -162,6 +162,23 @@ LZB_DEFINE_K1(lzb_decode_mirror_copy_kernel, false, true, 2, true, true)
 // .lzma streams with lc+lp > 4: literal table in a per-warp global workspace (ws + warp_id * ws_stride_u16).
 LZB_DEFINE_K1(lzb_decode_biglit_kernel, true, true, 1, false, true)
 
+// decompress::raw decoders (lzb_raw_*): one warp per CTA, one work item per CTA; the item's LzbCarry record holds the
+// DecoderState between calls and its literal area is the kernel's literal workspace.  A latency path (one stream per
+// call), not a throughput path: the reconvergence-barrier guard of tools/check_sass.py does not apply.
+extern "C" __global__ void __launch_bounds__(32, 1)
+    lzb_decode_carry_kernel(const LzbItem* __restrict__ items, const uint8_t* __restrict__ in_blob, uint8_t* out_blob,
+                            LzbResult* results, const __grid_constant__ LzbKC kc) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const LzbItem* it = items + blockIdx.x;
+    uint16_t* T = reinterpret_cast<uint16_t*>(smem);
+    const TabSm tab = {(uint32_t)__cvta_generic_to_shared(T)};
+    LzbCarry* carry = reinterpret_cast<LzbCarry*>(it->host_out);
+    uint16_t* lit = reinterpret_cast<uint16_t*>(carry + 1) + T_LIT;
+    const TabPtr plain = {lit}, matched = {lit + 0x100};
+    decode_item<true, false, 0, true>(it, in_blob, out_blob, T, lit, tab, plain, matched, kc, carry->lclp_cap, results + blockIdx.x, lane);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: per-stream scan -> work items (+ size summary).  One thread per stream.
 // ------------------------------------------------------------------------------------------------

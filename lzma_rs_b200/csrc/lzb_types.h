@@ -30,10 +30,26 @@ enum { LZB_ITEM_LZMA = 0, LZB_ITEM_LZMA2 = 1, LZB_ITEM_PRESET = 2 };
 // the framing scan found a well-formed LZMA2 stream made of stored chunks only (what the reference's own encoders write,
 // src/encode/lzma2.rs:4-26); `unpacked` then holds its size.  Such streams need no range decoder: they are routed to
 // the stored-chunk copy kernel (lzb_stored_decode_kernel) when their output fits the capacity.
-enum { LZB_ITEM_F_IN_FROM_OUT = 1, LZB_ITEM_F_OUT_SCRATCH = 2, LZB_ITEM_F_ALL_STORED = 4 };
+enum { LZB_ITEM_F_IN_FROM_OUT = 1, LZB_ITEM_F_OUT_SCRATCH = 2, LZB_ITEM_F_ALL_STORED = 4, LZB_ITEM_F_CARRY = 8 };
 #define LZB_UNKNOWN_SIZE 0xFFFFFFFFFFFFFFFFull
 // K1's order array: a warp whose pre-assigned first entry is this value takes no part in the launch (lzb_sched.h)
 #define LZB_ORDER_PARK 0xFFFFFFFFu
+
+// decompress::raw decoders keep their DecoderState between two decompress() calls (src/decode/lzma.rs:597-633,
+// src/decode/lzma2.rs:11-48): probabilities, state, rep[4] and -- for LZMA2 -- the properties of the last props reset; the
+// output window does NOT persist (every call builds a fresh LzCircularBuffer / LzAccumBuffer).  A work item with
+// LZB_ITEM_F_CARRY points (host_out) at this record in device memory; the carry kernel starts from it and writes it back.
+struct LzbCarry {
+    uint32_t fresh;     // 1: DecoderState::new / reset_state -- every probability 0x400, state 0, rep 0
+    uint32_t state;
+    uint32_t rep[4];
+    uint32_t lc, lp, pb;
+    uint32_t lclp_cap;  // the literal area below holds 0x300 << lclp_cap entries
+    uint32_t pad[6];
+    // uint16_t small[T_LIT];             the small tables in K1's layout (T_IS_MATCH .. T_REP_LEN)
+    // uint16_t lit[0x300 << lclp_cap];   the literal table in the reference's layout, used in place by the kernel
+};
+static inline uint64_t lzb_carry_bytes(uint32_t lclp_cap);
 
 // Per-stream result written by the decode kernel.
 struct LzbResult {
@@ -95,3 +111,6 @@ struct LzbKC {
 // the shared-memory footprint and raises residency from 14 to 28 streams per SM at lc+lp = 3.
 static inline uint32_t lzb_table_u16(uint32_t lclp) { return (uint32_t)T_LIT + (0x100u << lclp); }
 static inline uint32_t lzb_matched_u16(uint32_t lclp) { return 0x200u << lclp; }
+static inline uint64_t lzb_carry_bytes(uint32_t lclp_cap) {
+    return sizeof(LzbCarry) + (uint64_t)T_LIT * 2 + ((uint64_t)0x300 << lclp_cap) * 2;
+}

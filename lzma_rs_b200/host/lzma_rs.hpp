@@ -136,9 +136,7 @@ inline void lzma_compress(std::istream& in, std::ostream& out) { lzma_compress_w
 inline void lzma2_compress(std::istream& in, std::ostream& out) { detail::encode(LZB_FMT_LZMA2, nullptr, in, out); }
 inline void xz_compress(std::istream& in, std::ostream& out) { detail::encode(LZB_FMT_XZ, nullptr, in, out); }
 
-// lzma_rs::decompress::raw (feature `raw_decoder`, src/lib.rs:29-35).  The reference keeps a decoder's probability
-// state between two decompress() calls unless reset() is called; the GPU path always starts from a fresh state, so a
-// second decompress() without reset() throws instead of decoding something else.
+// lzma_rs::decompress::raw (feature `raw_decoder`, src/lib.rs:29-35): decoder objects over lzb_raw_*.
 namespace decompress {
 namespace raw {
 struct LzmaProperties {  // lzma.rs:41-66
@@ -152,51 +150,75 @@ struct LzmaParams {  // LzmaParams::new, lzma.rs:68-93
     uint32_t dict_size;
     std::optional<uint64_t> unpacked_size;
 };
+namespace detail {
+// One decode through a raw decoder object (lzb_raw_decompress): output, error and "unread trailing bytes stay" like run().
+inline void run_raw(lzb_raw* r, const lzb_options* opt, std::istream& in, std::ostream& out) {
+    std::vector<uint8_t> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    uint8_t* o = nullptr;
+    size_t out_len = 0, consumed = 0;
+    lzb_status st{};
+    int rc = lzb_raw_decompress(r, opt, buf.data(), buf.size(), &o, &out_len, &consumed, &st);
+    if (rc != LZB_RC_OK) throw std::runtime_error(std::string("lzma_b200: ") + lzb_last_error(lzma_rs::detail::ctx()));
+    if (out_len) out.write(reinterpret_cast<const char*>(o), (std::streamsize)out_len);
+    lzb_free(o);
+    if (st.code != LZB_OK) {
+        char msg[512];
+        lzb_format_error(&st, msg, sizeof msg);
+        throw error::Error(static_cast<error::Kind>(st.kind), msg, st);
+    }
+    in.clear();
+    in.seekg((std::streamoff)consumed - (std::streamoff)buf.size(), std::ios::cur);
+    out.flush();
+}
+}  // namespace detail
+// Like the reference's, both decoders keep their DecoderState (probabilities, state, rep distances; LZMA2: the properties
+// of the last props reset) from one decompress() to the next until reset(); the state lives on the device (lzb_raw_*).
 class LzmaDecoder {  // lzma.rs:597-648: `in` is a headerless LZMA stream
    public:
     LzmaDecoder(const LzmaParams& p, std::optional<size_t> memlimit) : p_(p), memlimit_(memlimit), size_(p.unpacked_size) {
         p.properties.validate();
-        if (p.dict_size < 0x1000) throw std::invalid_argument("raw LzmaDecoder: dict_size < 4096 is not supported on the GPU path");
+        if (lzb_raw_create(lzma_rs::detail::ctx(), LZB_FMT_LZMA, p.properties.lc, p.properties.lp, p.properties.pb, p.dict_size,
+                           &raw_) != LZB_RC_OK)
+            throw std::invalid_argument("raw LzmaDecoder: lzb_raw_create failed");
     }
-    void reset() { used_ = false; }
-    void reset(std::optional<uint64_t> unpacked_size) { size_ = unpacked_size, used_ = false; }
+    ~LzmaDecoder() { lzb_raw_destroy(raw_); }
+    LzmaDecoder(const LzmaDecoder&) = delete;
+    LzmaDecoder& operator=(const LzmaDecoder&) = delete;
+    void reset() { lzb_raw_reset(raw_); }  // reset(None): the size stays (lzma.rs:620-627)
+    void reset(std::optional<uint64_t> unpacked_size) {
+        size_ = unpacked_size;
+        lzb_raw_reset(raw_);
+    }
     void decompress(std::istream& in, std::ostream& out) {
-        if (used_) throw std::logic_error("raw LzmaDecoder: call reset() before decoding another stream");
-        used_ = true;
-        // the work item is built from a 5-byte header (props, dict size) with UnpackedSize::UseProvided
-        std::string head(5, '\0');
-        head[0] = (char)((p_.properties.pb * 5 + p_.properties.lp) * 9 + p_.properties.lc);
-        for (int k = 0; k < 4; k++) head[1 + k] = (char)(p_.dict_size >> (8 * k));
-        std::string body((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
-        std::istringstream whole(head + body);
         lzb_options n{};
         n.unpacked_mode = 2;
         n.has_provided = size_.has_value();
         n.provided = size_.value_or(0);
         n.has_memlimit = memlimit_.has_value();
         n.memlimit = memlimit_.value_or(0);
-        detail::run(LZB_FMT_LZMA, &n, whole, out);
-        in.clear();
-        in.seekg((std::streamoff)whole.tellg() - 5 - (std::streamoff)body.size(), std::ios::cur);
+        detail::run_raw(raw_, &n, in, out);
     }
 
    private:
     LzmaParams p_;
     std::optional<size_t> memlimit_;
     std::optional<uint64_t> size_;
-    bool used_ = false;
+    lzb_raw* raw_ = nullptr;
 };
 class Lzma2Decoder {  // lzma2.rs:11-82
    public:
-    void reset() { used_ = false; }
-    void decompress(std::istream& in, std::ostream& out) {
-        if (used_) throw std::logic_error("raw Lzma2Decoder: call reset() before decoding another stream");
-        used_ = true;
-        detail::run(LZB_FMT_LZMA2, nullptr, in, out);
+    Lzma2Decoder() {
+        if (lzb_raw_create(lzma_rs::detail::ctx(), LZB_FMT_LZMA2, 0, 0, 0, 0, &raw_) != LZB_RC_OK)
+            throw std::runtime_error("raw Lzma2Decoder: lzb_raw_create failed");
     }
+    ~Lzma2Decoder() { lzb_raw_destroy(raw_); }
+    Lzma2Decoder(const Lzma2Decoder&) = delete;
+    Lzma2Decoder& operator=(const Lzma2Decoder&) = delete;
+    void reset() { lzb_raw_reset(raw_); }
+    void decompress(std::istream& in, std::ostream& out) { detail::run_raw(raw_, nullptr, in, out); }
 
    private:
-    bool used_ = false;
+    lzb_raw* raw_ = nullptr;
 };
 }  // namespace raw
 }  // namespace decompress

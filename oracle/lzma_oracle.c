@@ -1004,12 +1004,23 @@ static int lzma2_parse_lzma(decstate *st, lzbuf *accum, view *in, uint8_t status
     return ds_process(st, accum, &rc, e);
 }
 
+/* Lzma2Decoder::decompress, lzma2.rs:52-82, on a DecoderState that outlives the call (the raw decoder object) */
+static int lzma2_decompress_state(view *in, bytes *sink, decstate *stp, lzo_error *e);
+
 /* Lzma2Decoder::new + decompress, lzma2.rs:23-34, 52-82 */
 static int lzma2_decompress_view(view *in, bytes *sink, lzo_error *e) {
     decstate st;
+    int rcode;
+    ds_new(&st, 0, 0, 0, 0, 0);
+    rcode = lzma2_decompress_state(in, sink, &st, e);
+    ds_drop(&st);
+    return rcode;
+}
+
+static int lzma2_decompress_state(view *in, bytes *sink, decstate *stp, lzo_error *e) {
     lzbuf accum;
     int rcode = 0;
-    ds_new(&st, 0, 0, 0, 0, 0);
+#define st (*stp)
     lzb_init_accum(&accum, sink, (size_t)-1);
     for (;;) {
         uint8_t status;
@@ -1028,7 +1039,7 @@ static int lzma2_decompress_view(view *in, bytes *sink, lzo_error *e) {
     }
     if (!rcode) lzb_finish(&accum); /* lzma2.rs:80 */
     lzb_drop(&accum);
-    ds_drop(&st);
+#undef st
     return rcode;
 }
 
@@ -1461,6 +1472,73 @@ int lzo_xz_decompress(const uint8_t *in, size_t in_len, lzo_result *res) {
     pthread_once(&crc_once, crc_init);
     return finish_result(res, &r, &sink, xz_decompress_impl(&r, &sink, &res->err));
 }
+/* ------------------------------------------------------------------------------------------
+ * decompress::raw::{LzmaDecoder, Lzma2Decoder} as OBJECTS (feature raw_decoder): the DecoderState lives in the
+ * decoder and survives from one decompress() to the next (lzma.rs:597-648, lzma2.rs:11-82); every call builds a
+ * fresh output buffer.  Used to check the product's lzb_raw_* entry points.
+ * ---------------------------------------------------------------------------------------- */
+struct lzo_raw {
+    int fmt; /* 0 LzmaDecoder, 1 Lzma2Decoder */
+    decstate st;
+    uint32_t lc, lp, pb, dict_size;
+    size_t memlimit;
+};
+lzo_raw *lzo_raw_new(int fmt, uint32_t lc, uint32_t lp, uint32_t pb, uint32_t dict_size, int has_unpacked,
+                     uint64_t unpacked, int has_memlimit, uint64_t memlimit) {
+    lzo_raw *r = (lzo_raw *)calloc(1, sizeof *r);
+    r->fmt = fmt;
+    r->lc = lc;
+    r->lp = lp;
+    r->pb = pb;
+    r->dict_size = dict_size;
+    r->memlimit = has_memlimit ? (size_t)memlimit : (size_t)-1; /* lzma.rs:610 */
+    if (fmt == 0)
+        ds_new(&r->st, lc, lp, pb, has_unpacked, unpacked); /* LzmaDecoder::new, lzma.rs:607-613 */
+    else
+        ds_new(&r->st, 0, 0, 0, 0, 0); /* Lzma2Decoder::new, lzma2.rs:23-34 */
+    pthread_once(&crc_once, crc_init);
+    return r;
+}
+/* LzmaDecoder::reset(unpacked_size: Option<Option<u64>>), lzma.rs:620-627; Lzma2Decoder::reset, lzma2.rs:41-48 */
+void lzo_raw_reset(lzo_raw *r, int set_unpacked, int has_unpacked, uint64_t unpacked) {
+    if (r->fmt == 0) {
+        ds_reset_state(&r->st, r->lc, r->lp, r->pb);
+        if (set_unpacked) {
+            r->st.has_unpacked = has_unpacked;
+            r->st.unpacked_size = unpacked;
+        }
+    } else {
+        ds_reset_state(&r->st, 0, 0, 0);
+    }
+}
+int lzo_raw_decompress(lzo_raw *r, const uint8_t *in, size_t in_len, lzo_result *res) {
+    reader rd = {in, 0, in_len};
+    bytes sink = {0, 0, 0};
+    view v = view_all(&rd);
+    int rcode;
+    memset(res, 0, sizeof *res);
+    if (r->fmt == 0) { /* LzmaDecoder::decompress, lzma.rs:635-648 */
+        lzbuf out;
+        rangedec rc;
+        lzb_init_circ(&out, &sink, r->dict_size, r->memlimit);
+        if (rc_new(&rc, v)) {
+            rcode = fail(&res->err, LZO_ERR_LZMA, "LZMA stream too short: " IO_EOF_MSG);
+        } else {
+            rcode = ds_process(&r->st, &out, &rc, &res->err);
+            if (!rcode) lzb_finish(&out);
+        }
+        lzb_drop(&out);
+    } else {
+        rcode = lzma2_decompress_state(&v, &sink, &r->st, &res->err);
+    }
+    return finish_result(res, &rd, &sink, rcode);
+}
+void lzo_raw_free(lzo_raw *r) {
+    if (!r) return;
+    ds_drop(&r->st);
+    free(r);
+}
+
 void lzo_result_free(lzo_result *res) {
     free(res->out);
     res->out = NULL;

@@ -71,6 +71,14 @@ int lzo_lzma2_decompress(const uint8_t *in, size_t in_len, lzo_result *res);
 int lzo_xz_decompress(const uint8_t *in, size_t in_len, lzo_result *res);
 void lzo_result_free(lzo_result *res);
 
+/* decompress::raw decoder objects: the DecoderState survives between decompress() calls (lzma.rs:597-648, lzma2.rs:11-82) */
+typedef struct lzo_raw lzo_raw;
+lzo_raw *lzo_raw_new(int fmt, uint32_t lc, uint32_t lp, uint32_t pb, uint32_t dict_size, int has_unpacked,
+                     uint64_t unpacked, int has_memlimit, uint64_t memlimit);
+void lzo_raw_reset(lzo_raw *r, int set_unpacked, int has_unpacked, uint64_t unpacked);
+int lzo_raw_decompress(lzo_raw *r, const uint8_t *in, size_t in_len, lzo_result *res);
+void lzo_raw_free(lzo_raw *r);
+
 /* Formats the Display string of the error ("lzma error: ..."), src/error.rs:28-37. */
 void lzo_error_display(const lzo_error *err, char *buf, size_t buf_len);
 

@@ -548,9 +548,10 @@ pub fn xz_compress<R: io::BufRead, W: io::Write>(input: &mut R, output: &mut W) 
     encode(FMT_XZ, &LzbCompressOptions::default(), input, output)
 }
 
-/// `lzma_rs::decompress::raw` (feature `raw_decoder`, src/lib.rs:29-35) over the batch path.  The reference keeps a
-/// decoder's probability state between two `decompress` calls unless `reset` is called; the GPU path always starts
-/// from a fresh state, so a second `decompress` without `reset` is an error instead of a different decode.
+/// `lzma_rs::decompress::raw` (feature `raw_decoder`, src/lib.rs:29-35) over `lzb_raw_*`: decoder objects whose
+/// DecoderState -- probabilities, state, rep distances, and for LZMA2 the properties of the last props reset -- lives on
+/// the device and survives from one `decompress` to the next until `reset`, like the reference's
+/// (src/decode/lzma.rs:597-648, src/decode/lzma2.rs:11-82); every call starts an empty output window.
 pub mod raw {
     use super::*;
     /// src/decode/lzma.rs:41-66
@@ -564,48 +565,103 @@ pub mod raw {
             LzmaParams { properties, dict_size, unpacked_size }
         }
     }
-    fn stale() -> error::Error {
-        error::Error::IoError(io::Error::new(io::ErrorKind::Other, "raw decoder: call reset() before decoding another stream"))
+    #[repr(C)]
+    pub(crate) struct LzbRaw { _private: [u8; 0] }
+    extern "C" {
+        fn lzb_raw_create(ctx: *mut LzbCtx, fmt: c_int, lc: u32, lp: u32, pb: u32, dict_size: u32, raw: *mut *mut LzbRaw) -> c_int;
+        fn lzb_raw_reset(raw: *mut LzbRaw) -> c_int;
+        fn lzb_raw_decompress(
+            raw: *mut LzbRaw, opt: *const LzbOptions, input: *const u8, in_len: usize, out: *mut *mut u8,
+            out_len: *mut usize, consumed: *mut usize, st: *mut LzbStatus,
+        ) -> c_int;
+        fn lzb_raw_destroy(raw: *mut LzbRaw);
+    }
+    struct Handle(*mut LzbRaw);
+    unsafe impl Send for Handle {}
+    impl Drop for Handle {
+        fn drop(&mut self) { unsafe { lzb_raw_destroy(self.0) } }
+    }
+    fn create(fmt: c_int, lc: u32, lp: u32, pb: u32, dict_size: u32) -> error::Result<Handle> {
+        let mut h: *mut LzbRaw = std::ptr::null_mut();
+        let rc = with_ctx(|c| unsafe { lzb_raw_create(c, fmt, lc, lp, pb, dict_size, &mut h) })?;
+        if rc != 0 {
+            return Err(error::Error::IoError(io::Error::new(io::ErrorKind::Other, format!("lzb_raw_create failed: {}", rc))));
+        }
+        Ok(Handle(h))
+    }
+    /// One decode through the decoder object.  The raw decoders take a reader like the one-shot functions; in-memory
+    /// readers keep their trailing bytes unread (exactly `consumed` bytes are taken).
+    fn run_raw<R: io::BufRead, W: io::Write>(h: &Handle, opt: &LzbOptions, input: &mut R, output: &mut W) -> error::Result<()> {
+        let first: Vec<u8> = input.fill_buf()?.to_vec();
+        let n = first.len();
+        let mut buf = first;
+        let mut whole = false;
+        loop {
+            let mut out: *mut u8 = std::ptr::null_mut();
+            let (mut out_len, mut consumed) = (0usize, 0usize);
+            let mut st = LzbStatus::default();
+            let rc = unsafe { lzb_raw_decompress(h.0, opt, buf.as_ptr(), buf.len(), &mut out, &mut out_len, &mut consumed, &mut st) };
+            if rc != 0 {
+                return Err(error::Error::IoError(io::Error::new(io::ErrorKind::Other, format!("lzma_b200 call failed: {}", rc))));
+            }
+            let data = if out_len > 0 { unsafe { std::slice::from_raw_parts(out, out_len) }.to_vec() } else { Vec::new() };
+            unsafe { lzb_free(out as *mut c_void) };
+            if ran_out_of_input(&st) && !whole {
+                // a streaming reader whose buffer ended inside the stream: a failed call commits nothing to the decoder's
+                // state, so decode again with the whole reader (documented: INTEGRATION.md section 3)
+                input.consume(n);
+                input.read_to_end(&mut buf)?;
+                whole = true;
+                continue;
+            }
+            if !whole {
+                input.consume(consumed.min(n));
+            }
+            if !data.is_empty() {
+                output.write_all(&data)?;
+            }
+            if st.code != 0 {
+                return Err(to_error(&st));
+            }
+            output.flush()?;
+            return Ok(());
+        }
     }
     /// src/decode/lzma.rs:597-648
-    pub struct LzmaDecoder { params: LzmaParams, memlimit: Option<usize>, used: bool }
+    pub struct LzmaDecoder { params: LzmaParams, memlimit: Option<usize>, handle: Handle }
     impl LzmaDecoder {
         pub fn new(params: LzmaParams, memlimit: Option<usize>) -> error::Result<LzmaDecoder> {
             let p = params.properties;
             assert!(p.lc <= 8 && p.lp <= 4 && p.pb <= 4);
-            if params.dict_size < 0x1000 {
-                return Err(error::Error::IoError(io::Error::new(io::ErrorKind::Other, "dict_size < 4096 is not supported on the GPU path")));
-            }
-            Ok(LzmaDecoder { params, memlimit, used: false })
+            let handle = create(FMT_LZMA, p.lc, p.lp, p.pb, params.dict_size)?;
+            Ok(LzmaDecoder { params, memlimit, handle })
         }
+        /// src/decode/lzma.rs:620-627
         pub fn reset(&mut self, unpacked_size: Option<Option<u64>>) {
             if let Some(u) = unpacked_size { self.params.unpacked_size = u; }
-            self.used = false;
+            unsafe { lzb_raw_reset(self.handle.0) };
         }
         pub fn decompress<W: io::Write, R: io::BufRead>(&mut self, input: &mut R, output: &mut W) -> error::Result<()> {
-            if self.used { return Err(stale()); }
-            self.used = true;
-            let p = self.params.properties;
-            let mut head = vec![((p.pb * 5 + p.lp) * 9 + p.lc) as u8];
-            head.extend_from_slice(&self.params.dict_size.to_le_bytes());
             let opts = decompress::Options {
                 unpacked_size: decompress::UnpackedSize::UseProvided(self.params.unpacked_size),
                 memlimit: self.memlimit, allow_incomplete: false,
             };
-            run(FMT_LZMA, &options(&opts), &mut io::Read::chain(&head[..], input), output)
+            run_raw(&self.handle, &options(&opts), input, output)
         }
     }
     /// src/decode/lzma2.rs:11-82
-    #[derive(Default)]
-    pub struct Lzma2Decoder { used: bool }
+    pub struct Lzma2Decoder { handle: Handle }
     impl Lzma2Decoder {
-        pub fn new() -> Lzma2Decoder { Lzma2Decoder { used: false } }
-        pub fn reset(&mut self) { self.used = false; }
-        pub fn decompress<W: io::Write, R: io::BufRead>(&mut self, input: &mut R, output: &mut W) -> error::Result<()> {
-            if self.used { return Err(stale()); }
-            self.used = true;
-            run(FMT_LZMA2, &LzbOptions::default(), input, output)
+        pub fn new() -> Lzma2Decoder {
+            Lzma2Decoder { handle: create(FMT_LZMA2, 0, 0, 0, 0).expect("lzb_raw_create") }
         }
+        pub fn reset(&mut self) { unsafe { lzb_raw_reset(self.handle.0) }; }
+        pub fn decompress<W: io::Write, R: io::BufRead>(&mut self, input: &mut R, output: &mut W) -> error::Result<()> {
+            run_raw(&self.handle, &LzbOptions::default(), input, output)
+        }
+    }
+    impl Default for Lzma2Decoder {
+        fn default() -> Self { Self::new() }
     }
 }
 

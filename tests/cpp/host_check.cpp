@@ -57,11 +57,17 @@ int main(int argc, char** argv) {
                                    size == ~0ull ? std::nullopt : std::optional<uint64_t>(size)};
             raw::LzmaDecoder dec(params, std::nullopt);
             dec.decompress(in, out);
-            try {
-                dec.decompress(in, out);
-                return 4;  // must not decode again without reset()
-            } catch (const std::logic_error&) {
-            }
+            // decoding again without reset() continues from the carried DecoderState like the reference (lzma.rs:597-633);
+            // after reset() the same payload decodes to the same bytes again
+            in.clear();
+            in.seekg(13);
+            std::ostringstream again;
+            dec.reset();
+            dec.decompress(in, again);
+            std::ifstream first(argv[3], std::ios::binary);
+            out.flush();
+            std::string a((std::istreambuf_iterator<char>(first)), std::istreambuf_iterator<char>());
+            if (again.str() != a) return 4;
         }
         else lzma_rs::xz_decompress(in, out);
     } catch (const lzma_rs::error::Error& e) {

@@ -35,6 +35,12 @@ def lib():
         _lib.emul_sched_plan.restype = C.c_uint32
         _lib.emul_sched_simulate.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_uint32]
         _lib.emul_sched_simulate.restype = C.c_double
+        _lib.emul_raw_create.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        _lib.emul_raw_create.restype = vp
+        _lib.emul_raw_reset.argtypes = [vp]
+        _lib.emul_raw_destroy.argtypes = [vp]
+        _lib.emul_raw_decompress.argtypes = [vp, C.POINTER(_native.Options), C.c_char_p, C.c_uint64, vp, C.c_uint64, vp, vp,
+                                             C.POINTER(_native.Status)]
         _lib.lzb_format_error.argtypes = [C.POINTER(_native.Status), C.c_char_p, C.c_size_t]
         _lib.lzb_format_error.restype = C.c_size_t
     return _lib
@@ -95,3 +101,39 @@ def sched_simulate(work, counts=None, sms=148, warps=28):
         return L.emul_sched_simulate(w.ctypes.data, len(w), None, 0, sms, warps)
     c = np.ascontiguousarray(counts, dtype=np.uint32)
     return L.emul_sched_simulate(w.ctypes.data, len(w), c.ctypes.data, len(c), sms, warps)
+
+
+class RawHandle:
+    """CPU-tier twin of lzma_rs_b200.RawHandle (lzb_raw_*): K1's CARRY path through the host emulation."""
+
+    def __init__(self, fmt, lc, lp, pb, dict_size):
+        self._h = lib().emul_raw_create(fmt, lc, lp, pb, dict_size)
+
+    def reset(self):
+        lib().emul_raw_reset(self._h)
+
+    def decompress(self, data, options=None):
+        L = lib()
+        opt = options._native() if options is not None else _native.make_options()
+        data = bytes(data)
+        cap = max(1 << 16, len(data) * 8)
+        while True:
+            out = np.zeros(cap + 16, dtype=np.uint8)
+            out_len, consumed = C.c_uint64(), C.c_uint64()
+            st = _native.Status()
+            code = L.emul_raw_decompress(self._h, C.byref(opt), data, len(data), out.ctypes.data, cap, C.byref(out_len),
+                                         C.byref(consumed), C.byref(st))
+            if code == -1 and cap < (1 << 30):
+                cap *= 4
+                continue
+            break
+        row = np.zeros((), dtype=_native.STATUS_DTYPE)
+        row["code"], row["kind"], row["a0"], row["a1"], row["a2"] = st.code, st.kind, st.a0, st.a1, st.a2
+        disp = "" if st.code == 0 else _native.format_status(L, st)
+        return Result(out[:out_len.value].tobytes(), consumed.value, row, disp)
+
+    def __del__(self):
+        try:
+            lib().emul_raw_destroy(self._h)
+        except Exception:
+            pass

@@ -136,3 +136,62 @@ extern "C" double emul_sched_simulate(const double* work, uint32_t n, const uint
     std::vector<uint32_t> c(counts, counts + n_counts);
     return lzb_sched::simulate(w, &c, sms, warps);
 }
+
+// ---- decompress::raw decoder objects: K1's CARRY path on the CPU (the state record lives in host memory here) ----
+// Same contract as lzb_raw_create / reset / decompress of the C ABI, minus the device: one record per decoder, every
+// call runs decode_item<LIT_GLOBAL, ..., CARRY> on a copy and commits it unless the output capacity was too small.
+struct EmulRaw {
+    int fmt;
+    uint32_t lc, lp, pb, dict_size, lclp_cap;
+    std::vector<uint8_t> state;
+};
+static void emul_raw_fresh(EmulRaw* r) {
+    LzbCarry h;
+    memset(&h, 0, sizeof h);
+    h.fresh = 1;
+    h.lc = r->fmt == LZB_FMT_LZMA ? r->lc : 0;
+    h.lp = r->fmt == LZB_FMT_LZMA ? r->lp : 0;
+    h.pb = r->fmt == LZB_FMT_LZMA ? r->pb : 0;
+    h.lclp_cap = r->lclp_cap;
+    memcpy(r->state.data(), &h, sizeof h);
+}
+extern "C" EmulRaw* emul_raw_create(int fmt, uint32_t lc, uint32_t lp, uint32_t pb, uint32_t dict_size) {
+    EmulRaw* r = new EmulRaw{fmt, lc, lp, pb, dict_size, fmt == LZB_FMT_LZMA ? lc + lp : 4u, {}};
+    r->state.assign((size_t)lzb_carry_bytes(r->lclp_cap) + 64, 0);
+    emul_raw_fresh(r);
+    return r;
+}
+extern "C" void emul_raw_reset(EmulRaw* r) { emul_raw_fresh(r); }
+extern "C" void emul_raw_destroy(EmulRaw* r) { delete r; }
+// out: caller's buffer of `cap` bytes.  Returns the status code (LZB_E_CAPACITY: nothing committed, call again larger).
+extern "C" int emul_raw_decompress(EmulRaw* r, const lzb_options* opt, const uint8_t* in, uint64_t in_len, uint8_t* out,
+                                   uint64_t cap, uint64_t* out_len, uint64_t* consumed, lzb_status* st) {
+    std::vector<uint8_t> work(r->state);
+    std::vector<uint16_t> T(T_LIT + 16);
+    std::vector<uint8_t> inbuf(in, in + in_len);
+    inbuf.resize(in_len + 16);
+    LzbItem it;
+    memset(&it, 0, sizeof it);
+    it.in_len = in_len;
+    it.out_cap = cap;
+    it.unpacked = (r->fmt == LZB_FMT_LZMA && opt && opt->has_provided) ? opt->provided : LZB_UNKNOWN_SIZE;
+    it.memlimit = opt && opt->has_memlimit ? opt->memlimit : ~0ull;
+    it.dict_size = r->dict_size;
+    it.kind = r->fmt == LZB_FMT_LZMA ? LZB_ITEM_LZMA : LZB_ITEM_LZMA2;
+    it.lc = (uint8_t)r->lc;
+    it.lp = (uint8_t)r->lp;
+    it.pb = (uint8_t)r->pb;
+    it.flags = LZB_ITEM_F_CARRY;
+    it.host_out = (uint64_t)(uintptr_t)work.data();
+    LzbResult res;
+    memset(&res, 0, sizeof res);
+    const LzbKC kc = LZB_KC_INIT;
+    uint16_t* lit = reinterpret_cast<uint16_t*>(work.data() + sizeof(LzbCarry)) + T_LIT;
+    const TabPtr tab = {T.data()}, plain = {lit}, matched = {lit + 0x100};
+    decode_item<true, false, 0, true>(&it, inbuf.data(), out, T.data(), lit, tab, plain, matched, kc, r->lclp_cap, &res, 0);
+    if (res.code == LZB_OK) r->state.swap(work);  // like lzb_raw_decompress: a failed call commits nothing
+    lzb::status_from_result(res, st);
+    *out_len = res.sink_len;
+    *consumed = res.consumed;
+    return res.code;
+}

@@ -59,6 +59,12 @@ def lib():
             f.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
         _lib.lzo_lzma_compress.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_COpt), C.POINTER(C.POINTER(C.c_uint8)),
                                            C.POINTER(C.c_size_t)]
+        _lib.lzo_raw_new.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.c_int,
+                                     C.c_uint64]
+        _lib.lzo_raw_new.restype = C.c_void_p
+        _lib.lzo_raw_reset.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64]
+        _lib.lzo_raw_decompress.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(_Res)]
+        _lib.lzo_raw_free.argtypes = [C.c_void_p]
         _lib.lzo_buffer_free.argtypes = [C.POINTER(C.c_uint8)]
         _lib.lzo_crc32.argtypes = [C.c_char_p, C.c_size_t]
         _lib.lzo_crc32.restype = C.c_uint32
@@ -118,6 +124,32 @@ def xz_decompress(data):
     res = _Res()
     lib().lzo_xz_decompress(bytes(data), len(data), C.byref(res))
     return _finish(res)
+
+
+class RawDecoder:
+    """decompress::raw::LzmaDecoder (fmt 0) / Lzma2Decoder (fmt 1) restated in the oracle: the DecoderState survives
+    from one decompress() to the next until reset() (lzma.rs:597-648, lzma2.rs:11-82)."""
+
+    def __init__(self, fmt, lc=0, lp=0, pb=0, dict_size=0, unpacked=None, memlimit=None):
+        self._h = lib().lzo_raw_new(fmt, lc, lp, pb, dict_size, 0 if unpacked is None else 1, unpacked or 0,
+                                    0 if memlimit is None else 1, memlimit or 0)
+
+    def reset(self, unpacked=...):
+        if unpacked is ...:
+            lib().lzo_raw_reset(self._h, 0, 0, 0)
+        else:
+            lib().lzo_raw_reset(self._h, 1, 0 if unpacked is None else 1, unpacked or 0)
+
+    def decompress(self, data):
+        res = _Res()
+        lib().lzo_raw_decompress(self._h, bytes(data), len(data), C.byref(res))
+        return _finish(res)
+
+    def __del__(self):
+        try:
+            lib().lzo_raw_free(self._h)
+        except Exception:
+            pass
 
 
 def crc32(data):
