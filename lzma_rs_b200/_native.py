@@ -113,6 +113,7 @@ def bind(path):
         lib.lzb_ipc_open.argtypes = [vp, C.POINTER(IpcHandle), C.POINTER(vp)]
         lib.lzb_ipc_close.argtypes = [vp, vp]
         lib.lzb_decode_batch_peer.argtypes = [vp, C.c_int, C.POINTER(Options), vp, u64p, C.c_uint32, vp, u64p, u64p, u64p, vp]
+    if hasattr(lib, "lzb_raw_create"):
         lib.lzb_raw_create.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
         lib.lzb_raw_reset.argtypes = [vp]
         lib.lzb_raw_decompress.argtypes = [vp, C.POINTER(Options), vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t),

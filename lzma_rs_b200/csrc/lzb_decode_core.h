@@ -742,6 +742,13 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
         // process_mode(Finish), lzma.rs:435-455, 496-511
         for (;;) {
+            // All lanes update the probability tables redundantly, which is only sound while they run in lockstep (every
+            // lane has loaded a probability before any lane stores its update).  The throughput kernels are convergent by
+            // construction (tools/check_sass.py guards it); the LIT_GLOBAL instantiations (lc+lp > 4 kernel, raw decoder
+            // objects) are compiled with reconvergence barriers all over the bit loop, i.e. the lanes MAY drift apart after
+            // a lane-dependent branch (the literal store of lane 0) -- observed on the device as nondeterministic decode
+            // errors of the raw decoder kernel.  Re-align them once per symbol; these are latency paths.
+            if (LIT_GLOBAL) LZB_SYNCWARP();
             if (MIRROR && LZB_UNLIKELY(opos >= mirror_next) && hout) {
                 const uint32_t upto = opos & ~15u;
                 mirror_to_host(out, hout, mirrored, upto, lane);
@@ -961,16 +968,13 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     // (identical index expressions on both sides: written as src[0] the compiler folds the load into the
                     // lane-dependent fill and loses the warp-uniformity of prev_byte downstream)
 #if LZB_R2_COPY
-#ifdef LZB_FILL_SHORTCUT  // (experiment: the shortcut in the `fill` instantiation too, reconvergence barriers and all)
                     if (dist == 1) {
-#else
-                    if (WIDE != 1 && dist == 1) {
-#endif
-                        // run of the previous byte (zero fills in real data): that byte is already in a register -- it is
-                        // the literal context -- so the next symbol's prev_byte / match_byte need no memory round trip
-                        // and no index reduced modulo dist.  (Not in the `fill` instantiation: there the same shortcut
-                        // makes ptxas lose the warp-uniformity of prev_byte -- 85 BSSY pairs in the bit loop, whichever
-                        // way the fill value is produced; tools/check_sass.py.)
+                        // run of the previous byte (zero fills in real data; every symbol of BASELINE config 5): that
+                        // byte is already in a register -- it is the literal context -- so the next symbol's prev_byte /
+                        // match_byte need no memory round trip and no index reduced modulo dist.  In the `fill`
+                        // instantiation this costs ptxas its proof that prev_byte is warp-uniform (85 BSSY pairs in the
+                        // bit loop, whichever way the fill value is produced) and is still 13 % faster on config 5
+                        // (628 -> 710 GB/s): two global round trips per 273-byte symbol weigh more than the barriers.
                         match_byte = prev_byte;
                     } else
 #endif

@@ -215,11 +215,12 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
     p->wide = stored_bytes * 5 >= cap_sum * 4 && stored_bytes ? 2 : cap_sum > 16 * in_sum ? 1 : 0;
     p->order_small.clear();
     p->order_big.clear();
+    const bool force_big = getenv("LZB_FORCE_BIGLIT") != nullptr;  // test switch: every .lzma stream through the lc+lp > 4 kernel
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t lclp = (uint32_t)items[i].lc + items[i].lp;
         if (stored_route(items[i])) {
             p->order_stored.push_back(i);
-        } else if (items[i].kind == LZB_ITEM_LZMA && lclp > 4) {
+        } else if (items[i].kind == LZB_ITEM_LZMA && (lclp > 4 || force_big)) {
             p->order_big.push_back(i);
             lclp_big = std::max(lclp_big, lclp);
         } else {

@@ -181,7 +181,7 @@ def test_cpp_host_mirror(ctx, golden, tmp_path):
         src, dst = tmp_path / "in.bin", tmp_path / "out.bin"
         src.write_bytes(golden.compressed(v))
         r = subprocess.run([str(exe), fmt, str(src), str(dst)], capture_output=True, text=True)
-        assert hashlib.sha256(dst.read_bytes()).hexdigest() == v["plain_sha256"], name
+        assert hashlib.sha256(dst.read_bytes()).hexdigest() == v["plain_sha256"], (name, fmt, r.returncode, r.stderr)
         if "error" in v:
             assert r.returncode == 3 and r.stderr == v["error"], (name, r.stderr)
         else:
