@@ -572,13 +572,14 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
     // first flush point staggered per stream: equal streams started together would otherwise all flush at the same
     // instant and serialise on the PCIe link (measured: +4.8 ms per 256 MiB, exactly one bulk copy)
     uint32_t mirror_next = 4096u + (uint32_t)((itp->out_off >> 4) * 2654435761ull >> 20 & 0xFF0u);
-    uint8_t* const hout = MIRROR ? reinterpret_cast<uint8_t*>(itp->host_out) : nullptr;
+    uint8_t* const hout = MIRROR && !(CARRY && (itp->flags & LZB_ITEM_F_CARRY)) ? reinterpret_cast<uint8_t*>(itp->host_out) : nullptr;
     uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
     uint32_t lc = 0, lp = 0, pb = 0;
     uint32_t prev_byte = 0, match_byte = 0;
     bool mb_valid = false, tables_fresh = true;
     bool carry_live = false;  // CARRY: the tables in shared memory are this decoder's state (written back at the end)
-    LzbCarry* const carry = CARRY ? reinterpret_cast<LzbCarry*>(itp->host_out) : nullptr;
+    // (a run-time property of the work item inside the instantiations compiled with CARRY)
+    LzbCarry* const carry = CARRY && (itp->flags & LZB_ITEM_F_CARRY) ? reinterpret_cast<LzbCarry*>(itp->host_out) : nullptr;
     uint32_t dict_size = 0xFFFFFFFFu, mem_stop = 0xFFFFFFFFu;
     uint32_t target = 0;
     bool has_target = false;
@@ -617,7 +618,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
         target = (uint32_t)LZB_MIN(itp->unpacked, (uint64_t)0xFFFFFFFFu);  // sizes beyond the cap are never reached
         if (LZB_UNLIKELY(lc + lp > tab_lclp)) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
     }
-    if (CARRY && !carry->fresh) {  // continue from the state the previous decompress() call left
+    if (CARRY && carry && !carry->fresh) {  // continue from the state the previous decompress() call left
         const uint16_t* saved = reinterpret_cast<const uint16_t*>(carry + 1);
         for (uint32_t i = lane; i < (uint32_t)T_LIT; i += LZB_LANES) T[i] = saved[i];
         LZB_SYNCWARP();
@@ -637,7 +638,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
         // global part: the whole literal table (LIT_GLOBAL; .lzma props never change mid-stream) or the matched columns
         fill_tables(gws, LIT_GLOBAL ? 0x300u << (lc + lp) : 0x200u << tab_lclp, lane);
     }
-    carry_live = CARRY;
+    carry_live = CARRY && carry != nullptr;
 
     for (;;) {  // LZMA2 chunk loop (lzma2.rs:59-78); a .lzma stream is a single pass
         if (is_lzma1) {
@@ -747,8 +748,9 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
             // construction (tools/check_sass.py guards it); the LIT_GLOBAL instantiations (lc+lp > 4 kernel, raw decoder
             // objects) are compiled with reconvergence barriers all over the bit loop, i.e. the lanes MAY drift apart after
             // a lane-dependent branch (the literal store of lane 0) -- observed on the device as nondeterministic decode
-            // errors of the raw decoder kernel.  Re-align them once per symbol; these are latency paths.
-            if (LIT_GLOBAL) LZB_SYNCWARP();
+            // errors of the raw decoder kernel.  Re-align them once per symbol; these are latency paths.  The `fill`
+            // instantiations carry the barriers too since the dist-1 shortcut (one WARPSYNC per 273-byte symbol there).
+            if (LIT_GLOBAL || WIDE == 1) LZB_SYNCWARP();
             if (MIRROR && LZB_UNLIKELY(opos >= mirror_next) && hout) {
                 const uint32_t upto = opos & ~15u;
                 mirror_to_host(out, hout, mirrored, upto, lane);

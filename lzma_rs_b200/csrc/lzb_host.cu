@@ -44,7 +44,6 @@ LZB_K1_PROTO(lzb_decode_biglit_kernel);
 extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, const uint64_t*, const uint64_t*, uint32_t,
                                            LzbItem*, LzbScan*, uint64_t, uint64_t*);
 extern "C" __global__ void lzb_layout_kernel(const uint64_t*, uint32_t, uint64_t*);
-extern "C" __global__ void lzb_decode_carry_kernel(const LzbItem*, const uint8_t*, uint8_t*, LzbResult*, const LzbKC);
 extern "C" __global__ void lzb_crc_partial_kernel(const uint8_t*, const LzbCrcRange*, const uint32_t*, uint64_t,
                                                   uint32_t*, uint64_t*);
 extern "C" __global__ void lzb_stored_decode_kernel(const LzbItem*, const uint32_t*, const uint8_t*, uint8_t*, LzbResult*);
@@ -1430,7 +1429,7 @@ struct lzb_raw {
     uint32_t lc = 0, lp = 0, pb = 0, dict_size = 0, lclp_cap = 0;
     DevBuf state[2];  // [cur]: the committed state; the other one is what the running call works on
     int cur = 0;
-    DevBuf d_item, d_result;
+    DevBuf d_item, d_result, d_aux;  // d_aux: the one-entry queue {0} and the queue counter of the launch
 };
 
 static int raw_write_fresh(lzb_raw* r) {
@@ -1464,7 +1463,8 @@ extern "C" int lzb_raw_create(lzb_ctx* ctx, int fmt, uint32_t lc, uint32_t lp, u
     const size_t bytes = (size_t)lzb_carry_bytes(r->lclp_cap);
     int rc = LZB_RC_OK;
     if (r->state[0].ensure(bytes) != cudaSuccess || r->state[1].ensure(bytes) != cudaSuccess ||
-        r->d_item.ensure(sizeof(LzbItem)) != cudaSuccess || r->d_result.ensure(sizeof(LzbResult)) != cudaSuccess)
+        r->d_item.ensure(sizeof(LzbItem)) != cudaSuccess || r->d_result.ensure(sizeof(LzbResult)) != cudaSuccess ||
+        r->d_aux.ensure(64) != cudaSuccess)
         rc = LZB_RC_OOM;
     if (rc == LZB_RC_OK) rc = raw_write_fresh(r);
     if (rc != LZB_RC_OK) {
@@ -1489,6 +1489,7 @@ extern "C" void lzb_raw_destroy(lzb_raw* r) {
     r->state[1].release();
     r->d_item.release();
     r->d_result.release();
+    r->d_aux.release();
     delete r;
 }
 
@@ -1536,8 +1537,12 @@ extern "C" int lzb_raw_decompress(lzb_raw* r, const lzb_options* opt, const uint
         it.flags = LZB_ITEM_F_CARRY;
         it.host_out = (uint64_t)(uintptr_t)r->state[work].p;
         CUDA_TRY(ctx, cudaMemcpyAsync(r->d_item.p, &it, sizeof it, cudaMemcpyHostToDevice, s));
-        lzb_decode_carry_kernel<<<1, 32, smem, s>>>(r->d_item.as<LzbItem>(), ctx->d_in.as<uint8_t>(), ctx->d_out.as<uint8_t>(),
-                                                    r->d_result.as<LzbResult>(), kc);
+        // the lc+lp > 4 kernel with one warp: queue = {0}, counter zeroed (d_aux[0] = order entry, d_aux[8..] = counter)
+        CUDA_TRY(ctx, cudaMemsetAsync(r->d_aux.p, 0, 64, s));
+        lzb_decode_biglit_kernel<<<1, 32, smem, s>>>(r->d_item.as<LzbItem>(), r->d_aux.as<uint32_t>(), 1u, 0u, ctx->d_in.as<uint8_t>(),
+                                                     ctx->d_out.as<uint8_t>(), r->d_result.as<LzbResult>(),
+                                                     r->d_aux.as<unsigned int>() + 8, r->lclp_cap, (uint32_t)smem, nullptr, 0ull, kc,
+                                                     nullptr);
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaMemcpyAsync(&res, r->d_result.p, sizeof res, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(ctx, cudaStreamSynchronize(s));

@@ -109,8 +109,12 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
             continue;
         }
         if (LIT_GLOBAL) {  // whole literal table in the global workspace (reference layout)
-            const TabPtr plain = {gws}, matched = {gws + 0x100};
-            decode_item<true, MIRROR, WIDE>(items + idx, in_blob, out_blob, T, gws, tab, plain, matched, kc, tab_lclp, results + idx, lane);
+            // raw decoder objects (lzb_raw_*): the literal workspace is the decoder's own state record (lzb_types.h)
+            uint16_t* lit = gws;
+            if (items[idx].flags & LZB_ITEM_F_CARRY)
+                lit = reinterpret_cast<uint16_t*>(reinterpret_cast<LzbCarry*>(items[idx].host_out) + 1) + T_LIT;
+            const TabPtr plain = {lit}, matched = {lit + 0x100};
+            decode_item<true, MIRROR, WIDE, true>(items + idx, in_blob, out_blob, T, lit, tab, plain, matched, kc, tab_lclp, results + idx, lane);
         } else {  // plain columns in shared memory, matched columns in the global workspace
             const TabSm plain = {tab.a + (uint32_t)T_LIT * 2u};
             const TabPtr matched = {gws};
@@ -159,25 +163,10 @@ LZB_DEFINE_K1(lzb_decode_drain_copy_kernel, false, false, 2, true, true)
 LZB_DEFINE_K1(lzb_decode_mirror_kernel, false, true, 0, true, true)
 LZB_DEFINE_K1(lzb_decode_mirror_fill_kernel, false, true, 1, true, true)
 LZB_DEFINE_K1(lzb_decode_mirror_copy_kernel, false, true, 2, true, true)
-// .lzma streams with lc+lp > 4: literal table in a per-warp global workspace (ws + warp_id * ws_stride_u16).
+// .lzma streams with lc+lp > 4: literal table in a per-warp global workspace (ws + warp_id * ws_stride_u16).  Also the
+// kernel of the raw decoder objects (lzb_raw_*, work items with LZB_ITEM_F_CARRY): there the literal workspace is the
+// decoder's state record, and the small tables are loaded from / written back to it (decode_item's CARRY path).
 LZB_DEFINE_K1(lzb_decode_biglit_kernel, true, true, 1, false, true)
-
-// decompress::raw decoders (lzb_raw_*): one warp per CTA, one work item per CTA; the item's LzbCarry record holds the
-// DecoderState between calls and its literal area is the kernel's literal workspace.  A latency path (one stream per
-// call), not a throughput path: the reconvergence-barrier guard of tools/check_sass.py does not apply.
-extern "C" __global__ void __launch_bounds__(32, 1)
-    lzb_decode_carry_kernel(const LzbItem* __restrict__ items, const uint8_t* __restrict__ in_blob, uint8_t* out_blob,
-                            LzbResult* results, const __grid_constant__ LzbKC kc) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31;
-    const LzbItem* it = items + blockIdx.x;
-    uint16_t* T = reinterpret_cast<uint16_t*>(smem);
-    const TabSm tab = {(uint32_t)__cvta_generic_to_shared(T)};
-    LzbCarry* carry = reinterpret_cast<LzbCarry*>(it->host_out);
-    uint16_t* lit = reinterpret_cast<uint16_t*>(carry + 1) + T_LIT;
-    const TabPtr plain = {lit}, matched = {lit + 0x100};
-    decode_item<true, false, 0, true>(it, in_blob, out_blob, T, lit, tab, plain, matched, kc, carry->lclp_cap, results + blockIdx.x, lane);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K2: per-stream scan -> work items (+ size summary).  One thread per stream.

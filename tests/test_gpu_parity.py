@@ -321,10 +321,28 @@ def test_raw_decoders(ctx):
     # a large-lc decoder (literal table of 0x300 << 8 entries in the state record) used three times in a row
     import lzma_rs_b200 as L
     raw = L.decompress.raw
-    data = corpus.mixed_text(777, 90_000)
-    blob = corpus.lzma_alone_known_size(data, dict_size=1 << 16, lc=8, lp=0, pb=0)
-    dec = raw.LzmaDecoder(raw.LzmaParams(raw.LzmaProperties(8, 0, 0), 1 << 16, len(data)), None, ctx)
-    ora = oracle.RawDecoder(0, 8, 0, 0, 1 << 16, len(data))
+    data = corpus.mixed_text(777, 6_000)
+    enc = corpus.LzmaEncoder(8, 4, 0)  # liblzma refuses lc + lp > 4: hand-encoded payload (literals + a match every 40 bytes)
+    i = 0
+    while i < len(data):
+        if i >= 64 and i % 40 == 0 and i + 12 <= len(data):
+            k = data.rfind(data[i:i + 3], 0, i)
+            if k >= 0 and data[k:k + 3] == data[i:i + 3]:
+                n = 3
+                while n < 12 and data[k + n] == data[i + n] and k + n < i:
+                    n += 1
+                enc.match(n, i - k)
+                i += n
+                continue
+        enc.literal(data[i])
+        i += 1
+    assert bytes(enc.hist) == data
+    payload = enc.finish()
+    dec = raw.LzmaDecoder(raw.LzmaParams(raw.LzmaProperties(8, 4, 0), 1 << 16, len(data)), None, ctx)
+    ora = oracle.RawDecoder(0, 8, 4, 0, 1 << 16, len(data))
+    blob = b"\0" * 13 + payload
+    assert ora.decompress(payload).out == data
+    ora.reset()
     for _ in range(3):
         want = ora.decompress(blob[13:])
         try:
