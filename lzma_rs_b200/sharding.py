@@ -170,11 +170,13 @@ def decode_sharded_tensors(decode_fn, blob, in_off, caps, src=0, group=None):
     # 16 bytes of slack behind every shard: the kernels read whole aligned words
     if rank == src:
         out_t = torch.zeros(int(out_all_off[-1]) + 16, dtype=torch.uint8, device=dev)
-        reqs = []
+        # one batched group of sends: all peers are fed concurrently (unbatched NCCL P2P calls are serialised)
+        ops = []
         for r in range(world):
             a, b = int(in_all[cuts[r]]), int(in_all[cuts[r + 1]])
             if r != src and b > a:
-                reqs.append(dist.isend(blob[a:b], dst=r, group=group))
+                ops.append(dist.P2POp(dist.isend, blob[a:b], r, group))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
         # the source decodes straight out of / into the full blobs.  The kernels read whole aligned words: when the
         # source's own range reaches the end of `blob` without 16 bytes of slack behind it, decode a padded copy instead
         shard, shard_base, out_base = blob, 0, 0
@@ -198,22 +200,32 @@ def decode_sharded_tensors(decode_fn, blob, in_off, caps, src=0, group=None):
     # gather: decoded shards are contiguous slices of the full output blob; per-stream results ride along as int64
     if rank != src:
         res = torch.from_numpy(np.concatenate([np.asarray(out_len, dtype=np.int64), np.asarray(codes, dtype=np.int64)])).to(dev)
+        ops = []
         if n_loc:
-            dist.send(res, dst=src, group=group)
+            ops.append(dist.P2POp(dist.isend, res, src, group))
         if out_hi > out_lo:
-            dist.send(out_t[:out_hi - out_lo], dst=src, group=group)
+            ops.append(dist.P2POp(dist.isend, out_t[:out_hi - out_lo], src, group))
+        for q in (dist.batch_isend_irecv(ops) if ops else []):
+            q.wait()
         return None
     all_len, all_codes = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.int32)
     all_len[lo:hi], all_codes[lo:hi] = out_len, codes
+    # one batched group of receives, posted AFTER the source's own decode: all peers deliver concurrently, and the NCCL
+    # kernel does not sit on SMs the persistent decode kernel needs (it owns every register of an SM it runs on)
+    ops, metas = [], []
     for r in range(world):
         a, b = int(cuts[r]), int(cuts[r + 1])
         if r == src or b == a:
             continue
         res = torch.empty(2 * (b - a), dtype=torch.int64, device=dev)
-        dist.recv(res, src=r, group=group)
+        ops.append(dist.P2POp(dist.irecv, res, r, group))
         oa, ob = int(out_all_off[a]), int(out_all_off[b])
         if ob > oa:
-            dist.recv(out_t[oa:ob], src=r, group=group)
+            ops.append(dist.P2POp(dist.irecv, out_t[oa:ob], r, group))
+        metas.append((a, b, res))
+    for q in (dist.batch_isend_irecv(ops) if ops else []):
+        q.wait()
+    for a, b, res in metas:
         rn = res.cpu().numpy()
         all_len[a:b], all_codes[a:b] = rn[:b - a].astype(np.uint64), rn[b - a:].astype(np.int32)
     return out_t, out_all_off, all_len, all_codes
