@@ -182,6 +182,12 @@ struct TabPtr {
     LZB_MEM uint32_t ldn(const LzbKC&, uint32_t node) const { return b[node]; }
     LZB_MEM void stn(const LzbKC&, uint32_t node, uint32_t v) const { b[node] = (uint16_t)v; }
     LZB_MEM uint32_t node_index(const LzbKC&, uint32_t node) const { return node; }
+    // entries [i, i+1] (i even) / [i, i+3] (i a multiple of 4) as one / two 32-bit words, low entry in the low half
+    LZB_MEM uint32_t ldw(const LzbKC&, uint32_t i) const { return (uint32_t)b[i] | ((uint32_t)b[i + 1] << 16); }
+    LZB_MEM void ldq(const LzbKC& kc, uint32_t i, uint32_t& lo, uint32_t& hi) const {
+        lo = ldw(kc, i);
+        hi = ldw(kc, i + 2);
+    }
     LZB_MEM TabPtr at(const LzbKC&, uint32_t off) const {
         TabPtr t = {b + off};
         return t;
@@ -215,6 +221,15 @@ struct TabSm {
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(node), "h"((uint16_t)v) : "memory");
     }
     LZB_MEM uint32_t node_index(const LzbKC&, uint32_t node) const { return (node - a) >> 1; }
+    // (latency kernels) entries [i, i+1] / [i, i+3]: the table is 4-byte / 8-byte aligned at entry i
+    LZB_MEM uint32_t ldw(const LzbKC& kc, uint32_t i) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(i * kc.two + a) : "memory");
+        return v;
+    }
+    LZB_MEM void ldq(const LzbKC& kc, uint32_t i, uint32_t& lo, uint32_t& hi) const {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(i * kc.two + a) : "memory");
+    }
     LZB_MEM TabSm at(const LzbKC& kc, uint32_t off) const {
         TabSm t = {off * kc.two + a};
         return t;
@@ -326,6 +341,110 @@ LZB_DEV uint32_t rc_tree_upto(Dec& d, const LzbKC& kc, const Tab& t, uint32_t nb
         if (!more) break;
     }
     return t.node_index(kc, node);
+}
+
+// ---- latency form of the tree walks (LAT instantiations of K1: calls with so few streams that a warp has an SM
+// sub-partition almost to itself, so the time of a decision is its dependent chain, not its instruction count) --------
+// In the throughput kernels every level of a walk is load -> multiply -> compare -> child address -> load: ~55 cycles of
+// which 29 are the shared-memory load.  Here the probabilities are fetched AHEAD of the decisions that select them: the
+// children of node m are the adjacent entries (2m, 2m+1) and its grandchildren the four entries 4m .. 4m+3, so one 8-byte
+// load issued when m becomes known delivers both candidates for the pair (= children) of the NEXT node; the chain per
+// level is then select -> shift -> multiply -> compare (~20 cycles) and no load sits on it.
+struct LatPre {  // entries 0 .. 7 of a tree: the root (1), its children (2, 3) and grandchildren (4 .. 7)
+    uint32_t w0, w1, w2, w3;
+};
+template <bool A8, class Tab>
+LZB_DEV LatPre lat_preload(const LzbKC& kc, const Tab& t) {
+    LatPre p;
+    if (A8) {  // the tree starts on an 8-byte boundary
+        t.ldq(kc, 0, p.w0, p.w1);
+        t.ldq(kc, 4, p.w2, p.w3);
+    } else {
+        p.w0 = t.ldw(kc, 0);
+        p.w1 = t.ldw(kc, 2);
+        p.w2 = t.ldw(kc, 4);
+        p.w3 = t.ldw(kc, 6);
+    }
+    return p;
+}
+template <bool A8, class Tab>
+LZB_DEV void lat_ldq(const LzbKC& kc, const Tab& t, uint32_t i, uint32_t& lo, uint32_t& hi) {
+    if (A8) {
+        t.ldq(kc, i, lo, hi);
+    } else {
+        lo = t.ldw(kc, i);
+        hi = t.ldw(kc, i + 2);
+    }
+}
+
+// State of a walk at node m: pv = p(m); (qp_lo, qp_hi) = the four entries below m's PARENT and pbit the decision taken
+// there, i.e. m's children are the half selected by pbit; (qc_lo, qc_hi) = the four entries 4m .. 4m+3 (in flight).
+// Every level issues the load for the node it arrives at and consumes the one issued two decisions earlier.
+// `nb` levels (1 .. MAXNB) are walked; EXACT: nb == MAXNB.  `lim`: entries of the tree (no load reaches beyond it).
+template <int MAXNB, bool A8, bool EXACT, class Tab>
+LZB_DEV uint32_t lat_walk(Dec& d, const LzbKC& kc, const Tab& t, uint32_t m, uint32_t pv, uint32_t qp_lo, uint32_t qp_hi,
+                          uint32_t pbit, uint32_t qc_lo, uint32_t qc_hi, uint32_t nb, uint32_t lim) {
+    // (Tried: the normalisation bodies moved out of the fall-through path with gotos, so that the common case takes no
+    // branch -- a lone warp pays ~20 cycles per taken branch.  nvcc / ptxas lay the blocks out inline again.)
+#pragma unroll
+    for (int i = 0; i < MAXNB; i++) {
+        uint32_t np;
+        const uint32_t bit = rc_step(d, kc, pv, np);
+        t.st16(kc, m, np);
+        const uint32_t pair = pbit ? qp_hi : qp_lo;  // entries 2m, 2m+1
+        pv = bit ? pair >> 16 : pair & 0xFFFFu;
+        m = m * 2u + bit;
+        qp_lo = qc_lo;
+        qp_hi = qc_hi;
+        pbit = bit;
+        // entries 4m .. 4m+3 of the node just reached: the probabilities of the level after next
+        if (i + 3 < MAXNB && (EXACT || 4u * m + 3u < lim)) lat_ldq<A8>(kc, t, 4u * m, qc_lo, qc_hi);
+        rc_normalize(d);
+        if (!EXACT && (uint32_t)(i + 1) >= nb) break;
+    }
+    return m;
+}
+
+// Walk from the root with the first three levels preloaded (lat_preload).
+template <int MAXNB, bool A8, bool EXACT, class Tab>
+LZB_DEV uint32_t lat_tree(Dec& d, const LzbKC& kc, const Tab& t, const LatPre& pre, uint32_t nb) {
+    return lat_walk<MAXNB, A8, EXACT>(d, kc, t, 1u, pre.w0 >> 16, pre.w1, pre.w1, 0u, pre.w2, pre.w3, nb, 1u << MAXNB);
+}
+
+// Rest of a literal walk from node m (1 <= m < 0x100) of the plain tree `t` (after the first mismatching bit of a
+// matched literal, lzma.rs:540-556): up to 7 levels, rolled.  One exposed load at the start, look-ahead after it.
+template <class Tab>
+LZB_DEV uint32_t lat_lit_rest(Dec& d, const LzbKC& kc, const Tab& t, uint32_t m) {
+    if (m >= 0x100u) return m;
+    uint32_t pv = t.ld16(kc, m), pair = 0, qc_lo = 0, qc_hi = 0, pbit = 0;
+    if (m < 0x80u) pair = t.ldw(kc, 2u * m);
+    if (m < 0x40u) t.ldq(kc, 4u * m, qc_lo, qc_hi);
+    uint32_t qp_lo = pair, qp_hi = pair;
+#pragma unroll 1
+    do {
+        uint32_t np;
+        const uint32_t bit = rc_step(d, kc, pv, np);
+        t.st16(kc, m, np);
+        const uint32_t pr = pbit ? qp_hi : qp_lo;
+        pv = bit ? pr >> 16 : pr & 0xFFFFu;
+        m = m * 2u + bit;
+        qp_lo = qc_lo;
+        qp_hi = qc_hi;
+        pbit = bit;
+        if (m < 0x40u) t.ldq(kc, 4u * m, qc_lo, qc_hi);
+        rc_normalize(d);
+    } while (m < 0x100u);
+    return m;
+}
+
+// decode_bit on a probability fetched earlier (its address did not depend on the decisions in between)
+template <class Tab>
+LZB_DEV uint32_t rc_bit_pre(Dec& d, const LzbKC& kc, const Tab& t, uint32_t idx, uint32_t pv) {
+    uint32_t np;
+    const uint32_t bit = rc_step(d, kc, pv, np);
+    t.st16(kc, idx, np);
+    rc_normalize(d);
+    return bit;
 }
 
 LZB_DEV uint32_t rev_bits(uint32_t v, uint32_t nb) {  // the low nb bits of v, reversed
@@ -539,7 +658,11 @@ LZB_DEV void mirror_to_host(const uint8_t* out, uint8_t* hout, uint32_t from, ui
 // CARRY : decompress::raw decoders -- the DecoderState a previous call left in an LzbCarry record (itp->host_out) is the
 //         starting point, and what this call leaves is written back (lzb_types.h).  LIT_GLOBAL form only: the record's
 //         literal area IS the kernel's literal workspace.
-template <bool LIT_GLOBAL, bool MIRROR, int WIDE, bool CARRY = false, class MainTab, class PlainTab, class MatchedTab>
+// LAT   : latency form for calls with few streams per SM (see lat_walk): the whole literal table in shared memory with
+//         the reference's layout (plain = T + T_LIT, matched = + 0x100, stride 0x300, no global workspace), probabilities
+//         fetched ahead of the decisions that select them.  More instructions per symbol, a much shorter dependent chain.
+template <bool LIT_GLOBAL, bool MIRROR, int WIDE, bool CARRY = false, bool LAT = false, class MainTab, class PlainTab,
+          class MatchedTab>
 LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t* __restrict__ in_blob,
                                   uint8_t* out_blob, uint16_t* T, uint16_t* gws, const MainTab tab,
                                   const PlainTab plain, const MatchedTab matched, const LzbKC kc_in, uint32_t tab_lclp,
@@ -565,8 +688,8 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
     // (pinning this pointer in a register pair with an opaque asm was tried: ptxas then loses the address space (generic
     // ST instead of STG) and the warp-uniformity of everything derived from it -- 76 BSSY pairs in the bit loop)
     const uint32_t cap = (uint32_t)LZB_MIN(itp->out_cap, (uint64_t)0xFFFFF000u);
-    const uint32_t tab_u16 = LIT_GLOBAL ? (uint32_t)T_LIT : T_LIT + (0x100u << tab_lclp);
-    const uint32_t plain_stride = LIT_GLOBAL ? 0x300u : 0x100u, matched_stride = LIT_GLOBAL ? 0x300u : 0x200u;
+    const uint32_t tab_u16 = LIT_GLOBAL ? (uint32_t)T_LIT : T_LIT + ((LAT ? 0x300u : 0x100u) << tab_lclp);
+    const uint32_t plain_stride = LIT_GLOBAL || LAT ? 0x300u : 0x100u, matched_stride = LIT_GLOBAL || LAT ? 0x300u : 0x200u;
     uint32_t opos = 0, dict_base = 0;
     uint32_t mirrored = 0;  // MIRROR: bytes already copied to the host buffer (multiple of 16)
     // first flush point staggered per stream: equal streams started together would otherwise all flush at the same
@@ -636,7 +759,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
     } else {
         fill_tables(T, tab_u16, lane);
         // global part: the whole literal table (LIT_GLOBAL; .lzma props never change mid-stream) or the matched columns
-        fill_tables(gws, LIT_GLOBAL ? 0x300u << (lc + lp) : 0x200u << tab_lclp, lane);
+        if (!LAT) fill_tables(gws, LIT_GLOBAL ? 0x300u << (lc + lp) : 0x200u << tab_lclp, lane);
     }
     carry_live = CARRY && carry != nullptr;
 
@@ -697,7 +820,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                 if (LZB_UNLIKELY(lc + lp > tab_lclp)) FAIL(LZB_E_UNSUPPORTED, lc + lp, tab_lclp);
                 if (!tables_fresh) {  // reset_state, lzma.rs:216-249
                     fill_tables(T, tab_u16, lane);
-                    fill_tables(gws, LIT_GLOBAL ? 0x300u << (lc + lp) : 0x200u << tab_lclp, lane);
+                    if (!LAT) fill_tables(gws, LIT_GLOBAL ? 0x300u << (lc + lp) : 0x200u << tab_lclp, lane);
                 } else if (LIT_GLOBAL) {  // the table was initialised for the old lc+lp: cover the new one
                     fill_tables(gws, 0x300u << (lc + lp), lane);
                 }
@@ -750,7 +873,7 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
             // a lane-dependent branch (the literal store of lane 0) -- observed on the device as nondeterministic decode
             // errors of the raw decoder kernel.  Re-align them once per symbol; these are latency paths.  The `fill`
             // instantiations carry the barriers too since the dist-1 shortcut (one WARPSYNC per 273-byte symbol there).
-            if (LIT_GLOBAL || WIDE == 1) LZB_SYNCWARP();
+            if (LIT_GLOBAL || WIDE == 1 || LAT) LZB_SYNCWARP();
             if (MIRROR && LZB_UNLIKELY(opos >= mirror_next) && hout) {
                 const uint32_t upto = opos & ~15u;
                 mirror_to_host(out, hout, mirrored, upto, lane);
@@ -783,11 +906,18 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
             const uint32_t p_is_match = tab.ld16(kc, i_is_match);
 #if LZB_R2_STATE
             // (unconditional: after a match the value is simply not used -- cheaper than the predicate and the zero)
-            const uint32_t lit_pv = probs.ldn(kc, probs.root(kc));
+            const uint32_t lit_pv = LAT ? 0u : probs.ldn(kc, probs.root(kc));
 #else
             uint32_t lit_pv = 0;
             if (state < 7) lit_pv = probs.ldn(kc, probs.root(kc));
 #endif
+            // LAT: the first three levels of the plain literal tree and is_rep's probability travel with is_match's
+            LatPre lit_pre = {0u, 0u, 0u, 0u};
+            uint32_t p_is_rep = 0;
+            if (LAT) {
+                lit_pre = lat_preload<true>(kc, probs);
+                p_is_rep = tab.ld16(kc, T_IS_REP + state);
+            }
             uint32_t np_im;
             const uint32_t is_lz = rc_step(d, kc, p_is_match, np_im);
             tab.st16(kc, i_is_match, np_im);
@@ -806,16 +936,36 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
                     }
                     uint32_t mb = match_byte;
                     const MatchedTab mprobs = matched.at(kc, lit_row * matched_stride);
+                    if (LAT) {
+                        // the eight probabilities along the path the match byte predicts are fetched at once: level k is
+                        // entry (match_bit_k << 8) + sym_k, sym_k = the top k bits of the match byte behind a leading 1
+                        const uint32_t mbx = 0x100u | match_byte;
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) pk[k] = mprobs.ld16(kc, (((mbx >> (7 - k)) & 1u) << 8) + (mbx >> (8 - k)));
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const uint32_t match_bit = (mbx >> (7 - k)) & 1u;
+                            const uint32_t bit = rc_bit_pre(d, kc, mprobs, (match_bit << 8) + sym, pk[k]);
+                            sym = (sym << 1) | bit;
+                            if (match_bit != bit) break;
+                        }
+                        sym = lat_lit_rest(d, kc, probs, sym);  // the plain tree from the first mismatch on
+                    } else {
 #pragma unroll 1
-                    do {
-                        const uint32_t match_bit = (mb >> 7) & 1u;
-                        mb <<= 1;
-                        const uint32_t bit = rc_bit(d, kc, mprobs, (match_bit << 8) + sym);
-                        sym = (sym << 1) | bit;
-                        if (match_bit != bit) break;
-                    } while (sym < 0x100);
+                        do {
+                            const uint32_t match_bit = (mb >> 7) & 1u;
+                            mb <<= 1;
+                            const uint32_t bit = rc_bit(d, kc, mprobs, (match_bit << 8) + sym);
+                            sym = (sym << 1) | bit;
+                            if (match_bit != bit) break;
+                        } while (sym < 0x100);
 #pragma unroll 1
-                    while (sym < 0x100) sym = (sym << 1) | rc_bit(d, kc, probs, sym);
+                        while (sym < 0x100) sym = (sym << 1) | rc_bit(d, kc, probs, sym);
+                    }
+                } else if (LAT) {
+                    sym = lat_tree<8, true, true>(d, kc, probs, lit_pre, 8);
+                    LZB_LIT_TAIL(state > 3 ? state - 3 : 0u)
                 } else {  // plain 8-level walk (root fetched above, while is_match was being decoded)
                     const uint32_t x0 = probs.x0(kc), x1 = probs.x1(kc);
                     uint32_t node = probs.root(kc), pv = lit_pv;
@@ -841,7 +991,101 @@ LZB_DEV_NOINLINE void decode_item(const LzbItem* __restrict__ itp, const uint8_t
 
             // ---- LZ, lzma.rs:309-390
             uint32_t mlen;
-            {
+            if (LAT) {
+                // every probability whose address depends on state / pos_state only is fetched now and used up to five
+                // decisions later; the length trees of this pos_state are fetched whole (8 entries each)
+                const uint32_t p_g0 = tab.ld16(kc, T_IS_REP_G0 + state);
+                const uint32_t p_r0l = tab.ld16(kc, T_IS_REP0LONG + (state << 4) + pos_state);
+                const uint32_t p_g1 = tab.ld16(kc, T_IS_REP_G1 + state);
+                const uint32_t p_g2 = tab.ld16(kc, T_IS_REP_G2 + state);
+                const uint32_t ch_len = tab.ldw(kc, T_LEN), ch_rep = tab.ldw(kc, T_REP_LEN);  // choice : choice2
+                const bool is_rep = rc_bit_pre(d, kc, tab, T_IS_REP + state, p_is_rep) != 0;
+                const uint32_t L = is_rep ? (uint32_t)T_REP_LEN : (uint32_t)T_LEN;
+                const uint32_t ch = is_rep ? ch_rep : ch_len;
+                const MainTab t_low = tab.at(kc, L + T_LEN_LOW + pos_state * 8), t_mid = tab.at(kc, L + T_LEN_MID + pos_state * 8);
+                const MainTab t_high = tab.at(kc, L + T_LEN_HIGH);
+                const LatPre pre_low = lat_preload<false>(kc, t_low), pre_mid = lat_preload<false>(kc, t_mid);
+                // the distance slot tree of lengths >= 5 (the usual case), ahead of the length decode
+                LatPre pre_ps3 = {0u, 0u, 0u, 0u};
+                if (!is_rep) pre_ps3 = lat_preload<true>(kc, tab.at(kc, T_POS_SLOT + 3 * 64));
+                bool short_rep = false;
+                if (is_rep) {  // lzma.rs:312-345
+                    if (!rc_bit_pre(d, kc, tab, T_IS_REP_G0 + state, p_g0)) {
+                        if (!rc_bit_pre(d, kc, tab, T_IS_REP0LONG + (state << 4) + pos_state, p_r0l)) short_rep = true;
+                    } else {
+                        uint32_t dist;
+                        if (!rc_bit_pre(d, kc, tab, T_IS_REP_G1 + state, p_g1)) {
+                            dist = rep1;
+                        } else {
+                            if (!rc_bit_pre(d, kc, tab, T_IS_REP_G2 + state, p_g2)) {
+                                dist = rep2;
+                            } else {
+                                dist = rep3;
+                                rep3 = rep2;
+                            }
+                            rep2 = rep1;
+                        }
+                        rep1 = rep0;
+                        rep0 = dist;
+                    }
+                } else {  // lzma.rs:355-361
+                    rep3 = rep2;
+                    rep2 = rep1;
+                    rep1 = rep0;
+                }
+                if (short_rep) {
+                    state = state < 7 ? 9 : 11;
+                    mlen = 1;
+                } else {
+                    // LenDecoder::decode, rangecoder.rs:256-269
+                    uint32_t l;
+                    const uint32_t c1 = rc_bit_pre(d, kc, tab, L + 0, ch & 0xFFFFu);
+                    if (!c1) {
+                        l = lat_tree<3, false, true>(d, kc, t_low, pre_low, 3) - 8;
+                    } else {
+                        const LatPre pre_high = lat_preload<false>(kc, t_high);
+                        if (!rc_bit_pre(d, kc, tab, L + 1, ch >> 16))
+                            l = lat_tree<3, false, true>(d, kc, t_mid, pre_mid, 3) - 8 + 8;
+                        else
+                            l = lat_tree<8, false, true>(d, kc, t_high, pre_high, 8) - 256 + 16;
+                    }
+                    if (is_rep) {
+                        state = state < 7 ? 8 : 11;
+                    } else {
+                        state = state < 7 ? 7 : 10;
+                        // decode_distance, lzma.rs:563-592
+                        LatPre pre_ps = pre_ps3;
+                        if (l < 3) pre_ps = lat_preload<true>(kc, tab.at(kc, T_POS_SLOT + l * 64));
+                        const uint32_t pos_slot =
+                            lat_tree<6, true, true>(d, kc, tab.at(kc, T_POS_SLOT + (l < 3 ? l : 3) * 64), pre_ps, 6) - 64;
+                        if (pos_slot < 4) {
+                            rep0 = pos_slot;
+                        } else {
+                            const uint32_t nd = (pos_slot >> 1) - 1;
+                            uint32_t r = (2u | (pos_slot & 1u)) << nd;
+                            if (pos_slot < 14) {
+                                const uint32_t off = 2u * ((1u << nd) - 2u) + ((pos_slot & 1u) << nd);
+                                const MainTab t_pd = tab.at(kc, T_POS_DEC + off);
+                                const LatPre pre_pd = lat_preload<false>(kc, t_pd);
+                                r += rev_bits(lat_tree<5, false, false>(d, kc, t_pd, pre_pd, nd), nd);
+                            } else {
+                                const MainTab t_al = tab.at(kc, T_ALIGN);
+                                const LatPre pre_al = lat_preload<true>(kc, t_al);  // arrives while the direct bits are taken
+                                r += rc_direct(d, nd - 4) << 4;
+                                r += rev_bits(lat_tree<4, true, true>(d, kc, t_al, pre_al, 4), 4);
+                            }
+                            rep0 = r;
+                        }
+                        if (LZB_UNLIKELY(d.p > d.lim)) FAIL(LZB_E_IO_EOF, 0, 0);
+                        if (rep0 == 0xFFFFFFFFu) {  // end-of-stream marker, lzma.rs:373-381
+                            if (d.code == 0 && d.p == d.lim) goto chunk_done;
+                            FAIL(LZB_E_EOS_MORE_BYTES, 0, 0);
+                        }
+                    }
+                    mlen = l + 2;
+                }
+                if (LZB_UNLIKELY(d.p > d.lim)) FAIL(LZB_E_IO_EOF, 0, 0);
+            } else {
                 const bool is_rep = rc_bit(d, kc, tab, T_IS_REP + state) != 0;
                 bool short_rep = false;
                 if (is_rep) {  // lzma.rs:312-345

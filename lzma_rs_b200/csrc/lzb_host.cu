@@ -41,6 +41,8 @@ LZB_K1_PROTO(lzb_decode_mirror_kernel);
 LZB_K1_PROTO(lzb_decode_mirror_fill_kernel);
 LZB_K1_PROTO(lzb_decode_mirror_copy_kernel);
 LZB_K1_PROTO(lzb_decode_biglit_kernel);
+LZB_K1_PROTO(lzb_decode_lat_kernel);
+LZB_K1_PROTO(lzb_decode_lat_mirror_kernel);
 extern "C" __global__ void lzb_scan_kernel(int, lzb_options, const uint8_t*, const uint64_t*, const uint64_t*, uint32_t,
                                            LzbItem*, LzbScan*, uint64_t, uint64_t*);
 extern "C" __global__ void lzb_layout_kernel(const uint64_t*, uint32_t, uint64_t*);
@@ -149,12 +151,13 @@ struct LaunchCfg {
 typedef void (*k1_t)(const LzbItem*, const uint32_t*, uint32_t, uint32_t, const uint8_t*, uint8_t*, LzbResult*,
                      unsigned int*, uint32_t, uint32_t, uint16_t*, unsigned long long, const LzbKC,
                      const unsigned long long*);
-const k1_t k1_variants[13] = {
+const k1_t k1_variants[15] = {
     lzb_decode_kernel,        lzb_decode_fill_kernel,        lzb_decode_copy_kernel,
     lzb_decode_sched_kernel,  lzb_decode_sched_fill_kernel,  lzb_decode_sched_copy_kernel,
     lzb_decode_drain_kernel,  lzb_decode_drain_fill_kernel,  lzb_decode_drain_copy_kernel,
     lzb_decode_mirror_kernel, lzb_decode_mirror_fill_kernel, lzb_decode_mirror_copy_kernel,
-    lzb_decode_biglit_kernel};
+    lzb_decode_biglit_kernel,
+    lzb_decode_lat_kernel,    lzb_decode_lat_mirror_kernel};  // latency form (few streams per SM): 13 plain, 14 page stores
 
 LaunchCfg decode_config(const lzb_ctx* ctx, uint32_t n, uint32_t lclp) {
     LaunchCfg c;
@@ -184,6 +187,7 @@ struct DecodePlan {
     uint32_t parked = 0;          // warps the placement keeps out of the launch
     uint64_t big_stride_u16 = 0;  // workspace u16 per warp
     int wide = 0;                 // K1 variant: 0 lean, 1 word-wide run fills, 2 vector stored-chunk copies
+    bool lat = false;             // first launch with the latency kernels (at most LZB_LAT_WARPS streams per SM, one round)
     bool host_io = false;         // launch with the host-I/O kernels (input gate; done words or page stores)
 };
 
@@ -234,6 +238,23 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
     p->n_small = (uint32_t)p->order_small.size();
     p->cfg_small = decode_config(ctx, p->n_small, lclp_small);
     p->n_static = p->parked = 0;
+    p->lat = false;
+    if (p->n_small && p->wide == 0 && !getenv("LZB_NO_LAT")) {
+        // Few streams per SM: a stream's time is the dependent chain of its decisions, not the instruction count.  The
+        // latency kernels (lzb_decode_core.h, lat_walk) fetch probabilities ahead of the decisions that select them and keep
+        // the whole literal table in shared memory; they win while a warp has most of an SM sub-partition to itself.
+        const uint32_t lat_bytes = (lzb_lat_table_u16(lclp_small) * 2 + 15u) & ~15u;
+        uint32_t lat_warps = std::min<uint32_t>(LZB_LAT_WARPS, (uint32_t)ctx->smem_optin / lat_bytes);
+        if (const char* e = getenv("LZB_LAT_WARPS_MAX")) lat_warps = std::min<uint32_t>(lat_warps, (uint32_t)atoi(e));  // experiments
+        const uint32_t sm = (uint32_t)ctx->sm_count;
+        if (lat_warps && p->n_small <= sm * lat_warps) {
+            p->lat = true;
+            LaunchCfg& c = p->cfg_small;
+            c.warp_bytes = lat_bytes;
+            c.warps = (p->n_small + sm - 1) / sm;
+            c.grid = std::min<uint32_t>(sm, (p->n_small + c.warps - 1) / c.warps);
+        }
+    }
     if (p->n_small > (uint32_t)ctx->sm_count * p->cfg_small.warps) {
         // several rounds: streams that would still be running when the queue is empty get less crowded SMs
         std::vector<double> work(n);
@@ -246,7 +267,7 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
             p->cfg_small.grid = sp.grid;
         }
     }
-    if (host_io && !p->n_static && p->n_small) {
+    if ((host_io || p->lat) && !p->n_static && p->n_small) {
         // the host-I/O kernels exist in the static-prefix form only (lzb_kernels.cu): without a placement plan, hand the
         // head of the queue out round-robin over the CTAs, which is what the dynamic queue does in effect
         const uint32_t grid = p->cfg_small.grid, warps = p->cfg_small.warps, ns = grid * warps;
@@ -298,10 +319,10 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         const LaunchCfg& c = p.cfg_small;
         const int smem = (int)(c.warps * c.warp_bytes);
         // per-warp global workspace for the matched-literal columns (L2-resident: 8 KiB per warp at lc+lp = 3)
-        const uint64_t mstride = lzb_matched_u16(c.lclp);
-        CUDA_TRY(ctx, matchws.ensure((size_t)c.grid * c.warps * mstride * 2));
+        const uint64_t mstride = p.lat ? 0 : lzb_matched_u16(c.lclp);
+        if (!p.lat) CUDA_TRY(ctx, matchws.ensure((size_t)c.grid * c.warps * mstride * 2));
         const k1_t* kernels = k1_variants;
-        const int v = (p.host_io ? (mirror ? 9 : 6) : p.n_static ? 3 : 0) + p.wide;
+        const int v = p.lat ? (mirror ? 14 : 13) : (p.host_io ? (mirror ? 9 : 6) : p.n_static ? 3 : 0) + p.wide;
         if (int rc = fire()) return rc;
         kernels[v]<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, p.n_static, d_in_base, d_out_base, d_results,
                                                       d_counter, c.lclp, c.warp_bytes, matchws.as<uint16_t>(), mstride, kc,
@@ -656,7 +677,11 @@ class CudaExecutor : public lzb::Executor {
             cudaEventRecord(ev0, s_);
         }
         const unsigned long long* gate = gate_;
-        if (gate_ && upload_phase == 0 && queue_upload.src && plan.order_big.empty() && !getenv("LZB_GATE_BYTES")) {
+        // Queue-order upload only when the launch has a dynamic queue (more than one round): in a one-round launch every
+        // warp waits for its first stream anyway, so the blob-order upload in few large copies finishes first (C2, 4 096 x
+        // 32 KiB: one copy per stream costs 22 ms of driver calls and short transfers, 55.8 vs 33.9 ms per call).
+        if (gate_ && upload_phase == 0 && queue_upload.src && plan.order_big.empty() && !getenv("LZB_GATE_BYTES") &&
+            (plan.n_small > plan.n_static || getenv("LZB_GATE_QUEUE"))) {
             rc = arm_gate_queue(ctx, queue_upload.src, queue_upload.lead, queue_upload.in_lo, queue_upload.in_bytes, items,
                                 plan.order_small, plan.order_stored, &before_first_kernel);
             if (rc < 0) return rc;

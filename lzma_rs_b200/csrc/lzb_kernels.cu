@@ -67,7 +67,9 @@ __device__ __forceinline__ bool input_arrived(const LzbItem* it, const unsigned 
 // any code around decode_item that depends on the stream index makes ptxas treat the loop's exits as divergent and wrap
 // every branch of the bit loop in BSSY / BSYNC pairs (10 -> 78 in the kernel, +20 % instructions; tools/check_sass.py
 // counts them) -- the host gives launches without a placement plan a trivial static prefix instead (launch_plan).
-template <bool LIT_GLOBAL, bool MIRROR, int WIDE, bool SCHED, bool GATE>
+// LAT: latency form (lzb_decode_core.h, lat_walk) for launches with few streams per SM -- whole literal table in shared
+// memory (warp_smem_bytes covers T_LIT + (0x300 << tab_lclp) entries), no global workspace.
+template <bool LIT_GLOBAL, bool MIRROR, int WIDE, bool SCHED, bool GATE, bool LAT = false>
 __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, const uint32_t* __restrict__ order,
                                             uint32_t n_items, uint32_t n_static, const uint8_t* __restrict__ in_blob,
                                             uint8_t* out_blob, LzbResult* results, unsigned int* counter, uint32_t tab_lclp,
@@ -108,13 +110,17 @@ __device__ __forceinline__ void decode_loop(const LzbItem* __restrict__ items, c
             }
             continue;
         }
-        if (LIT_GLOBAL) {  // whole literal table in the global workspace (reference layout)
+        if constexpr (LIT_GLOBAL) {  // whole literal table in the global workspace (reference layout)
             // raw decoder objects (lzb_raw_*): the literal workspace is the decoder's own state record (lzb_types.h)
             uint16_t* lit = gws;
             if (items[idx].flags & LZB_ITEM_F_CARRY)
                 lit = reinterpret_cast<uint16_t*>(reinterpret_cast<LzbCarry*>(items[idx].host_out) + 1) + T_LIT;
             const TabPtr plain = {lit}, matched = {lit + 0x100};
             decode_item<true, MIRROR, WIDE, true>(items + idx, in_blob, out_blob, T, lit, tab, plain, matched, kc, tab_lclp, results + idx, lane);
+        } else if constexpr (LAT) {  // reference layout in shared memory: matched columns 0x100 entries behind the plain ones
+            const TabSm plain = {tab.a + (uint32_t)T_LIT * 2u};
+            const TabSm matched = {tab.a + (uint32_t)T_LIT * 2u + 0x200u};
+            decode_item<false, MIRROR, WIDE, false, true>(items + idx, in_blob, out_blob, T, nullptr, tab, plain, matched, kc, tab_lclp, results + idx, lane);
         } else {  // plain columns in shared memory, matched columns in the global workspace
             const TabSm plain = {tab.a + (uint32_t)T_LIT * 2u};
             const TabPtr matched = {gws};
@@ -167,6 +173,16 @@ LZB_DEFINE_K1(lzb_decode_mirror_copy_kernel, false, true, 2, true, true)
 // kernel of the raw decoder objects (lzb_raw_*, work items with LZB_ITEM_F_CARRY): there the literal workspace is the
 // decoder's state record, and the small tables are loaded from / written back to it (decode_item's CARRY path).
 LZB_DEFINE_K1(lzb_decode_biglit_kernel, true, true, 1, false, true)
+
+// Latency form ("LAT"): launches with at most LZB_LAT_WARPS streams per SM, one round.  Static-prefix
+// form with the host-I/O code compiled in (gate == nullptr and host_out == 0 switch it off); own launch bounds, so the
+// look-ahead registers never spill.
+#define LZB_DEFINE_K1_LAT(NAME, MIRROR)                                                                   \
+    extern "C" __global__ void __launch_bounds__(LZB_LAT_WARPS * 32, 1) NAME(LZB_KERNEL_ARGS) {          \
+        decode_loop<false, MIRROR, 0, true, true, true>(LZB_KERNEL_PASS);                                \
+    }
+LZB_DEFINE_K1_LAT(lzb_decode_lat_kernel, false)
+LZB_DEFINE_K1_LAT(lzb_decode_lat_mirror_kernel, true)
 
 // ------------------------------------------------------------------------------------------------
 // K2: per-stream scan -> work items (+ size summary).  One thread per stream.

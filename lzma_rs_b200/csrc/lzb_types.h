@@ -101,6 +101,13 @@ enum {
 #define LZB_MAX_WARPS 28
 #endif
 
+// Latency kernels (LAT): at most this many streams per SM; beyond it the throughput kernels win (measured crossover).
+#ifndef LZB_LAT_WARPS
+#define LZB_LAT_WARPS 8
+#endif
+// their shared-memory u16 per warp: small tables + the whole literal table in the reference's layout
+static inline uint32_t lzb_lat_table_u16(uint32_t lclp) { return (uint32_t)T_LIT + (0x300u << lclp); }
+
 struct LzbKC {
     uint32_t two, four, m1, m2017, k2048, shr11;
 };

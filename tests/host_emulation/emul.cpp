@@ -3,6 +3,7 @@
 // into the product's host planning code (lzb_plan.cpp) through the Executor interface, and exposes the same
 // batch entry point as the C ABI.  This lets the CPU-only test tier check the decode logic, the container walk
 // and the status mapping against the oracle without a GPU.  The real GPU parity tests are tests/test_gpu_*.py.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -16,13 +17,22 @@ class HostEmulExecutor : public lzb::Executor {
     HostEmulExecutor(const uint8_t* in, uint8_t* out) : in_(in), out_(out) {}
     int decode(const LzbItem* items, uint32_t n, uint32_t max_lclp, uint64_t /*stored_bytes*/, LzbResult* results) override {
         const uint32_t small_lclp = max_lclp > 4 ? 4 : max_lclp;
-        std::vector<uint16_t> T(lzb_table_u16(small_lclp) + 8), M(lzb_matched_u16(small_lclp) + 8), T4, M4, G;
+        std::vector<uint16_t> T(lzb_table_u16(small_lclp) + 8), M(lzb_matched_u16(small_lclp) + 8), T4, M4, G, TL;
         for (uint32_t i = 0; i < n; i++) {
             memset(&results[i], 0, sizeof results[i]);
             const uint32_t lclp = (uint32_t)items[i].lc + items[i].lp;
             if (items[i].kind == LZB_ITEM_LZMA && lclp > 4) {  // whole literal table outside "shared memory"
                 G.assign((size_t)0x300u << lclp, 0);
                 run<true>(items + i, T.data(), G.data(), lclp, results + i);
+                continue;
+            }
+            if (getenv("LZB_EMUL_LAT")) {  // the latency form of K1 (look-ahead walks, whole literal table in "shared memory")
+                TL.assign(lzb_lat_table_u16(small_lclp) + 8, 0);
+                run_lat(items + i, TL.data(), small_lclp, results + i);
+                if (results[i].code == LZB_E_UNSUPPORTED && results[i].a1 == small_lclp && results[i].a0 <= 4) {
+                    TL.assign(lzb_lat_table_u16(4) + 8, 0);
+                    run_lat(items + i, TL.data(), 4, results + i);
+                }
                 continue;
             }
             run<false>(items + i, T.data(), M.data(), small_lclp, results + i);
@@ -83,6 +93,13 @@ class HostEmulExecutor : public lzb::Executor {
         const TabPtr plain = {BIG ? G : T + T_LIT};
         const TabPtr matched = {BIG ? G + 0x100 : G};
         decode_item<BIG, false, 1>(it, in_, out_, T, G, tab, plain, matched, kc, lclp, res, 0);
+    }
+    void run_lat(const LzbItem* it, uint16_t* T, uint32_t lclp, LzbResult* res) {
+        const LzbKC kc = LZB_KC_INIT;
+        const TabPtr tab = {T};
+        const TabPtr plain = {T + T_LIT};
+        const TabPtr matched = {T + T_LIT + 0x100};
+        decode_item<false, false, 0, false, true>(it, in_, out_, T, nullptr, tab, plain, matched, kc, lclp, res, 0);
     }
     const uint8_t* in_;
     uint8_t* out_;

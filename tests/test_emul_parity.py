@@ -33,6 +33,21 @@ def test_emulated_kernel_matches_oracle(family):
     assert not bad, f"{len(bad)}/{n} mismatches:\n" + "\n".join(bad[:40])
 
 
+@pytest.mark.parametrize("family", ["valid_lzma2_cases", "valid_lzma_cases", "hand_encoded_cases",
+                                    "truncation_and_corruption_cases", "xz_cases", "xz_chain_cases"])
+def test_emulated_latency_kernel_matches_oracle(family, monkeypatch):
+    """The latency form of K1 (LAT: look-ahead tree walks, probabilities fetched ahead of their decisions, whole literal
+    table in "shared memory") compiled as plain C++: same corpus, same oracle."""
+    monkeypatch.setenv("LZB_EMUL_LAT", "1")
+    test_emulated_kernel_matches_oracle(family)
+
+
+def test_structured_fuzz_latency_kernel(monkeypatch):
+    monkeypatch.setenv("LZB_EMUL_LAT", "1")
+    bad = structured_fuzz(_decode, 20261018, 300)
+    assert not bad, f"{len(bad)} mismatches:\n" + "\n".join(bad[:20])
+
+
 def fuzz_regressions():
     """Inputs on which tools/fuzz_soak.py once found a mismatch (tests/golden/fuzz_regressions/<seed>-r<round>-f<fmt>-<i>.bin)."""
     import glob

@@ -29,9 +29,18 @@ def _host(ctx):
     return lambda fmt, streams, opts: gpu_util.host_decode(ctx, fmt, streams, opts)
 
 
+@pytest.fixture(params=["auto", "throughput"])
+def kernel_family(request, monkeypatch):
+    """Batches of up to 8 streams per SM run on the latency kernels (lzb_decode_lat_*); LZB_NO_LAT=1 sends them through
+    the throughput kernels, so that the small batches of the parity corpus cover both families."""
+    if request.param == "throughput":
+        monkeypatch.setenv("LZB_NO_LAT", "1")
+    return request.param
+
+
 @pytest.mark.parametrize("family", ["valid_lzma2_cases", "valid_lzma_cases", "hand_encoded_cases",
                                     "truncation_and_corruption_cases", "xz_cases", "xz_chain_cases"])
-def test_cuda_path_matches_oracle(ctx, family):
+def test_cuda_path_matches_oracle(ctx, family, kernel_family):
     bad, n = [], 0
     for (fmt, okey), named in parity.group_cases(getattr(cases, family)()).items():
         bad += parity.check_group(_host(ctx), fmt, dict(okey), named)
@@ -542,7 +551,7 @@ def test_reference_suite_on_gpu(ctx, golden):
     run_reference_suite(L, foo)
 
 
-def test_structured_fuzz_on_gpu(ctx):
+def test_structured_fuzz_on_gpu(ctx, kernel_family):
     """Structure-aware differential fuzz (tools/fuzz_soak.py generators, fixed seed) through the CUDA path."""
     from test_emul_parity import structured_fuzz
     bad = structured_fuzz(_host(ctx), 20261018, 1500)

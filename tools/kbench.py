@@ -48,7 +48,10 @@ def main():
     stream = torch.cuda.Stream()
     sptr = C.c_void_p(stream.cuda_stream)
     opt = _native.make_options()
-    for path in a.libs:
+    for spec in a.libs:  # path[@NAME=value[,NAME=value]]: environment switches of the library for this build only
+        path, _, envs = spec.partition("@")
+        env = dict(kv.split("=", 1) for kv in envs.split(",") if kv)
+        os.environ.update(env)
         lib = _native.bind(os.path.abspath(path))
         h = C.c_void_p()
         assert lib.lzb_create(C.byref(h), 0) == 0
@@ -73,7 +76,9 @@ def main():
         assert lib.lzb_batch_collect(batch, sptr, ol.ctypes.data, cs.ctypes.data, st.ctypes.data) == 0
         ok = bool((st["code"] == 0).all()) and bool((ol == sizes).all()) and bool(torch.equal(d_out, d_want))
         med = ms[len(ms) // 2]
-        print(f"{os.path.basename(path):28s} median {med:9.3f} ms  min {ms[0]:9.3f}  {out_bytes / med / 1e6:9.2f} GB/s  "
+        for k in env:
+            del os.environ[k]
+        print(f"{os.path.basename(spec):28s} median {med:9.3f} ms  min {ms[0]:9.3f}  {out_bytes / med / 1e6:9.2f} GB/s  "
               f"bit-exact={'yes' if ok else 'NO'}", flush=True)
         lib.lzb_batch_destroy(batch)
         lib.lzb_destroy(h)
