@@ -484,6 +484,7 @@ def bench_ns(a, rank, local_rank, world):
                                d_out.data_ptr(), out_off.ctypes.data, C.byref(batch))
     assert rc == 0, (rc, ctx.last_error())
     kernels_per_step = lib.lzb_batch_kernels_per_launch(batch)
+    kernel_name = lib.lzb_batch_kernel_name(batch).decode()  # the K1 variant the planner picked for this batch
     out_len = np.zeros(n, dtype=np.uint64)
     consumed = np.zeros(n, dtype=np.uint64)
     st = np.zeros(n, dtype=_native.STATUS_DTYPE)
@@ -606,7 +607,7 @@ def bench_ns(a, rank, local_rank, world):
             "gpu_launches": kernels_per_step * a.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "lzb_decode_sched_kernel" if total_streams // world > 148 * 28 else "lzb_decode_kernel",
+                         "kernel": kernel_name,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": in_bytes + out_bytes,
                          "kernel_ms": kernel_ms},
             "cpu_baseline": cpu_obj,
@@ -823,6 +824,7 @@ def main():
                                d_out.data_ptr(), out_off.ctypes.data, C.byref(batch))
     assert rc == 0, (rc, ctx.last_error())
     kernels_per_step = lib.lzb_batch_kernels_per_launch(batch)
+    kernel_name = lib.lzb_batch_kernel_name(batch).decode()  # the K1 variant the planner picked for this batch
 
     def barrier():
         torch.cuda.synchronize()
@@ -944,7 +946,7 @@ def main():
             "gpu_launches": kernels_per_step * a.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
-                         "kernel": {"rep0": "lzb_decode_fill_kernel", "stored": "lzb_stored_decode_kernel"}.get(CFG["kind"], "lzb_decode_kernel"),
+                         "kernel": kernel_name,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": in_bytes + out_bytes, "kernel_ms": kernel_ms},
             "cpu_baseline": cpu_obj,

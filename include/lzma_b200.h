@@ -185,6 +185,9 @@ int lzb_batch_collect(lzb_batch *batch, void *cuda_stream, uint64_t *out_len, ui
 void lzb_batch_destroy(lzb_batch *batch);
 /* Number of kernels one lzb_batch_launch enqueues (for bench.py's gpu_launches claim). */
 int lzb_batch_kernels_per_launch(const lzb_batch *batch);
+/* Name of the decode kernel lzb_batch_launch runs first for this batch (the variant the planner picked: throughput /
+ * placement-plan / fill / copy / latency form, or the stored-chunk copy kernel); static string.  Measurement aid. */
+const char *lzb_batch_kernel_name(const lzb_batch *batch);
 
 /* ---- device-side sizing and layout (replaces the reference's incremental growth of its output
  * Vec: the sizes the reference learns chunk by chunk in lzma2.rs:128-136, 204-207 / from the .lzma header in

@@ -42,7 +42,7 @@ assert STATUS_DTYPE.itemsize == C.sizeof(Status)
 # every symbol include/lzma_b200.h declares
 EXPORTS = ["lzb_create", "lzb_destroy", "lzb_last_error", "lzb_abi_version", "lzb_scan", "lzb_decode_batch",
            "lzb_decode_batch_device", "lzb_batch_prepare", "lzb_batch_launch", "lzb_batch_collect", "lzb_batch_destroy",
-           "lzb_batch_kernels_per_launch", "lzb_decompress_alloc", "lzb_free", "lzb_crc_device", "lzb_format_error",
+           "lzb_batch_kernels_per_launch", "lzb_batch_kernel_name", "lzb_decompress_alloc", "lzb_free", "lzb_crc_device", "lzb_format_error",
            "lzb_encode_bound", "lzb_encode_batch", "lzb_encode_batch_device",
            "lzb_scan_device", "lzb_batch_prepare_device", "lzb_create_multi", "lzb_destroy_multi", "lzb_multi_device_count",
            "lzb_multi_ctx", "lzb_multi_last_error", "lzb_decode_batch_multi", "lzb_ipc_export", "lzb_ipc_open",
@@ -86,6 +86,8 @@ def bind(path):
     lib.lzb_batch_collect.argtypes = [vp, vp, u64p, u64p, vp]
     lib.lzb_batch_destroy.argtypes = [vp]
     lib.lzb_batch_kernels_per_launch.argtypes = [vp]
+    lib.lzb_batch_kernel_name.argtypes = [vp]
+    lib.lzb_batch_kernel_name.restype = C.c_char_p
     lib.lzb_decompress_alloc.argtypes = [vp, C.c_int, C.POINTER(Options), vp, C.c_size_t, C.POINTER(vp),
                                          C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(Status)]
     lib.lzb_free.argtypes = [vp]

@@ -159,6 +159,13 @@ const k1_t k1_variants[15] = {
     lzb_decode_biglit_kernel,
     lzb_decode_lat_kernel,    lzb_decode_lat_mirror_kernel};  // latency form (few streams per SM): 13 plain, 14 page stores
 
+const char* const k1_names[15] = {
+    "lzb_decode_kernel",        "lzb_decode_fill_kernel",        "lzb_decode_copy_kernel",
+    "lzb_decode_sched_kernel",  "lzb_decode_sched_fill_kernel",  "lzb_decode_sched_copy_kernel",
+    "lzb_decode_drain_kernel",  "lzb_decode_drain_fill_kernel",  "lzb_decode_drain_copy_kernel",
+    "lzb_decode_mirror_kernel", "lzb_decode_mirror_fill_kernel", "lzb_decode_mirror_copy_kernel",
+    "lzb_decode_biglit_kernel", "lzb_decode_lat_kernel",         "lzb_decode_lat_mirror_kernel"};
+
 LaunchCfg decode_config(const lzb_ctx* ctx, uint32_t n, uint32_t lclp) {
     LaunchCfg c;
     c.lclp = lclp;
@@ -292,6 +299,11 @@ void make_plan(const lzb_ctx* ctx, const LzbItem* items, uint32_t n, uint32_t lz
     }
 }
 
+// Index into k1_variants / k1_names of the first launch's kernel.
+int k1_variant(const DecodePlan& p, bool mirror) {
+    return p.lat ? (mirror ? 14 : 13) : (p.host_io ? (mirror ? 9 : 6) : p.n_static ? 3 : 0) + p.wide;
+}
+
 // Enqueues counter resets + K1 launch(es) on `s`.  All pointers are device pointers; d_order holds order_small
 // followed by order_big; d_counter holds two counters.
 int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem* d_items, const uint32_t* d_order,
@@ -322,7 +334,7 @@ int launch_plan(lzb_ctx* ctx, cudaStream_t s, const DecodePlan& p, const LzbItem
         const uint64_t mstride = p.lat ? 0 : lzb_matched_u16(c.lclp);
         if (!p.lat) CUDA_TRY(ctx, matchws.ensure((size_t)c.grid * c.warps * mstride * 2));
         const k1_t* kernels = k1_variants;
-        const int v = p.lat ? (mirror ? 14 : 13) : (p.host_io ? (mirror ? 9 : 6) : p.n_static ? 3 : 0) + p.wide;
+        const int v = k1_variant(p, mirror);
         if (int rc = fire()) return rc;
         kernels[v]<<<c.grid, c.warps * 32, smem, s>>>(d_items, d_order, ns, p.n_static, d_in_base, d_out_base, d_results,
                                                       d_counter, c.lclp, c.warp_bytes, matchws.as<uint16_t>(), mstride, kc,
@@ -423,7 +435,13 @@ int arm_gate_queue(lzb_ctx* ctx, const uint8_t* src, uint64_t lead, uint64_t in_
     CUDA_TRY(ctx, cudaEventRecord(ctx->gate_ready, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->gate_ready, 0));
     const size_t npos = queue.size();
-    const size_t head = std::min<size_t>(npos, 768);
+    // Environments in which a kernel launch blocks the host until the kernel has finished (profilers and
+    // compute-sanitizer inject themselves through CUDA_INJECTION64_PATH; CUDA_LAUNCH_BLOCKING): nothing can be enqueued
+    // behind the launch, so the whole upload goes in front of it.
+    const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
+    const bool blocking_launch = getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_PORT_BASE") ||
+                                 getenv("NV_TPS_LAUNCH_TOKEN") || (lb && lb[0] && lb[0] != '0');
+    const size_t head = blocking_launch ? npos : std::min<size_t>(npos, 768);
     // a watermark update every `step` positions: at most LZB_GATE_MARKS of them
     const size_t step = std::max<size_t>(16, (npos + LZB_GATE_MARKS - 2) / (LZB_GATE_MARKS - 1));
     std::vector<uint32_t> q(queue), t(tail);
@@ -1058,6 +1076,13 @@ extern "C" int lzb_batch_launch(lzb_batch* b, void* cuda_stream) {
 
 extern "C" int lzb_batch_kernels_per_launch(const lzb_batch* b) {
     return b ? (int)!b->plan.order_small.empty() + (int)!b->plan.order_big.empty() + (int)!b->plan.order_stored.empty() : 0;
+}
+
+extern "C" const char* lzb_batch_kernel_name(const lzb_batch* b) {
+    if (!b) return "";
+    if (!b->plan.order_small.empty()) return k1_names[k1_variant(b->plan, false)];
+    if (!b->plan.order_big.empty()) return k1_names[12];
+    return b->plan.order_stored.empty() ? "" : "lzb_stored_decode_kernel";
 }
 
 extern "C" int lzb_batch_collect(lzb_batch* b, void* cuda_stream, uint64_t* out_len, uint64_t* consumed, lzb_status* st) {
