@@ -310,3 +310,54 @@ def test_python_multi_context(ctx):
         assert not got[-1].ok and got[-1].display == "io error: failed to fill whole buffer"
     finally:
         mc.close()
+
+
+def test_kernel_family_selection(ctx, monkeypatch):
+    """Which K1 variant the planner picks (lzb_batch_kernel_name): batches of at most 8 streams per SM run on the latency
+    kernels, LZB_NO_LAT=1 and larger batches on the throughput kernels; all of them bit-exact."""
+    import ctypes as C
+
+    import torch
+
+    import corpus
+    from lzma_rs_b200 import _native
+    lib = _native.load()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    plain = [corpus.mixed_text(7100 + i, 3000 + 17 * i) for i in range(16)]
+    comp = [corpus.raw_lzma2(p, dict_size=1 << 16) for p in plain]
+
+    def run(n, env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        streams = [comp[i % 16] for i in range(n)]
+        blob, in_off = _native.pack_streams(streams)
+        sizes = np.array([len(plain[i % 16]) for i in range(n)], dtype=np.uint64)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum((sizes + np.uint64(15)) // np.uint64(16) * np.uint64(16), out=out_off[1:])
+        d_in = torch.from_numpy(blob).cuda()
+        d_out = torch.zeros(int(out_off[-1]) + 16, dtype=torch.uint8, device="cuda")
+        opt = _native.make_options()
+        batch = C.c_void_p()
+        rc = lib.lzb_batch_prepare(ctx.handle, _native.FMT_LZMA2, C.byref(opt), d_in.data_ptr(), in_off.ctypes.data, n,
+                                   d_out.data_ptr(), out_off.ctypes.data, C.byref(batch))
+        assert rc == 0, (rc, ctx.last_error())
+        name = lib.lzb_batch_kernel_name(batch).decode()
+        assert lib.lzb_batch_launch(batch, None) == 0
+        st = np.zeros(n, dtype=_native.STATUS_DTYPE)
+        ol = np.zeros(n, dtype=np.uint64)
+        cs = np.zeros(n, dtype=np.uint64)
+        assert lib.lzb_batch_collect(batch, None, ol.ctypes.data, cs.ctypes.data, st.ctypes.data) == 0
+        lib.lzb_batch_destroy(batch)
+        for k in env:
+            monkeypatch.delenv(k)
+        assert (st["code"] == 0).all() and (ol == sizes).all()
+        out = d_out.cpu().numpy()
+        for i in (0, 1, n // 2, n - 1):
+            assert out[int(out_off[i]):int(out_off[i]) + int(ol[i])].tobytes() == plain[i % 16], (name, i)
+        return name
+
+    assert run(5, {}) == "lzb_decode_lat_kernel"
+    assert run(8 * sms, {}) == "lzb_decode_lat_kernel"
+    assert run(5, {"LZB_NO_LAT": "1"}) == "lzb_decode_kernel"
+    assert run(8 * sms + 1, {}) == "lzb_decode_kernel"
+    assert run(28 * sms + 300, {}) in ("lzb_decode_kernel", "lzb_decode_sched_kernel")
